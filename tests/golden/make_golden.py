@@ -1,0 +1,258 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference in this container.
+
+    python tests/golden/make_golden.py            # needs /root/reference (build container only)
+
+The reference (/root/reference/2_AlphaOmok: agents.py, utils.py, model.py, env/env_small.py, env/env_regular.py) is
+imported as-is behind a 2-file pygame stub. Its random decisions (np.random.choice / np.random.dirichlet, call sites
+agents.py:97,163,194 and utils.py:192,202) are routed through oracle.omok_oracle.DecisionStream so that the oracle
+and the device can consume the very same decisions. While generating, every fixture is cross-checked against the
+oracle restatement (assertion failure = oracle bug), then written as small .npz files which the CPU tests
+(tests/test_oracle_golden.py) and the GPU tests replay without /root/reference.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("ALPHA_OMOK_REF", "/root/reference/2_AlphaOmok")
+
+from oracle import omok_oracle as O  # noqa: E402
+from oracle import pvnet_ref  # noqa: E402
+
+
+def import_reference():
+    stub = tempfile.mkdtemp(prefix="pygame_stub_")
+    os.makedirs(os.path.join(stub, "pygame"))
+    with open(os.path.join(stub, "pygame", "__init__.py"), "w") as f:
+        f.write("")
+    with open(os.path.join(stub, "pygame", "locals.py"), "w") as f:
+        f.write("QUIT = 12\n")
+    sys.path.insert(0, stub)
+    sys.path.insert(0, REF)
+    import agents, model, utils  # noqa: E401
+    from env import env_regular, env_small
+    agents.PRINT_MCTS = False
+    return types.SimpleNamespace(agents=agents, model=model, utils=utils, env_small=env_small, env_regular=env_regular)
+
+
+# ------------------------------------------------------------------------------------------------ synthetic NN
+def synth_eval(moves, A):
+    """Hash 'network': exact float32 outputs, identical here, in the oracle tests and in csrc (EVAL_SYNTH)."""
+    hh = 0xCBF29CE484222325
+    for m in moves[1:]:
+        hh = ((hh ^ (m + 1)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    lo, hi = hh & 0xFFFFFFFF, hh >> 32
+    pol = np.empty(A, np.float32)
+    for a in range(A):
+        w = O.philox4x32((a, 0, lo, hi), (0x5EED, 0x0A0A))
+        pol[a] = np.float32(((w[0] >> 8) + 1) * 2.0 ** -24)
+    w = O.philox4x32((0xFFFF, 0, lo, hi), (0x5EED, 0x0A0A))
+    val = np.float32((w[1] >> 8) * 2.0 ** -23 - 1.0)
+    return pol, val
+
+
+class StubModel:
+    """nn.Module-like object for agents.ZeroAgent.model (agents.py:173-178)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.cur_leaf = None
+        self.log = []
+
+    def eval(self):
+        return self
+
+    def __call__(self, x):
+        p, v = self.fn(self.cur_leaf, x)
+        self.log.append((self.cur_leaf, np.asarray(p, np.float32), np.float32(v)))
+        return torch.from_numpy(np.asarray(p, np.float32))[None], torch.from_numpy(np.asarray([v], np.float32))
+
+
+class RngPatch:
+    def __init__(self):
+        self.stream = None
+
+    def choice(self, a, size=None, replace=True, p=None):
+        if p is None:
+            return self.stream.choice(int(a))
+        return self.stream.choice_p(np.asarray(p))
+
+    def dirichlet(self, alpha, size=None):
+        return self.stream.dirichlet(len(alpha))
+
+
+PATCH = RngPatch()
+
+
+def ref_self_play(R, B, sims, stream, model_stub, noise, tau_thres, max_moves, inplanes=5):
+    """main.py:132-250 (one episode) driven with the reference's own agents/utils/env objects."""
+    PATCH.stream = stream
+    env_mod = R.env_small if B == 9 else R.env_regular
+    agent = R.agents.ZeroAgent(B, sims, inplanes, noise=noise)
+    agent.model = model_stub
+    orig = agent._expansion_evaluation
+
+    def wrapped(leaf_id, win_index):
+        model_stub.cur_leaf = leaf_id
+        return orig(leaf_id, win_index)
+
+    agent._expansion_evaluation = wrapped
+    env = env_mod.GameState("text")
+    root_id, win_index, t = (0,), 0, 0
+    visits, pis = [], []
+    while win_index == 0 and (max_moves is None or t < max_moves):
+        tau = 1 if t < tau_thres else 0
+        pi = agent.get_pi(root_id, tau)
+        visits.append(agent.visit.astype(np.int64))
+        pis.append(pi.copy())
+        action, action_index = R.utils.get_action(pi)
+        root_id += (int(action_index),)
+        _, _, win_index, _, _ = env.step(action)
+        t += 1
+    return dict(moves=list(root_id[1:]), visits=visits, pis=pis, winner=int(win_index))
+
+
+def gen_mcts_game(R, name, B, sims, seed, game, noise, tau_thres, max_moves, nn_kind, sd=None):
+    A = B * B
+    tape = O.make_gamma_tape(seed, game, A + 2, A, 10 / A)
+    if nn_kind == "synth":
+        fn = lambda leaf, x: synth_eval(leaf, A)  # noqa: E731
+    else:
+        net = R.model.PVNet(pvnet_ref.n_blocks_of(sd), 5, 128, B)
+        net.load_state_dict(sd, strict=False)
+        net.eval()
+
+        def fn(leaf, x):
+            with torch.no_grad():
+                p, v = net(x)
+            return p[0].numpy(), v[0].item()
+    stub = StubModel(fn)
+    ref = ref_self_play(R, B, sims, O.DecisionStream(seed, game, tape), stub, noise, tau_thres, max_moves)
+    # ---- cross-check the oracle restatement on the same decisions and the same NN outputs
+    log = {}
+    for leaf, p, v in stub.log:
+        log[leaf] = (p, v)
+    ora = O.self_play_game(B, sims, lambda mv: log[mv], O.DecisionStream(seed, game, tape), tau_thres=tau_thres,
+                           noise=noise, max_moves=max_moves)
+    assert ora["moves"] == ref["moves"], (name, ora["moves"], ref["moves"])
+    assert ora["winner"] == ref["winner"]
+    for a, b in zip(ora["visits"], ref["visits"]):
+        assert np.array_equal(a, b), name
+    for a, b in zip(ora["pis"], ref["pis"]):
+        assert np.array_equal(a, b), name
+    out = dict(B=B, sims=sims, seed=seed, game=game, noise=int(noise), tau_thres=tau_thres,
+               max_moves=-1 if max_moves is None else max_moves, nn_kind=nn_kind,
+               moves=np.asarray(ref["moves"], np.int32), winner=ref["winner"],
+               visits=np.asarray(ref["visits"], np.int32), gamma_tape=tape[:len(ref["moves"]) + 2])
+    if nn_kind != "synth":  # ship the NN outputs of the non-terminal expansions, in call order
+        keep = [(leaf, p, v) for leaf, p, v in stub.log
+                if R.utils.check_win(R.utils.get_board(leaf, B), 5) == 0]
+        out["nn_policy"] = np.stack([p for _, p, _ in keep])
+        out["nn_value"] = np.asarray([v for _, _, v in keep], np.float32)
+        out["nn_leaf_len"] = np.asarray([len(leaf) for leaf, _, _ in keep], np.int32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {len(ref['moves'])} moves, winner {ref['winner']}, {len(stub.log)} evals  OK (oracle == reference)")
+
+
+def gen_rules(R):
+    rs = np.random.RandomState(1234)
+    out = {}
+    for B in (9, 15):
+        A = B * B
+        boards, wins = [], []
+        for k in range(300):
+            fill = rs.randint(0, A + 1)
+            cells = rs.permutation(A)[:fill]
+            b = np.zeros(A)
+            b[cells] = rs.choice([-1.0, 1.0], size=fill)
+            if k % 3 == 0 and fill:  # plant lines (fives, overlines, both colours)
+                for _ in range(rs.randint(1, 3)):
+                    L = rs.randint(4, 8)
+                    dy, dx = [(0, 1), (1, 0), (1, 1), (1, -1)][rs.randint(4)]
+                    y0, x0 = rs.randint(B), rs.randint(B)
+                    col = rs.choice([-1.0, 1.0])
+                    for i in range(L):
+                        y, x = y0 + i * dy, x0 + i * dx
+                        if 0 <= y < B and 0 <= x < B:
+                            b[y * B + x] = col
+            if k % 10 == 9:  # full boards (draw candidates)
+                b = rs.choice([-1.0, 1.0], size=A)
+            b = b.reshape(B, B)
+            w = R.utils.check_win(b, 5)
+            assert O.check_win(b, 5) == w
+            boards.append(b.astype(np.int8))
+            wins.append(w)
+        out[f"boards{B}"] = np.stack(boards)
+        out[f"wins{B}"] = np.asarray(wins, np.int8)
+        # IDs: states, legal-action order at every stone count
+        ids, states, legal = [], [], []
+        for s in list(range(0, A)) + list(range(A - 20, A)):
+            mv = (0,) + tuple(int(x) for x in rs.permutation(A)[:s])
+            la = R.utils.legal_actions(mv, B)
+            assert O.legal_actions(mv, B) == la, (B, s)
+            st = R.utils.get_state_pt(mv, B, 5)
+            assert np.array_equal(O.get_state_pt(mv, B, 5), st)
+            assert np.array_equal(O.get_board(mv, B), R.utils.get_board(mv, B))
+            assert O.get_turn(mv) == R.utils.get_turn(mv)
+            ids.append(np.asarray(mv + (-1,) * (A + 1 - len(mv)), np.int16))
+            states.append(np.packbits(st.astype(np.uint8).reshape(-1)))
+            legal.append(np.asarray(la + [-1] * (A - len(la)), np.int16))
+        out[f"ids{B}"] = np.stack(ids)
+        out[f"states{B}"] = np.stack(states)
+        out[f"legal{B}"] = np.stack(legal)
+    # numpy pairwise-sum restatement vs ndarray.sum
+    for n in (81, 225):
+        for _ in range(2000):
+            v = (rs.rand(n).astype(np.float32) ** 8).astype(np.float64) * (rs.rand(n) < 0.8)
+            assert O.np_pairwise_sum(v) == v.sum()
+    np.savez_compressed(os.path.join(HERE, "rules.npz"), **out)
+    print("rules.npz OK")
+
+
+def gen_nn(R):
+    rs = np.random.RandomState(7)
+    for B, n_block, jitter, seed, name in ((9, 10, False, 0, "nn_9_init"), (9, 10, True, 1, "nn_9_jitter"),
+                                            (15, 10, False, 0, "nn_15_init"), (9, 2, True, 3, "nn_9_small")):
+        A = B * B
+        sd = pvnet_ref.make_state_dict(seed, n_block, 5, 128, B, bn_jitter=jitter)
+        net = R.model.PVNet(n_block, 5, 128, B)
+        missing = net.load_state_dict(sd, strict=False)
+        assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing
+        net.eval()
+        ids = []
+        for _ in range(24):
+            s = rs.randint(0, min(A, 60))
+            ids.append((0,) + tuple(int(x) for x in rs.permutation(A)[:s]))
+        x = torch.tensor(np.stack([R.utils.get_state_pt(i, B, 5) for i in ids])).float()
+        with torch.no_grad():
+            p, v = net(x)
+        p2, v2 = pvnet_ref.pvnet_forward(sd, x)
+        assert torch.allclose(p, p2, atol=1e-6) and torch.allclose(v, v2, atol=1e-6)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), B=B, n_block=n_block, jitter=int(jitter), seed=seed,
+                            ids=np.stack([np.asarray(i + (-1,) * (A + 1 - len(i)), np.int16) for i in ids]),
+                            p=p.numpy(), v=v.numpy())
+        print(name, "OK  max|p-p_ref|", float((p - p2).abs().max()))
+
+
+def main():
+    R = import_reference()
+    np.random.choice = PATCH.choice
+    np.random.dirichlet = PATCH.dirichlet
+    gen_rules(R)
+    gen_nn(R)
+    gen_mcts_game(R, "mcts_9_synth_s40", 9, 40, seed=11, game=0, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
+    gen_mcts_game(R, "mcts_9_synth_s400", 9, 400, seed=12, game=3, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
+    gen_mcts_game(R, "mcts_9_synth_nonoise", 9, 60, seed=13, game=1, noise=False, tau_thres=0, max_moves=None, nn_kind="synth")
+    gen_mcts_game(R, "mcts_15_synth_s50", 15, 50, seed=14, game=2, noise=True, tau_thres=6, max_moves=40, nn_kind="synth")
+    sd = pvnet_ref.make_state_dict(0, 10, 5, 128, 9)
+    gen_mcts_game(R, "mcts_9_pvnet_s40", 9, 40, seed=15, game=0, noise=True, tau_thres=6, max_moves=None, nn_kind="pvnet", sd=sd)
+
+
+if __name__ == "__main__":
+    main()
