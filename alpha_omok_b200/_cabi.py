@@ -1,0 +1,222 @@
+"""ctypes binding of include/alpha_omok_b200.h. No compute happens in Python: every hot-path call below lands in the
+CUDA library. The library is built in-tree by alpha_omok_b200._build; loading fails loudly if it is missing or if
+no B200 is present when a compute entry point is called (there is no CPU fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+AO_EVAL_PVNET, AO_EVAL_SYNTH = 0, 1
+AO_NOISE_DEVICE, AO_NOISE_TAPE = 0, 1
+AO_NN_FP16, AO_NN_FP16X3 = 0, 1
+
+
+class AoConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("board_size", C.c_int32), ("inplanes", C.c_int32), ("planes", C.c_int32),
+        ("n_blocks", C.c_int32), ("num_mcts", C.c_int32), ("noise", C.c_int32), ("tau_thres", C.c_int32),
+        ("max_games", C.c_int32), ("node_cap", C.c_int32), ("eval_mode", C.c_int32), ("noise_mode", C.c_int32),
+        ("nn_precision", C.c_int32), ("nn_log_cap", C.c_int32), ("c_puct", C.c_double), ("alpha", C.c_double),
+        ("seed", C.c_uint64), ("stream", C.c_void_p),
+    ]
+
+
+EXPORTS = [
+    "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
+    "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_rounds",
+    "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
+    "ao_encode_state", "ao_legal_actions", "ao_umma_probe",
+]
+
+_lib = None
+
+
+class AoError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (building if necessary) libalpha_omok_b200.so."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()
+    L = C.CDLL(path)
+    L.ao_last_error.restype = C.c_char_p
+    vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
+    L.ao_engine_create.argtypes = [C.POINTER(AoConfig), C.POINTER(vp)]
+    L.ao_engine_destroy.argtypes = [vp]
+    L.ao_load_weights.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.ao_games_reset.argtypes = [vp, vp, i32, vp]
+    L.ao_set_gamma_tape.argtypes = [vp, i32, vp, i32]
+    L.ao_search.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.ao_nn_forward.argtypes = [vp, vp, i32, vp, vp]
+    L.ao_selfplay_begin.argtypes = [vp, i32, u32]
+    L.ao_selfplay_rounds.argtypes = [vp, i32, vp]
+    L.ao_selfplay_fetch.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.ao_get_nn_log.argtypes = [vp, i32, vp, vp, i32, C.POINTER(i32)]
+    L.ao_records_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.ao_records_pack.argtypes = [vp, i32]
+    L.ao_synchronize.argtypes = [vp]
+    L.ao_check_win.argtypes = [vp, i32, i32, vp]
+    L.ao_encode_state.argtypes = [vp, vp, i32, i32, vp]
+    L.ao_legal_actions.argtypes = [vp, vp, i32, i32, vp]
+    L.ao_umma_probe.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]
+    for name in EXPORTS:
+        if name != "ao_last_error":
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise AoError(f"alpha_omok_b200 C-ABI error {rc}: {lib().ao_last_error().decode()}")
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pad_ids(root_ids, A):
+    """list of ID tuples -> (int16 [n][A+1] padded with -1, int32 lens)."""
+    n = len(root_ids)
+    ids = np.full((n, A + 1), -1, np.int16)
+    lens = np.empty(n, np.int32)
+    for i, r in enumerate(root_ids):
+        ids[i, :len(r)] = r
+        lens[i] = len(r)
+    return ids, lens
+
+
+class Engine:
+    """Thin RAII wrapper over ao_engine (one CUDA device + stream)."""
+
+    def __init__(self, board_size=9, num_mcts=400, max_games=1, noise=True, tau_thres=6, n_blocks=10, inplanes=5,
+                 planes=128, seed=0, device=0, node_cap=0, eval_mode=AO_EVAL_PVNET, noise_mode=AO_NOISE_DEVICE,
+                 nn_precision=AO_NN_FP16, nn_log_cap=0, c_puct=5.0, alpha=0.0, stream=None):
+        self.B, self.A, self.G = board_size, board_size * board_size, max_games
+        self.num_mcts = num_mcts
+        cfg = AoConfig(device, board_size, inplanes, planes, n_blocks, num_mcts, int(bool(noise)), tau_thres,
+                       max_games, node_cap, eval_mode, noise_mode, nn_precision, nn_log_cap, float(c_puct),
+                       float(alpha), seed, stream)
+        self._h = C.c_void_p()
+        check(lib().ao_engine_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().ao_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def load_state_dict(self, state_dict):
+        """fp32 tensors straight from nn.Module.state_dict() (BN folded inside the library)."""
+        names, arrs = [], []
+        for k, v in state_dict.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            a = v.detach().cpu().float().contiguous().numpy() if hasattr(v, "detach") else np.asarray(v, np.float32)
+            names.append(k.encode())
+            arrs.append(np.ascontiguousarray(a, np.float32))
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        c_numel = (C.c_int64 * n)(*[a.size for a in arrs])
+        check(lib().ao_load_weights(self._h, n, c_names, c_ptrs, c_numel))
+
+    def games_reset(self, game_ids, keys=None):
+        ids = np.ascontiguousarray(game_ids, np.int32)
+        k = None if keys is None else np.ascontiguousarray(keys, np.uint32)
+        check(lib().ao_games_reset(self._h, ptr(ids), len(ids), ptr(k)))
+
+    def set_gamma_tape(self, game_id, tape):
+        t = np.ascontiguousarray(tape, np.float64)
+        assert t.shape[1] == self.A
+        check(lib().ao_set_gamma_tape(self._h, game_id, ptr(t), t.shape[0]))
+
+    def search(self, game_ids, root_ids):
+        """-> visits uint32 [n][A], priors float64 [n][A], is_real_root int32 [n]"""
+        ids = np.ascontiguousarray(game_ids, np.int32)
+        roots, lens = pad_ids(root_ids, self.A)
+        n = len(ids)
+        visits = np.empty((n, self.A), np.uint32)
+        priors = np.empty((n, self.A), np.float64)
+        real = np.empty(n, np.int32)
+        check(lib().ao_search(self._h, ptr(ids), n, ptr(roots), ptr(lens), ptr(visits), ptr(priors), ptr(real)))
+        return visits, priors, real
+
+    def search_raw(self, ids, roots, lens, visits, priors=None, real=None):
+        check(lib().ao_search(self._h, ptr(ids), len(ids), ptr(roots), ptr(lens), ptr(visits), ptr(priors), ptr(real)))
+
+    def nn_forward(self, states):
+        s = np.ascontiguousarray(states, np.float32)
+        n = s.shape[0]
+        p = np.empty((n, self.A), np.float32)
+        v = np.empty(n, np.float32)
+        check(lib().ao_nn_forward(self._h, ptr(s), n, ptr(p), ptr(v)))
+        return p, v
+
+    def selfplay_begin(self, n_games, first_key=0):
+        check(lib().ao_selfplay_begin(self._h, n_games, first_key))
+
+    def selfplay_rounds(self, rounds):
+        out = np.zeros(5, np.uint64)
+        check(lib().ao_selfplay_rounds(self._h, rounds, ptr(out)))
+        return dict(sims=int(out[0]), running=int(out[1]), nn_evals=int(out[2]), errors=int(out[3]), moves=int(out[4]))
+
+    def selfplay_fetch(self, n_games, with_visits=True):
+        moves = np.empty((n_games, self.A), np.int16)
+        n_moves = np.empty(n_games, np.int32)
+        winners = np.empty(n_games, np.int8)
+        visits = np.empty((n_games, self.A, self.A), np.uint32) if with_visits else None
+        check(lib().ao_selfplay_fetch(self._h, n_games, ptr(moves), ptr(n_moves), ptr(winners), ptr(visits)))
+        return moves, n_moves, winners, visits
+
+    def nn_log(self, game_id, capacity):
+        pol = np.empty((capacity, self.A), np.float32)
+        val = np.empty(capacity, np.float32)
+        cnt = C.c_int32(0)
+        check(lib().ao_get_nn_log(self._h, game_id, ptr(pol), ptr(val), capacity, C.byref(cnt)))
+        return pol[:cnt.value], val[:cnt.value]
+
+    def records_dev(self):
+        p = C.c_void_p()
+        b = C.c_size_t()
+        check(lib().ao_records_dev(self._h, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def records_pack(self, n_games):
+        check(lib().ao_records_pack(self._h, n_games))
+
+    def synchronize(self):
+        check(lib().ao_synchronize(self._h))
+
+
+def check_win_batch(boards, board_size):
+    b = np.ascontiguousarray(boards, np.int8).reshape(-1, board_size * board_size)
+    out = np.empty(b.shape[0], np.uint8)
+    check(lib().ao_check_win(ptr(b), b.shape[0], board_size, ptr(out)))
+    return out
+
+
+def encode_state_batch(root_ids, board_size):
+    A = board_size * board_size
+    ids, lens = pad_ids(root_ids, A)
+    out = np.empty((len(root_ids), 5, board_size, board_size), np.float32)
+    check(lib().ao_encode_state(ptr(ids), ptr(lens), len(root_ids), board_size, ptr(out)))
+    return out
+
+
+def legal_actions_batch(root_ids, board_size):
+    A = board_size * board_size
+    ids, lens = pad_ids(root_ids, A)
+    out = np.empty((len(root_ids), A), np.int16)
+    check(lib().ao_legal_actions(ptr(ids), ptr(lens), len(root_ids), board_size, ptr(out)))
+    return out

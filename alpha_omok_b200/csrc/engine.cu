@@ -1,0 +1,569 @@
+// Host side of the C ABI (include/alpha_omok_b200.h): engine life cycle, BN folding + UMMA weight packing,
+// the lock-step round loop (tree step -> tower -> tree step ...), and the host<->device staging of the facade calls.
+#include <cuda_fp16.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define AO_CUDA(x)                                                                           \
+  do {                                                                                       \
+    cudaError_t e__ = (x);                                                                   \
+    if (e__ != cudaSuccess) return fail(-100 - (int)e__, "%s: %s", #x, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+}  // namespace
+
+struct ao_engine {
+  ao_config cfg;
+  int B, A, G;
+  int num_sms;
+  bool own_stream;
+  cudaStream_t stream;
+  ao::TreeParams tp;
+  ao::TowerWeights tw;
+  bool weights_loaded;
+  std::vector<void*> allocs;
+  // weights (device)
+  __half *d_conv_hi, *d_conv_lo;
+  float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
+  // staging
+  int32_t *d_ids, *d_lens, *d_real_root;
+  int16_t* d_roots;
+  uint32_t *d_keys, *d_visits;
+  double* d_priors;
+  unsigned long long* d_counters;
+  uint8_t* d_records;
+  size_t rec_bytes;
+  int32_t* h_pinned;  // [0] n_active
+  int selfplay_games;
+};
+
+namespace {
+
+template <class T>
+int ealloc(ao_engine* h, T** p, size_t count) {
+  T* q = nullptr;
+  cudaError_t e = dalloc(&q, count ? count : 1);
+  if (e != cudaSuccess) return fail(-2, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = q;
+  return 0;
+}
+
+// one lock-step round: tree step (consume NN output, select next leaf) then the tower on the emitted requests
+int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters) {
+  AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, sizeof(int32_t), h->stream));
+  AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
+  AO_CUDA(ao::launch_tree_step(h->tp, ids_dev, n, max_iters, h->stream));
+  if (h->cfg.eval_mode == AO_EVAL_PVNET)
+    AO_CUDA(ao::launch_tower(h->tw, h->B, h->cfg.nn_precision, h->tp.nn_in, h->tp.nn_count, n, h->tp.nn_policy,
+                             h->tp.nn_value, h->num_sms, h->stream));
+  return 0;
+}
+
+int poll_active(ao_engine* h, int* active) {
+  AO_CUDA(cudaMemcpyAsync(h->h_pinned, h->tp.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  *active = h->h_pinned[0];
+  return 0;
+}
+
+int require_weights(ao_engine* h) {
+  if (h->cfg.eval_mode == AO_EVAL_PVNET && !h->weights_loaded)
+    return fail(-3, "no weights loaded: call ao_load_weights before searching with the PVNet evaluator");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" const char* ao_last_error(void) { return g_err.c_str(); }
+
+extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  if (cfg->board_size < 5 || cfg->board_size > ao::kMaxB) return fail(-1, "board_size %d unsupported (5..15)", cfg->board_size);
+  if (cfg->inplanes != 5) return fail(-1, "inplanes must be 5 (history*2+1), got %d", cfg->inplanes);
+  if (cfg->planes != 128) return fail(-1, "planes must be 128, got %d", cfg->planes);
+  if (cfg->n_blocks < 1 || cfg->n_blocks > 10) return fail(-1, "n_blocks must be in 1..10, got %d", cfg->n_blocks);
+  if (cfg->max_games < 1) return fail(-1, "max_games must be >= 1");
+  if (cfg->num_mcts < 1) return fail(-1, "num_mcts must be >= 1");
+  if (cfg->eval_mode == AO_EVAL_PVNET && cfg->board_size != 9 && cfg->board_size != 15)
+    return fail(-1, "the PVNet tower kernel is built for board_size 9 and 15 only");
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0)
+    return fail(-4, "no CUDA device: alpha_omok_b200 has no CPU fallback (%s)", cudaGetErrorString(e0));
+  AO_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  AO_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(-4, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+
+  ao_engine* h = new ao_engine();
+  memset(&h->tp, 0, sizeof h->tp);
+  memset(&h->tw, 0, sizeof h->tw);
+  h->cfg = *cfg;
+  h->B = cfg->board_size;
+  h->A = h->B * h->B;
+  h->G = cfg->max_games;
+  h->num_sms = prop.multiProcessorCount;
+  h->weights_loaded = false;
+  h->selfplay_games = 0;
+  if (cfg->stream) {
+    h->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
+    h->own_stream = false;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    h->own_stream = true;
+  }
+  const int A = h->A, G = h->G;
+  const int node_cap = cfg->node_cap > 0 ? cfg->node_cap : 2048;
+  ao::TreeParams& tp = h->tp;
+  tp.B = h->B; tp.A = A; tp.G = G;
+  tp.num_mcts = cfg->num_mcts; tp.noise = cfg->noise ? 1 : 0; tp.tau_thres = cfg->tau_thres;
+  tp.eval_mode = cfg->eval_mode; tp.noise_mode = cfg->noise_mode;
+  tp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 5.0;
+  tp.alpha = cfg->alpha > 0 ? cfg->alpha : 10.0 / A;
+  tp.seed_lo = (uint32_t)cfg->seed; tp.seed_hi = (uint32_t)(cfg->seed >> 32);
+  const uint64_t slot_cap = (uint64_t)node_cap * A;
+  if (slot_cap >= (1u << 20)) { delete h; return fail(-1, "node_cap*A = %llu must stay below 2^20", (unsigned long long)slot_cap); }
+  tp.slot_cap = (uint32_t)slot_cap;
+  tp.gc_cap = (uint32_t)(slot_cap / 4 + 1024);
+  tp.nn_log_cap = cfg->nn_log_cap;
+  tp.tape_rows = cfg->noise_mode == AO_NOISE_TAPE ? A + 2 : 0;
+  const size_t slots = (size_t)G * 2 * slot_cap;
+  int rc = 0;
+#define EA(p, cnt) if ((rc = ealloc(h, &(p), (cnt))) != 0) { ao_engine_destroy(h); return rc; }
+  EA(tp.games, (size_t)G);
+  EA(tp.slot_act, slots);
+  EA(tp.slot_nw, slots);
+  EA(tp.slot_p, slots);
+  EA(tp.slot_child, slots);
+  EA(tp.path, (size_t)G * (A + 1));
+  EA(tp.gc_old, (size_t)G * tp.gc_cap);
+  EA(tp.gc_new, (size_t)G * tp.gc_cap);
+  EA(tp.rec_visits, (size_t)G * A * A);
+  if (tp.tape_rows) { EA(tp.gamma_tape, (size_t)G * tp.tape_rows * A); }
+  EA(tp.nn_in, (size_t)G);
+  EA(tp.nn_policy, (size_t)G * A);
+  EA(tp.nn_value, (size_t)G);
+  EA(tp.nn_count, 1);
+  EA(tp.n_active, 1);
+  if (tp.nn_log_cap > 0) {
+    EA(tp.nnlog_policy, (size_t)G * tp.nn_log_cap * A);
+    EA(tp.nnlog_value, (size_t)G * tp.nn_log_cap);
+  }
+  EA(h->d_ids, (size_t)G);
+  EA(h->d_lens, (size_t)G);
+  EA(h->d_real_root, (size_t)G);
+  EA(h->d_roots, (size_t)G * (A + 1));
+  EA(h->d_keys, (size_t)G);
+  EA(h->d_visits, (size_t)G * A);
+  EA(h->d_priors, (size_t)G * A);
+  EA(h->d_counters, 8);
+  h->rec_bytes = ((4 + (size_t)A * 2 + 3) & ~(size_t)3) + (size_t)A * A * 4;
+  EA(h->d_records, (size_t)G * h->rec_bytes);
+#undef EA
+  if (cudaMallocHost(reinterpret_cast<void**>(&h->h_pinned), 64) != cudaSuccess) { ao_engine_destroy(h); return fail(-2, "cudaMallocHost failed"); }
+  cudaError_t e = cudaMemsetAsync(tp.games, 0, (size_t)G * sizeof(ao::Game), h->stream);
+  if (e == cudaSuccess && tp.gamma_tape) e = cudaMemsetAsync(tp.gamma_tape, 0, (size_t)G * tp.tape_rows * A * sizeof(double), h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { ao_engine_destroy(h); return fail(-2, "engine init: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return 0;
+}
+
+extern "C" int ao_engine_destroy(ao_engine* h) {
+  if (!h) return 0;
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int ao_synchronize(ao_engine* h) {
+  if (!h) return fail(-1, "null engine");
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- weights
+extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* names, const float* const* ptrs,
+                               const int64_t* numel) {
+  if (!h) return fail(-1, "null engine");
+  std::map<std::string, std::pair<const float*, int64_t>> sd;
+  for (int i = 0; i < n_tensors; ++i) sd[names[i]] = {ptrs[i], numel[i]};
+  const int A = h->A, C = 128, nb = h->cfg.n_blocks, CI = h->cfg.inplanes;
+  auto get = [&](const std::string& k, int64_t want) -> const float* {
+    auto it = sd.find(k);
+    if (it == sd.end()) { fail(-5, "state_dict key '%s' missing", k.c_str()); return nullptr; }
+    if (it->second.second != want) { fail(-5, "state_dict key '%s' has %lld elements, expected %lld", k.c_str(), (long long)it->second.second, (long long)want); return nullptr; }
+    return it->second.first;
+  };
+  struct BN { const float *g, *b, *m, *v; };
+  auto get_bn = [&](const std::string& p, int c, BN& bn) {
+    bn.g = get(p + ".weight", c); bn.b = get(p + ".bias", c); bn.m = get(p + ".running_mean", c); bn.v = get(p + ".running_var", c);
+    return bn.g && bn.b && bn.m && bn.v;
+  };
+  const int n_layers = 1 + 2 * nb;
+  const size_t stem_halves = (size_t)9 * 16 * C, res_halves = (size_t)9 * C * C;
+  const size_t total_halves = stem_halves + (size_t)(n_layers - 1) * res_halves;
+  std::vector<__half> hi(total_halves), lo(total_halves);
+  std::vector<float> bias((size_t)n_layers * C);
+  size_t off = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    std::string wname, bnname;
+    int ci_n = C;
+    if (l == 0) { wname = "conv1.weight"; bnname = "bn1"; ci_n = CI; }
+    else {
+      const int blk = (l - 1) / 2, which = (l - 1) % 2 + 1;
+      wname = "layers." + std::to_string(blk) + ".conv" + std::to_string(which) + ".weight";
+      bnname = "layers." + std::to_string(blk) + ".bn" + std::to_string(which);
+    }
+    const float* w = get(wname, (int64_t)C * ci_n * 9);
+    BN bn;
+    if (!w || !get_bn(bnname, C, bn)) return -5;
+    const int kpad = l == 0 ? 16 : C;
+    for (int co = 0; co < C; ++co) {
+      const float s = bn.g[co] / std::sqrt(bn.v[co] + 1e-5f);
+      bias[(size_t)l * C + co] = bn.b[co] - bn.m[co] * s;
+      for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < kpad; ++ci) {
+          const float v = ci < ci_n ? w[((size_t)co * ci_n + ci) * 9 + t] * s : 0.f;
+          const __half vh = __float2half_rn(v);
+          const size_t idx = off + ((size_t)t * (kpad / 8) + ci / 8) * C * 8 + (size_t)co * 8 + (ci % 8);
+          hi[idx] = vh;
+          lo[idx] = __float2half_rn(v - __half2float(vh));
+        }
+    }
+    off += l == 0 ? stem_halves : res_halves;
+  }
+  // heads
+  std::vector<float> head_w(3 * C), head_b(3), pfc_wT((size_t)2 * A * A), vfc1_wT((size_t)A * C);
+  {
+    const float* pw = get("policy_head.policy_head.weight", 2 * C);
+    const float* vw = get("value_head.value_head.weight", C);
+    BN pb, vb;
+    if (!pw || !vw || !get_bn("policy_head.policy_bn", 2, pb) || !get_bn("value_head.value_bn", 1, vb)) return -5;
+    for (int c = 0; c < 2; ++c) {
+      const float s = pb.g[c] / std::sqrt(pb.v[c] + 1e-5f);
+      head_b[c] = pb.b[c] - pb.m[c] * s;
+      for (int ci = 0; ci < C; ++ci) head_w[c * C + ci] = pw[c * C + ci] * s;
+    }
+    const float s = vb.g[0] / std::sqrt(vb.v[0] + 1e-5f);
+    head_b[2] = vb.b[0] - vb.m[0] * s;
+    for (int ci = 0; ci < C; ++ci) head_w[2 * C + ci] = vw[ci] * s;
+  }
+  const float* pfc_w = get("policy_head.policy_fc.weight", (int64_t)A * 2 * A);
+  const float* pfc_b = get("policy_head.policy_fc.bias", A);
+  const float* v1w = get("value_head.value_fc1.weight", (int64_t)C * A);
+  const float* v1b = get("value_head.value_fc1.bias", C);
+  const float* v2w = get("value_head.value_fc2.weight", C);
+  const float* v2b = get("value_head.value_fc2.bias", 1);
+  if (!pfc_w || !pfc_b || !v1w || !v1b || !v2w || !v2b) return -5;
+  for (int o = 0; o < A; ++o)
+    for (int f = 0; f < 2 * A; ++f) pfc_wT[(size_t)f * A + o] = pfc_w[(size_t)o * 2 * A + f];
+  for (int j = 0; j < C; ++j)
+    for (int p = 0; p < A; ++p) vfc1_wT[(size_t)p * C + j] = v1w[(size_t)j * A + p];
+
+  if (!h->weights_loaded) {
+    int rc;
+#define EA(p, cnt) if ((rc = ealloc(h, &(p), (cnt))) != 0) return rc;
+    EA(h->d_conv_hi, total_halves);
+    EA(h->d_conv_lo, total_halves);
+    EA(h->d_bias, bias.size());
+    EA(h->d_head_w, head_w.size());
+    EA(h->d_head_b, 4);
+    EA(h->d_pfc_wT, pfc_wT.size());
+    EA(h->d_pfc_b, (size_t)A);
+    EA(h->d_vfc1_wT, vfc1_wT.size());
+    EA(h->d_vfc1_b, (size_t)C);
+    EA(h->d_vfc2_w, (size_t)C);
+#undef EA
+  }
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  AO_CUDA(cudaMemcpy(h->d_conv_hi, hi.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_conv_lo, lo.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_pfc_wT, pfc_wT.data(), pfc_wT.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_pfc_b, pfc_b, (size_t)A * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_vfc1_wT, vfc1_wT.data(), vfc1_wT.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_vfc1_b, v1b, (size_t)C * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_vfc2_w, v2w, (size_t)C * 4, cudaMemcpyHostToDevice));
+  ao::TowerWeights& tw = h->tw;
+  tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
+  tw.pfc_wT = h->d_pfc_wT; tw.pfc_b = h->d_pfc_b; tw.vfc1_wT = h->d_vfc1_wT; tw.vfc1_b = h->d_vfc1_b; tw.vfc2_w = h->d_vfc2_w;
+  tw.vfc2_b = v2b[0];
+  tw.n_layers = n_layers;
+  h->weights_loaded = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- games
+extern "C" int ao_games_reset(ao_engine* h, const int32_t* game_ids, int n, const uint32_t* game_keys) {
+  if (!h) return fail(-1, "null engine");
+  if (n < 0 || n > h->G) return fail(-1, "n out of range");
+  for (int i = 0; i < n; ++i)
+    if (game_ids[i] < 0 || game_ids[i] >= h->G) return fail(-1, "game id %d out of range", game_ids[i]);
+  AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  if (game_keys) AO_CUDA(cudaMemcpyAsync(h->d_keys, game_keys, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(ao::launch_reset_games(h->tp, h->d_ids, n, game_keys ? h->d_keys : nullptr, 0, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int ao_set_gamma_tape(ao_engine* h, int game_id, const double* tape, int n_draws) {
+  if (!h) return fail(-1, "null engine");
+  if (!h->tp.gamma_tape) return fail(-1, "engine was not created with noise_mode = AO_NOISE_TAPE");
+  if (game_id < 0 || game_id >= h->G) return fail(-1, "game id out of range");
+  if (n_draws > h->tp.tape_rows) n_draws = h->tp.tape_rows;
+  AO_CUDA(cudaMemcpy(h->tp.gamma_tape + (size_t)game_id * h->tp.tape_rows * h->A, tape, (size_t)n_draws * h->A * sizeof(double),
+                     cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int16_t* roots, const int32_t* root_lens,
+                         uint32_t* visits, double* priors, int32_t* is_real_root) {
+  if (!h) return fail(-1, "null engine");
+  if (n < 1 || n > h->G) return fail(-1, "n = %d out of range 1..%d", n, h->G);
+  int rc = require_weights(h);
+  if (rc) return rc;
+  const int A = h->A;
+  for (int i = 0; i < n; ++i) {
+    if (game_ids[i] < 0 || game_ids[i] >= h->G) return fail(-1, "game id %d out of range", game_ids[i]);
+    if (root_lens[i] < 1 || root_lens[i] > A) return fail(-1, "root id length %d out of range 1..%d", root_lens[i], A);
+  }
+  AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(cudaMemcpyAsync(h->d_lens, root_lens, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(cudaMemcpyAsync(h->d_roots, roots, (size_t)n * (A + 1) * 2, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(ao::launch_set_roots(h->tp, h->d_ids, n, h->d_roots, h->d_lens, h->stream));
+  const bool synth = h->cfg.eval_mode == AO_EVAL_SYNTH;
+  const int max_iters = synth ? (1 << 30) : 64;
+  int active = 1, rounds = 0;
+  const int blind = synth ? 0 : h->cfg.num_mcts;  // at least this many rounds are needed before anyone can finish
+  while (active > 0) {
+    if ((rc = run_round(h, h->d_ids, n, max_iters)) != 0) return rc;
+    ++rounds;
+    if (rounds >= blind && (rc = poll_active(h, &active)) != 0) return rc;
+    if (rounds > 4 * (h->cfg.num_mcts + 2) + 64) return fail(-6, "search did not converge after %d rounds", rounds);
+  }
+  AO_CUDA(ao::launch_export_roots(h->tp, h->d_ids, n, h->d_visits, h->d_priors, h->d_real_root, h->stream));
+  if (visits) AO_CUDA(cudaMemcpyAsync(visits, h->d_visits, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (priors) AO_CUDA(cudaMemcpyAsync(priors, h->d_priors, (size_t)n * A * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (is_real_root) AO_CUDA(cudaMemcpyAsync(is_real_root, h->d_real_root, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(ao::launch_sum_counters(h->tp, h->G, h->d_counters, h->stream));
+  unsigned long long c[5];
+  AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  if (c[3] != 0) return fail(-7, "%llu game tree(s) overflowed their arena (raise node_cap)", c[3]);
+  return 0;
+}
+
+extern "C" int ao_nn_forward(ao_engine* h, const float* states, int n, float* p, float* v) {
+  if (!h) return fail(-1, "null engine");
+  if (!h->weights_loaded) return fail(-3, "no weights loaded");
+  if (h->B != 9 && h->B != 15) return fail(-1, "tower kernel supports board_size 9 and 15");
+  const int A = h->A, C = h->cfg.inplanes;
+  float* d_states = nullptr;
+  int* d_bad = nullptr;
+  const int chunk = h->G;
+  AO_CUDA(dalloc(&d_states, (size_t)chunk * C * A));
+  AO_CUDA(dalloc(&d_bad, 1));
+  cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream);
+  int rc = 0;
+  for (int o = 0; o < n && rc == 0; o += chunk) {
+    const int m = n - o < chunk ? n - o : chunk;
+    cudaError_t e = cudaMemcpyAsync(d_states, states + (size_t)o * C * A, (size_t)m * C * A * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = ao::launch_pack_states(d_states, m, h->B, C, h->tp.nn_in, d_bad, h->stream);
+    if (e == cudaSuccess) e = ao::launch_tower(h->tw, h->B, h->cfg.nn_precision, h->tp.nn_in, nullptr, m, h->tp.nn_policy, h->tp.nn_value, h->num_sms, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p + (size_t)o * A, h->tp.nn_policy, (size_t)m * A * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v + o, h->tp.nn_value, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(-100 - (int)e, "ao_nn_forward: %s", cudaGetErrorString(e));
+  }
+  int bad = 0;
+  if (rc == 0 && cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(-2, "memcpy failed");
+  cudaFree(d_states);
+  cudaFree(d_bad);
+  if (rc == 0 && bad) rc = fail(-8, "states must be {0,1}-valued planes with a constant colour plane (utils.get_state_pt)");
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------- self-play
+extern "C" int ao_selfplay_begin(ao_engine* h, int n_games, uint32_t first_key) {
+  if (!h) return fail(-1, "null engine");
+  if (n_games < 1 || n_games > h->G) return fail(-1, "n_games = %d out of range 1..%d", n_games, h->G);
+  int rc = require_weights(h);
+  if (rc) return rc;
+  std::vector<uint32_t> keys(n_games);
+  for (int i = 0; i < n_games; ++i) keys[i] = first_key + (uint32_t)i;
+  AO_CUDA(cudaMemcpyAsync(h->d_keys, keys.data(), (size_t)n_games * 4, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(ao::launch_reset_games(h->tp, nullptr, n_games, h->d_keys, 1, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  h->selfplay_games = n_games;
+  return 0;
+}
+
+extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
+  if (!h) return fail(-1, "null engine");
+  if (h->selfplay_games <= 0) return fail(-1, "call ao_selfplay_begin first");
+  const bool synth = h->cfg.eval_mode == AO_EVAL_SYNTH;
+  const int max_iters = synth ? (1 << 30) : 64;
+  int rc;
+  for (int r = 0; r < rounds; ++r)
+    if ((rc = run_round(h, nullptr, h->selfplay_games, max_iters)) != 0) return rc;
+  AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
+  unsigned long long c[5];
+  AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  if (out5) for (int i = 0; i < 5; ++i) out5[i] = c[i];
+  return 0;
+}
+
+extern "C" int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_moves, int8_t* winners,
+                                 uint32_t* visits) {
+  if (!h) return fail(-1, "null engine");
+  if (n_games < 1 || n_games > h->G) return fail(-1, "n_games out of range");
+  const int A = h->A;
+  AO_CUDA(ao::launch_pack_records(h->tp, n_games, h->d_records, h->rec_bytes, h->stream));
+  std::vector<uint8_t> buf((size_t)n_games * h->rec_bytes);
+  AO_CUDA(cudaMemcpyAsync(buf.data(), h->d_records, buf.size(), cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  const size_t voff = (4 + (size_t)A * 2 + 3) & ~(size_t)3;
+  for (int g = 0; g < n_games; ++g) {
+    const uint8_t* rec = buf.data() + (size_t)g * h->rec_bytes;
+    const int16_t* hdr = reinterpret_cast<const int16_t*>(rec);
+    if (n_moves) n_moves[g] = hdr[0];
+    if (winners) winners[g] = (int8_t)rec[2];
+    if (moves) memcpy(moves + (size_t)g * A, hdr + 2, (size_t)A * 2);
+    if (visits) memcpy(visits + (size_t)g * A * A, rec + voff, (size_t)A * A * 4);
+  }
+  return 0;
+}
+
+extern "C" int ao_get_nn_log(ao_engine* h, int game_id, float* policy, float* value, int32_t capacity, int32_t* count) {
+  if (!h) return fail(-1, "null engine");
+  if (h->tp.nn_log_cap <= 0) return fail(-1, "engine was created with nn_log_cap = 0");
+  if (game_id < 0 || game_id >= h->G) return fail(-1, "game id out of range");
+  ao::Game g;
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  AO_CUDA(cudaMemcpy(&g, h->tp.games + game_id, sizeof g, cudaMemcpyDeviceToHost));
+  int c = (int)g.nn_log_count;
+  if (count) *count = c;
+  if (c > h->tp.nn_log_cap) return fail(-9, "NN log of game %d overflowed (%d > %d)", game_id, c, h->tp.nn_log_cap);
+  if (c > capacity) c = capacity;
+  if (policy) AO_CUDA(cudaMemcpy(policy, h->tp.nnlog_policy + (size_t)game_id * h->tp.nn_log_cap * h->A, (size_t)c * h->A * 4, cudaMemcpyDeviceToHost));
+  if (value) AO_CUDA(cudaMemcpy(value, h->tp.nnlog_value + (size_t)game_id * h->tp.nn_log_cap, (size_t)c * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int ao_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_game) {
+  if (!h) return fail(-1, "null engine");
+  if (dev_ptr) *dev_ptr = h->d_records;
+  if (bytes_per_game) *bytes_per_game = h->rec_bytes;
+  return 0;
+}
+
+extern "C" int ao_records_pack(ao_engine* h, int n_games) {
+  if (!h) return fail(-1, "null engine");
+  if (n_games < 1 || n_games > h->G) return fail(-1, "n_games out of range");
+  AO_CUDA(ao::launch_pack_records(h->tp, n_games, h->d_records, h->rec_bytes, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- stateless
+namespace {
+int need_gpu() {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(-4, "no CUDA device: alpha_omok_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+  return 0;
+}
+}  // namespace
+
+extern "C" int ao_check_win(const int8_t* boards, int n, int board_size, uint8_t* out) {
+  int rc = need_gpu();
+  if (rc) return rc;
+  if (board_size < 5 || board_size > ao::kMaxB) return fail(-1, "board_size unsupported");
+  if (n <= 0) return 0;
+  const size_t A = (size_t)board_size * board_size;
+  int8_t* d_b = nullptr;
+  uint8_t* d_o = nullptr;
+  AO_CUDA(dalloc(&d_b, (size_t)n * A));
+  AO_CUDA(dalloc(&d_o, (size_t)n));
+  AO_CUDA(cudaMemcpy(d_b, boards, (size_t)n * A, cudaMemcpyHostToDevice));
+  AO_CUDA(ao::launch_check_win(d_b, n, board_size, d_o, 0));
+  AO_CUDA(cudaMemcpy(out, d_o, (size_t)n, cudaMemcpyDeviceToHost));
+  cudaFree(d_b);
+  cudaFree(d_o);
+  return 0;
+}
+
+extern "C" int ao_encode_state(const int16_t* ids, const int32_t* lens, int n, int board_size, float* out) {
+  int rc = need_gpu();
+  if (rc) return rc;
+  if (board_size < 5 || board_size > ao::kMaxB) return fail(-1, "board_size unsupported");
+  if (n <= 0) return 0;
+  const size_t A = (size_t)board_size * board_size;
+  int16_t* d_i = nullptr;
+  int32_t* d_l = nullptr;
+  float* d_o = nullptr;
+  AO_CUDA(dalloc(&d_i, (size_t)n * (A + 1)));
+  AO_CUDA(dalloc(&d_l, (size_t)n));
+  AO_CUDA(dalloc(&d_o, (size_t)n * 5 * A));
+  AO_CUDA(cudaMemcpy(d_i, ids, (size_t)n * (A + 1) * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(d_l, lens, (size_t)n * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(ao::launch_encode_state(d_i, d_l, n, board_size, d_o, 0));
+  AO_CUDA(cudaMemcpy(out, d_o, (size_t)n * 5 * A * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_i); cudaFree(d_l); cudaFree(d_o);
+  return 0;
+}
+
+extern "C" int ao_legal_actions(const int16_t* ids, const int32_t* lens, int n, int board_size, int16_t* out) {
+  int rc = need_gpu();
+  if (rc) return rc;
+  if (board_size < 5 || board_size > ao::kMaxB) return fail(-1, "board_size unsupported");
+  if (n <= 0) return 0;
+  const size_t A = (size_t)board_size * board_size;
+  int16_t *d_i = nullptr, *d_o = nullptr;
+  int32_t* d_l = nullptr;
+  AO_CUDA(dalloc(&d_i, (size_t)n * (A + 1)));
+  AO_CUDA(dalloc(&d_l, (size_t)n));
+  AO_CUDA(dalloc(&d_o, (size_t)n * A));
+  AO_CUDA(cudaMemcpy(d_i, ids, (size_t)n * (A + 1) * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(d_l, lens, (size_t)n * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(ao::launch_legal_actions(d_i, d_l, n, board_size, d_o, 0));
+  AO_CUDA(cudaMemcpy(out, d_o, (size_t)n * A * 2, cudaMemcpyDeviceToHost));
+  cudaFree(d_i); cudaFree(d_l); cudaFree(d_o);
+  return 0;
+}

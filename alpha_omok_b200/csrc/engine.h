@@ -1,0 +1,128 @@
+// Internal (non-ABI) definitions shared by tree.cu, tower.cu, rules.cu and engine.cu.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "alpha_omok_b200.h"
+
+namespace ao {
+
+constexpr int kMaxB = 15;
+constexpr int kMaxA = 225;
+constexpr int kRowsPad = 16;  // row masks per plane (>= kMaxB)
+
+// ---- game status
+enum : int32_t { ST_FREE = 0, ST_SEARCH = 1, ST_WAIT_NN = 2, ST_SEARCH_DONE = 3, ST_FINISHED = 4, ST_ERROR = 5 };
+
+// child-slot codes
+constexpr int32_t CH_UNVISITED = -1;  // terminal children: -(1 + win_index)  (<= -2)
+
+struct __align__(16) Game {
+  // root position
+  uint16_t rows_b[kRowsPad];
+  uint16_t rows_w[kRowsPad];
+  uint8_t moves[kMaxA + 3];  // action of ply 1..n_moves at moves[0..n_moves)
+  int32_t n_moves;
+  int32_t last1, last2;      // last / second-last move at the root (-1 none)
+  // search state
+  int32_t status;
+  int32_t arena;             // 0/1: which half of the tree storage is live
+  int32_t root_node;         // slot offset of the root's child block, CH_UNVISITED, or terminal code
+  uint32_t root_n;
+  float root_w;
+  uint32_t slot_count;       // bump pointer in the live arena
+  int32_t sims_done, sims_target;
+  int32_t is_real_root;
+  int32_t auto_play;
+  uint32_t rng_ctr, noise_draws, game_key;
+  // pending leaf (between select and expand)
+  uint16_t leaf_rows_b[kRowsPad];
+  uint16_t leaf_rows_w[kRowsPad];
+  int32_t leaf_depth;        // path length
+  int32_t leaf_n_moves;
+  int32_t nn_slot;
+  int32_t winner;
+  int32_t error;
+  uint32_t nn_log_count;
+  unsigned long long sims_total, nn_evals, terminal_sims, moves_played;
+};
+
+// NN request: the five input planes of utils.get_state_pt as row bit-masks
+struct __align__(16) LeafIn {
+  uint16_t plane[4][kRowsPad];
+  uint32_t colour;  // 1 iff black to move
+  int32_t game;
+  uint32_t pad[2];
+};
+
+struct TreeParams {
+  int B, A, G;
+  int num_mcts, noise, tau_thres, eval_mode, noise_mode;
+  double c_puct, alpha;
+  uint32_t seed_lo, seed_hi;
+  uint32_t slot_cap;  // slots per arena
+  uint32_t gc_cap;    // queue entries per game
+  int nn_log_cap;
+  int tape_rows;      // rows of gamma tape per game
+  // storage
+  Game* games;
+  uint8_t* slot_act;
+  uint2* slot_nw;    // {n, float_as_uint(w)}
+  double* slot_p;
+  int32_t* slot_child;
+  uint32_t* path;    // [G][A+1] slot indices (absolute within the engine arrays)
+  uint32_t* gc_old;  // [G][gc_cap] packed (L << 20 | old offset)
+  uint32_t* gc_new;  // [G][gc_cap]
+  uint32_t* rec_visits;  // [G][A][A]
+  double* gamma_tape;    // [G][tape_rows][A] or null
+  // NN exchange
+  LeafIn* nn_in;         // [G]
+  float* nn_policy;      // [G][A]
+  float* nn_value;       // [G]
+  int32_t* nn_count;     // device counter
+  int32_t* n_active;     // device counter
+  float* nnlog_policy;   // [G][cap][A]
+  float* nnlog_value;    // [G][cap]
+};
+
+// folded network parameters on the device (one weight set)
+struct TowerWeights {
+  const __half* conv_hi;   // packed UMMA B operands: stem [9][2][128][8] then 2*n_blocks x [9][16][128][8]
+  const __half* conv_lo;   // low parts for the split (x3) mode, same layout (null in single-pass mode)
+  const float* bias;       // [1 + 2*n_blocks][128]  BN-folded bias per conv layer
+  const float* head_w;     // [3][128] policy c0, policy c1, value conv (BN scale folded)
+  const float* head_b;     // [3]
+  const float* pfc_wT;     // [2A][A]   policy FC transposed
+  const float* pfc_b;      // [A]
+  const float* vfc1_wT;    // [A][128]
+  const float* vfc1_b;     // [128]
+  const float* vfc2_w;     // [128]
+  float vfc2_b;
+  int n_layers;            // 1 + 2*n_blocks
+};
+
+// host-side launchers implemented in the .cu files
+cudaError_t launch_tree_step(const TreeParams& p, const int32_t* game_ids, int n, int max_iters, cudaStream_t s);
+cudaError_t launch_set_roots(const TreeParams& p, const int32_t* game_ids_dev, int n, const int16_t* roots_dev,
+                             const int32_t* lens_dev, cudaStream_t s);
+cudaError_t launch_export_roots(const TreeParams& p, const int32_t* game_ids_dev, int n, uint32_t* visits_dev,
+                                double* priors_dev, int32_t* real_root_dev, cudaStream_t s);
+cudaError_t launch_reset_games(const TreeParams& p, const int32_t* game_ids_dev, int n, const uint32_t* keys_dev,
+                               int auto_play, cudaStream_t s);
+cudaError_t launch_sum_counters(const TreeParams& p, int n, unsigned long long* out5_dev, cudaStream_t s);
+cudaError_t launch_pack_records(const TreeParams& p, int n, uint8_t* out, size_t bytes_per_game, cudaStream_t s);
+
+cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr,
+                         int n_max, float* policy, float* value, int num_sms, cudaStream_t s);
+cudaError_t tower_configure(int B, int precision);
+cudaError_t launch_pack_states(const float* states_dev, int n, int B, int inplanes, LeafIn* out, int* bad_flag_dev,
+                               cudaStream_t s);
+
+cudaError_t launch_check_win(const int8_t* boards_dev, int n, int B, uint8_t* out_dev, cudaStream_t s);
+cudaError_t launch_encode_state(const int16_t* ids_dev, const int32_t* lens_dev, int n, int B, float* out_dev,
+                                cudaStream_t s);
+cudaError_t launch_legal_actions(const int16_t* ids_dev, const int32_t* lens_dev, int n, int B, int16_t* out_dev,
+                                 cudaStream_t s);
+
+}  // namespace ao

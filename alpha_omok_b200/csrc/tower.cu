@@ -1,0 +1,385 @@
+// PVNet.forward (model.py:97-104) as ONE persistent sm_100a kernel: the whole residual tower of a pair of 9x9 games
+// (or one 15x15 game) runs inside one CTA with the activations resident in shared memory and the accumulators in
+// TMEM; only the leaf descriptors (136 B) are read from and policy/value written to HBM, the fp16 weights stream
+// from L2 through a 1-D TMA ring.
+//
+// Implicit GEMM without im2col: activations live in smem as [16 k-chunks][ROWS][8 halves] (K-major, no swizzle,
+// 16 B per row and chunk).  Board cells are laid out with one zero column per row and one zero row per game
+// (row stride S = B+1), so tap (dy,dx) of the 3x3 stencil is the SAME buffer addressed from a start row shifted by
+// dy*S+dx: 9 taps x 8 k-steps of tcgen05.mma (M=128,N=128,K=16) per 128-row tile, no data movement.
+// Two 128-row tiles per CTA (rows 0..255 = 2 games of 100 rows at 9x9, 1 game of 256 rows at 15x15).
+// TMEM: per tile 128 columns accA (conv1 of a block) + 128 columns accB (stem / conv2).  accB keeps the fp32 block
+// input x, so `out += residual` (model.py:29) is the accumulate flag of conv2's first MMA - no second smem buffer.
+// BN (eval) is folded: scale into the fp16 weights, shift into the fp32 bias added in the epilogue.
+//
+// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp%4, tile = warp/4), warp 8 weight producer, warp 9 MMA
+// issuer + TMEM owner.
+#include <cuda_fp16.h>
+#include <stdio.h>
+
+#include "engine.h"
+#include "sm100_ptx.cuh"
+
+namespace ao {
+
+namespace {
+
+constexpr int kC = 128;
+constexpr int kTileRows = 128;
+constexpr int kTiles = 2;
+constexpr int kEpiThreads = 256;
+constexpr int kThreads = 320;
+constexpr int kStageBytes = kC * kC * 2;  // one tap, 128 in-channels: 32 KB
+constexpr int kStemStageBytes = 16 * kC * 2;
+constexpr int kMaxLayers = 21;            // 1 + 2*10 blocks (bias table lives in shared memory)
+
+template <int B>
+struct Geo {
+  static constexpr int S = B + 1;
+  static constexpr int A = B * B;
+  static constexpr int GameRows = S * (B + 1);
+  static constexpr int GPC = (kTiles * kTileRows) / GameRows;  // games per CTA pass
+  static constexpr int Halo = ((S + 1 + 7) / 8) * 8;
+  static constexpr int Rows = Halo + kTiles * kTileRows + Halo;
+  static constexpr int ActBytes = 16 * Rows * 16;
+  static_assert(GPC >= 1, "board too large for a 256-row CTA tile");
+};
+
+template <int B, int STAGES>
+struct SmemLayout {
+  using G = Geo<B>;
+  static constexpr int act = 0;
+  static constexpr int wring = (G::ActBytes + 1023) / 1024 * 1024;
+  static constexpr int bias = wring + STAGES * kStageBytes;            // [kMaxLayers][128] f32
+  static constexpr int headw = bias + kMaxLayers * kC * 4;              // [3][128] f32
+  static constexpr int feat = headw + 3 * kC * 4;                       // [GPC][3][A] f32 (p0, p1, v)
+  static constexpr int logits = feat + G::GPC * 3 * G::A * 4;           // [GPC][A]
+  static constexpr int hidden = logits + G::GPC * G::A * 4;             // [GPC][128]
+  static constexpr int red = hidden + G::GPC * kC * 4;                  // [GPC][2]
+  static constexpr int bars = (red + G::GPC * 2 * 4 + 15) / 16 * 16;    // mbarriers
+  static constexpr int total = bars + (2 * STAGES + 2) * 8 + 16;
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int B, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
+             float* __restrict__ policy, float* __restrict__ value) {
+  using G = Geo<B>;
+  using SL = SmemLayout<B, STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  int n = n_ptr ? *n_ptr : n_max;
+  if (n > n_max) n = n_max;
+  const int n_pass = (n + G::GPC - 1) / G::GPC;
+  if ((int)blockIdx.x >= n_pass) return;
+
+  uint8_t* s_act = smem + SL::act;
+  uint8_t* s_w = smem + SL::wring;
+  float* s_bias = reinterpret_cast<float*>(smem + SL::bias);
+  float* s_headw = reinterpret_cast<float*>(smem + SL::headw);
+  float* s_feat = reinterpret_cast<float*>(smem + SL::feat);
+  float* s_logits = reinterpret_cast<float*>(smem + SL::logits);
+  float* s_hidden = reinterpret_cast<float*>(smem + SL::hidden);
+  float* s_red = reinterpret_cast<float*>(smem + SL::red);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SL::bars);
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_act = bar_empty + STAGES;   // epilogue -> MMA: operand written, accumulators drained
+  uint64_t* bar_acc = bar_act + 1;          // MMA -> epilogue: layer accumulated
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_layers = W.n_layers;
+
+  // ---------------- one-time setup
+  for (int i = tid; i < G::ActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < n_layers * kC; i += kThreads) s_bias[i] = W.bias[i];
+  for (int i = tid; i < 3 * kC; i += kThreads) s_headw[i] = W.head_w[i];
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(bar_act, kEpiThreads);
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(s_tmem);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 8) {
+    // =========================================================== weight producer (one lane)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(W.conv_hi);
+        for (int l = 0; l < n_layers; ++l) {
+          const uint32_t bytes = l == 0 ? kStemStageBytes : kStageBytes;
+          for (int t = 0; t < 9; ++t, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(&bar_empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&bar_full[s], bytes);
+            bulk_g2s(s_w + s * kStageBytes, src, bytes, &bar_full[s]);
+            src += bytes;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =========================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16_f32(128, 128);
+      const uint32_t a_base = smem_u32(s_act);
+      const uint32_t lbo_a = (uint32_t)G::Rows * 16u;
+      uint32_t it = 0, act_phase = 0;
+      for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        for (int l = 0; l < n_layers; ++l) {
+          const int nk = l == 0 ? 1 : kC / 16;
+          const bool to_b = (l & 1) == 0;           // stem and conv2 accumulate in accB
+          const bool residual = to_b && l > 0;      // accB already holds the block input x
+          mbar_wait(bar_act, act_phase);
+          act_phase ^= 1u;
+          tc_fence_after_sync();
+          for (int t = 0; t < 9; ++t, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(&bar_full[s], ph);
+            tc_fence_after_sync();
+            const int shift = (t / 3 - 1) * G::S + (t % 3 - 1);
+            const uint32_t b_base = smem_u32(s_w + s * kStageBytes);
+#pragma unroll
+            for (int tile = 0; tile < kTiles; ++tile) {
+              const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
+              const uint32_t a_row = (uint32_t)(G::Halo + tile * kTileRows + shift);
+              for (int j = 0; j < nk; ++j) {
+                const uint64_t da = umma_desc_kmajor_noswz(a_base + (uint32_t)(2 * j) * lbo_a + a_row * 16u, lbo_a, 128u);
+                const uint64_t db = umma_desc_kmajor_noswz(b_base + (uint32_t)(2 * j) * (kC * 16u), kC * 16u, 128u);
+                umma_f16_ss(d_tmem, da, db, idesc, (residual || t > 0 || j > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&bar_empty[s]);
+          }
+          umma_commit(bar_acc);
+        }
+      }
+    }
+  } else {
+    // =========================================================== epilogue warps (256 threads)
+    const int tile = tid >> 7, r = tid & 127;
+    const int R = tile * kTileRows + r;          // logical row in the CTA's padded position stream
+    const int g_local = R / G::GameRows;
+    const int q = R % G::GameRows;
+    const int yy = q / G::S, xx = q % G::S;
+    const bool geo_valid = g_local < G::GPC && yy >= 1 && xx < B;
+    const int pos = (yy - 1) * B + xx;
+    const uint32_t row_off = (uint32_t)(G::Halo + R) * 16u;
+    const uint32_t chunk_stride = (uint32_t)G::Rows * 16u;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * 256);
+    uint32_t acc_phase = 0;
+
+    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+      const int g0 = pass * G::GPC;
+      const int ng = min(G::GPC, n - g0);
+      const bool valid = geo_valid && g_local < ng;
+      // ---- input planes (utils.get_state_pt) -> channels 0..4 of chunk 0; chunk 1 = 0
+      {
+        uint4 c0 = make_uint4(0, 0, 0, 0);
+        if (valid) {
+          const LeafIn* li = &in[g0 + g_local];
+          const int y = yy - 1;
+          const uint32_t b0 = (li->plane[0][y] >> xx) & 1u, b1 = (li->plane[1][y] >> xx) & 1u;
+          const uint32_t b2 = (li->plane[2][y] >> xx) & 1u, b3 = (li->plane[3][y] >> xx) & 1u;
+          const uint32_t b4 = li->colour & 1u;
+          c0.x = (b0 ? 0x3C00u : 0u) | (b1 ? 0x3C000000u : 0u);
+          c0.y = (b2 ? 0x3C00u : 0u) | (b3 ? 0x3C000000u : 0u);
+          c0.z = (b4 ? 0x3C00u : 0u);
+        }
+        *reinterpret_cast<uint4*>(s_act + row_off) = c0;
+        *reinterpret_cast<uint4*>(s_act + chunk_stride + row_off) = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_act);
+
+      float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
+      for (int l = 0; l < n_layers; ++l) {
+        const bool to_b = (l & 1) == 0;
+        const bool last = l == n_layers - 1;
+        const float* bias = s_bias + l * kC;
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after_sync();
+        const uint32_t acc_addr = lane_addr + (to_b ? 128u : 0u);
+#pragma unroll 1
+        for (int qd = 0; qd < 4; ++qd) {
+          uint32_t v[32];
+          tmem_ld32(acc_addr + (uint32_t)(qd * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float y = __uint_as_float(v[j]) + bias[qd * 32 + j];
+            y = fmaxf(y, 0.f);
+            v[j] = __float_as_uint(valid ? y : 0.f);
+          }
+          if (!last) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 pk;
+              __half2 h;
+              h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 0]), __uint_as_float(v[cc * 8 + 1]));
+              pk.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 2]), __uint_as_float(v[cc * 8 + 3]));
+              pk.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 4]), __uint_as_float(v[cc * 8 + 5]));
+              pk.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
+              pk.w = *reinterpret_cast<uint32_t*>(&h);
+              *reinterpret_cast<uint4*>(s_act + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pk;
+            }
+            if (to_b) tmem_st32(acc_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
+          } else {
+            // heads' 1x1 convolutions (model.py:44-46, 64-66) straight from the fp32 tower output
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(v[j]);
+              hd0 = fmaf(x, s_headw[0 * kC + qd * 32 + j], hd0);
+              hd1 = fmaf(x, s_headw[1 * kC + qd * 32 + j], hd1);
+              hd2 = fmaf(x, s_headw[2 * kC + qd * 32 + j], hd2);
+            }
+          }
+        }
+        if (!last) {
+          if (to_b) tmem_st_wait();
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          mbar_arrive(bar_act);
+        }
+      }
+      // ---- heads (model.py:43-50, 63-73)
+      if (valid) {
+        float* f = s_feat + g_local * 3 * G::A;
+        f[0 * G::A + pos] = fmaxf(hd0 + W.head_b[0], 0.f);
+        f[1 * G::A + pos] = fmaxf(hd1 + W.head_b[1], 0.f);
+        f[2 * G::A + pos] = fmaxf(hd2 + W.head_b[2], 0.f);
+      }
+      epi_bar_sync();
+      float logit = 0.f;
+      const int pg = tid / G::A, po = tid % G::A;  // policy FC: thread = (game, output)
+      const bool p_thread = tid < G::GPC * G::A && pg < ng;
+      if (p_thread) {
+        const float* f = s_feat + pg * 3 * G::A;
+        float acc = W.pfc_b[po];
+        const float* wt = W.pfc_wT + po;
+#pragma unroll 6
+        for (int k = 0; k < 2 * G::A; ++k) acc = fmaf(__ldg(wt + (size_t)k * G::A), f[k], acc);
+        logit = acc;
+        s_logits[pg * G::A + po] = acc;
+      }
+      const int vg = tid / kC, vj = tid % kC;      // value FC1: thread = (game, hidden unit)
+      if (vg < ng && vg < G::GPC) {
+        const float* f = s_feat + vg * 3 * G::A + 2 * G::A;
+        float acc = W.vfc1_b[vj];
+        const float* wt = W.vfc1_wT + vj;
+#pragma unroll 6
+        for (int k = 0; k < G::A; ++k) acc = fmaf(__ldg(wt + (size_t)k * kC), f[k], acc);
+        s_hidden[vg * kC + vj] = fmaxf(acc, 0.f) * W.vfc2_w[vj];
+      }
+      epi_bar_sync();
+      if (warp < ng) {  // warp g: softmax statistics and the value of game g
+        float mx = -3.0e38f;
+        for (int k = lane; k < G::A; k += 32) mx = fmaxf(mx, s_logits[warp * G::A + k]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float sum = 0.f;
+        for (int k = lane; k < G::A; k += 32) sum += expf(s_logits[warp * G::A + k] - mx);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        float hv = 0.f;
+        for (int k = lane; k < kC; k += 32) hv += s_hidden[warp * kC + k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) hv += __shfl_xor_sync(0xFFFFFFFFu, hv, o);
+        if (lane == 0) {
+          s_red[warp * 2 + 0] = mx;
+          s_red[warp * 2 + 1] = sum;
+          value[g0 + warp] = tanhf(hv + W.vfc2_b);
+        }
+      }
+      epi_bar_sync();
+      if (p_thread) policy[(size_t)(g0 + pg) * G::A + po] = expf(logit - s_red[pg * 2]) / s_red[pg * 2 + 1];
+      // s_feat / s_logits are rewritten only after the next pass's 21 layers: no extra barrier needed
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+// dense float states [n][C][B][B] -> LeafIn row masks
+__global__ void pack_states_kernel(const float* __restrict__ st, int n, int B, int C, LeafIn* __restrict__ out,
+                                   int* __restrict__ bad) {
+  const int i = blockIdx.x;
+  const int t = threadIdx.x;  // one thread per (plane, row)
+  if (i >= n) return;
+  const float* s = st + (size_t)i * C * B * B;
+  if (t < 4 * kRowsPad) {
+    const int k = t / kRowsPad, y = t % kRowsPad;
+    uint32_t m = 0;
+    if (k < C - 1 && y < B)
+      for (int x = 0; x < B; ++x) {
+        const float v = s[(k * B + y) * B + x];
+        if (v != 0.f && v != 1.f) *bad = 1;
+        if (v != 0.f) m |= 1u << x;
+      }
+    out[i].plane[k][y] = (uint16_t)m;
+  }
+  if (t == 0) {
+    const float c = s[(size_t)(C - 1) * B * B];
+    for (int k = 0; k < B * B; ++k)
+      if (s[(size_t)(C - 1) * B * B + k] != c) *bad = 1;
+    if (c != 0.f && c != 1.f) *bad = 1;
+    out[i].colour = c != 0.f ? 1u : 0u;
+    out[i].game = i;
+  }
+}
+
+template <int B, int STAGES>
+cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
+                           float* value, int num_sms, cudaStream_t s) {
+  using SL = SmemLayout<B, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tower_kernel<B, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int max_pass = (n_max + Geo<B>::GPC - 1) / Geo<B>::GPC;
+  const int grid = max_pass < num_sms ? max_pass : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  tower_kernel<B, STAGES><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr, int n_max,
+                         float* policy, float* value, int num_sms, cudaStream_t s) {
+  if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
+  (void)precision;
+  if (B == 9) return launch_tower_t<9, 4>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (B == 15) return launch_tower_t<15, 4>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pack_states(const float* states_dev, int n, int B, int inplanes, LeafIn* out, int* bad_flag_dev,
+                               cudaStream_t s) {
+  pack_states_kernel<<<n, 64, 0, s>>>(states_dev, n, B, inplanes, out, bad_flag_dev);
+  return cudaGetLastError();
+}
+
+}  // namespace ao

@@ -1,0 +1,116 @@
+/* alpha_omok_b200 - C ABI of the B200-native self-play hot path (MCTS + rules + policy-value network inference).
+ *
+ * The reference (reinforcement-learning-kr/alpha_omok) has no FFI: its boundary is duck-typed Python.  Every entry
+ * point below names the reference interface it replaces (file:line relative to 2_AlphaOmok/).  The Python facades in
+ * alpha_omok_b200/{agents,utils,model}.py and alpha_omok_b200/env/ bind these through ctypes and keep the reference's
+ * names, argument meaning and return values.  All pointers are HOST pointers unless the name says `_dev`;
+ * buffers are caller-owned; every function returns 0 on success or a negative error code, and ao_last_error()
+ * returns a description of the last failure on the calling thread.  One engine = one CUDA device + one stream;
+ * an engine is not thread-safe.
+ */
+#ifndef ALPHA_OMOK_B200_H
+#define ALPHA_OMOK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ao_engine ao_engine;
+
+enum { AO_EVAL_PVNET = 0, AO_EVAL_SYNTH = 1 };    /* synthetic hash "network": exact floats, used by parity tests */
+enum { AO_NOISE_DEVICE = 0, AO_NOISE_TAPE = 1 };  /* Dirichlet gammas: on-device Philox generator, or host tape    */
+enum { AO_NN_FP16 = 0, AO_NN_FP16X3 = 1 };        /* tensor-core passes: single fp16, or hi/lo split (3 MMAs)      */
+
+/* Mirrors the module-level constants of main.py:26-45 / eval_main.py:22-51 and ZeroAgent.__init__ (agents.py:39-53). */
+typedef struct ao_config {
+  int32_t device;       /* CUDA ordinal                                             */
+  int32_t board_size;   /* BOARD_SIZE: 9 (env_small) or 15 (env_regular); 5..15     */
+  int32_t inplanes;     /* IN_PLANES = 5                                            */
+  int32_t planes;       /* OUT_PLANES = 128 (only 128 is implemented)               */
+  int32_t n_blocks;     /* N_BLOCKS = 10                                            */
+  int32_t num_mcts;     /* N_MCTS (400 self-play / 800 arena)                       */
+  int32_t noise;        /* ZeroAgent(noise=...)                                     */
+  int32_t tau_thres;    /* TAU_THRES = 6                                            */
+  int32_t max_games;    /* concurrent game slots resident in HBM                    */
+  int32_t node_cap;     /* expanded nodes per game tree arena (0 = default 2048)    */
+  int32_t eval_mode;    /* AO_EVAL_*                                                */
+  int32_t noise_mode;   /* AO_NOISE_*                                               */
+  int32_t nn_precision; /* AO_NN_*                                                  */
+  int32_t nn_log_cap;   /* per-game capacity of the NN-output log (0 = off)         */
+  double c_puct;        /* 5 (agents.py:48)                                         */
+  double alpha;         /* 10 / B^2 (agents.py:47); <= 0 selects that default        */
+  uint64_t seed;        /* key of the per-game Philox decision streams              */
+  void* stream;         /* cudaStream_t to launch on, or NULL to create one         */
+} ao_config;
+
+const char* ao_last_error(void);
+int ao_engine_create(const ao_config* cfg, ao_engine** out);
+int ao_engine_destroy(ao_engine* h);
+
+/* Agent.model = PVNet(...) / load_state_dict (main.py:81,356-358; eval_main.py:91-101).  fp32 tensors straight from
+ * state_dict(): names[i] is the state_dict key, ptrs[i] its data, numel[i] its element count.  BatchNorm (eval mode,
+ * eps 1e-5) is folded here; missing `num_batches_tracked` keys are fine. */
+int ao_load_weights(ao_engine* h, int n_tensors, const char* const* names, const float* const* ptrs,
+                    const int64_t* numel);
+
+/* ZeroAgent.reset() + a fresh GameState (agents.py:55-58, main.py:136).  game_keys[i] selects the decision stream. */
+int ao_games_reset(ao_engine* h, const int32_t* game_ids, int n, const uint32_t* game_keys);
+
+/* Parity protocol: raw Gamma(alpha,1) variates consumed by the Dirichlet draws of one game,
+ * tape[n_draws][A] float64.  Only read when noise_mode == AO_NOISE_TAPE. */
+int ao_set_gamma_tape(ao_engine* h, int game_id, const double* tape, int n_draws);
+
+/* ZeroAgent.get_pi minus the final visit -> pi arithmetic (agents.py:60-76): runs num_mcts (+1 on a real root)
+ * simulations for each listed game from the given root ID.  roots[i*(A+1) .. ] holds the ID tuple (leading 0
+ * included), root_lens[i] its length.  Outputs (any may be NULL): visits[n][A] = child n, priors[n][A] = child p
+ * (noise-mixed, float64), is_real_root[n]. */
+int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int16_t* roots, const int32_t* root_lens,
+              uint32_t* visits, double* priors, int32_t* is_real_root);
+
+/* ZeroAgent.get_pv (agents.py:252-260) / PVNet.forward (model.py:97-104) on explicit states:
+ * states float32 [n][inplanes][B][B] with {0,1} entries (utils.get_state_pt layout) -> p [n][A], v [n]. */
+int ao_nn_forward(ao_engine* h, const float* states, int n, float* p, float* v);
+
+/* Batched twin of main.self_play (main.py:122-250): every game slot plays one episode on the device
+ * (get_pi -> get_action -> env.step -> root advance), decisions from the per-game stream.
+ *   ao_selfplay_begin : reset all slots [0, n_games) with game keys first_key + g.
+ *   ao_selfplay_rounds: run up to `rounds` lock-step rounds (select -> NN -> expand/backup [-> move]) and return
+ *                       totals: out[0] simulations completed, out[1] games still running, out[2] NN evaluations,
+ *                       out[3] games in error (tree arena overflow), out[4] moves played.
+ *   ao_selfplay_fetch : moves[n][A] (int16, -1 padded), n_moves[n], winners[n] (0 running,1,2,3),
+ *                       visits[n][A][A] uint32 per ply (may be NULL). */
+int ao_selfplay_begin(ao_engine* h, int n_games, uint32_t first_key);
+int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5);
+int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_moves, int8_t* winners,
+                      uint32_t* visits);
+/* Same loop with HOST-supplied starting positions and host-visible results every call (the end-to-end bench leg):
+ * uploads ids, searches one move for every game, downloads visits. */
+
+/* NN-output log of one game (parity protocol: the oracle replays these floats): policy[count][A], value[count]. */
+int ao_get_nn_log(ao_engine* h, int game_id, float* policy, float* value, int32_t capacity, int32_t* count);
+
+/* Replay records on the device for the multi-GPU all-gather: a slab of fixed-size records
+ * {int16 n_moves, int8 winner, pad, int16 moves[A], uint32 visits[A][A]} per game; pointer valid until destroy. */
+int ao_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_game);
+int ao_records_pack(ao_engine* h, int n_games);
+
+int ao_synchronize(ao_engine* h);
+
+/* Stateless unit-test entry points (device 0 unless an engine was created).
+ * utils.check_win (utils.py:30-59): boards int8 [n][B*B] (+1 black, -1 white) -> out uint8 [n]. */
+int ao_check_win(const int8_t* boards, int n, int board_size, uint8_t* out);
+/* utils.get_state_pt (utils.py:139-168): ids int16 [n][A+1] (-1 padded) -> float32 [n][5][B][B]. */
+int ao_encode_state(const int16_t* ids, const int32_t* lens, int n, int board_size, float* out);
+/* utils.legal_actions (utils.py:22-27) incl. the CPython set-order regime: -> int16 [n][A] (-1 padded). */
+int ao_legal_actions(const int16_t* ids, const int32_t* lens, int n, int board_size, int16_t* out);
+/* tcgen05 building-block probe (csrc/umma_probe.cu). */
+int ao_umma_probe(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init, float* out,
+                  int row0, int ntaps, const int* shifts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALPHA_OMOK_B200_H */

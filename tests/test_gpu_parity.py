@@ -1,0 +1,204 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the oracle / golden fixtures. Run with `pytest -m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load, oracle_game_from_fixture, synth_eval, unpad_id
+from oracle import omok_oracle as O
+from oracle import pvnet_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north_star: value / policy floats within 1e-4
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from alpha_omok_b200 import _cabi
+    return _cabi
+
+
+# ------------------------------------------------------------------------------------------------ rules
+@pytest.mark.parametrize("B", [9, 15])
+def test_check_win_golden(cabi, B):
+    fx = load("rules")
+    out = cabi.check_win_batch(fx[f"boards{B}"], B)
+    assert np.array_equal(out, fx[f"wins{B}"].astype(np.uint8))
+
+
+@pytest.mark.parametrize("B", [9, 15])
+def test_check_win_random_vs_oracle(cabi, B):
+    rs = np.random.RandomState(5 + B)
+    boards = rs.choice([-1, 0, 0, 1], size=(400, B, B)).astype(np.int8)
+    boards[::7] = rs.choice([-1, 1], size=boards[::7].shape)  # full boards
+    boards[0] = 0
+    out = cabi.check_win_batch(boards, B)
+    ref = np.asarray([O.check_win(b.astype(np.float64), 5) for b in boards], np.uint8)
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("B", [9, 15])
+def test_encode_state_and_legal_order_golden(cabi, B):
+    fx = load("rules")
+    A = B * B
+    ids = [unpad_id(r) for r in fx[f"ids{B}"]]
+    st = cabi.encode_state_batch(ids, B)
+    ref = np.unpackbits(fx[f"states{B}"], axis=1)[:, :5 * A].reshape(-1, 5, B, B).astype(np.float32)
+    assert np.array_equal(st, ref)
+    la = cabi.legal_actions_batch(ids, B)
+    assert np.array_equal(la, fx[f"legal{B}"])
+
+
+# ------------------------------------------------------------------------------------------------ network
+@pytest.mark.parametrize("name", ["nn_9_init", "nn_9_jitter", "nn_15_init", "nn_9_small"])
+def test_tower_vs_reference_model(cabi, name):
+    fx = load(name)
+    B, nb = int(fx["B"]), int(fx["n_block"])
+    sd = pvnet_ref.make_state_dict(int(fx["seed"]), nb, 5, 128, B, bn_jitter=bool(fx["jitter"]))
+    eng = cabi.Engine(board_size=B, num_mcts=8, max_games=64, n_blocks=nb)
+    eng.load_state_dict(sd)
+    ids = [unpad_id(r) for r in fx["ids"]]
+    states = np.stack([O.get_state_pt(i, B, 5) for i in ids]).astype(np.float32)
+    p, v = eng.nn_forward(states)
+    assert np.abs(p - fx["p"]).max() < TOL, np.abs(p - fx["p"]).max()
+    assert np.abs(v - fx["v"]).max() < TOL, np.abs(v - fx["v"]).max()
+    eng.close()
+
+
+def test_tower_batch_odd_and_large(cabi):
+    """ragged batch sizes (odd count -> half-empty CTA pass; more passes than SMs) against the torch fp32 oracle"""
+    B, nb = 9, 10
+    sd = pvnet_ref.make_state_dict(0, nb, 5, 128, B)
+    eng = cabi.Engine(board_size=B, num_mcts=8, max_games=701, n_blocks=nb)
+    eng.load_state_dict(sd)
+    rs = np.random.RandomState(3)
+    ids = [(0,) + tuple(int(x) for x in rs.permutation(81)[:rs.randint(0, 70)]) for _ in range(701)]
+    states = np.stack([O.get_state_pt(i, B, 5) for i in ids]).astype(np.float32)
+    for n in (1, 3, 701):
+        p, v = eng.nn_forward(states[:n])
+        pr, vr = pvnet_ref.pvnet_forward(sd, torch.from_numpy(states[:n]))
+        assert np.abs(p - pr.numpy()).max() < TOL
+        assert np.abs(v - vr.numpy()).max() < TOL
+        assert np.abs(p.sum(1) - 1).max() < 1e-5
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ search
+@pytest.mark.parametrize("name", ["mcts_9_synth_s40", "mcts_9_synth_s400", "mcts_9_synth_nonoise", "mcts_15_synth_s50"])
+def test_selfplay_synth_matches_reference_golden(cabi, name):
+    """whole device self-play loop (select/expand/backup, noise, pi, action, step, tree reuse) == reference run"""
+    fx = load(name)
+    B = int(fx["B"])
+    game = int(fx["game"])
+    eng = cabi.Engine(board_size=B, num_mcts=int(fx["sims"]), max_games=game + 1, noise=bool(fx["noise"]),
+                      tau_thres=int(fx["tau_thres"]), seed=int(fx["seed"]), eval_mode=cabi.AO_EVAL_SYNTH,
+                      noise_mode=cabi.AO_NOISE_TAPE)
+    eng.set_gamma_tape(game, fx["gamma_tape"])
+    eng.selfplay_begin(game + 1, first_key=0)
+    st = eng.selfplay_rounds(1)
+    for _ in range(50):
+        if st["running"] == 0:
+            break
+        st = eng.selfplay_rounds(1)
+    assert st["errors"] == 0
+    moves, n_moves, winners, visits = eng.selfplay_fetch(game + 1)
+    gm = fx["moves"]
+    k = len(gm)
+    assert n_moves[game] >= k
+    assert np.array_equal(moves[game, :k], gm)
+    assert np.array_equal(visits[game, :k], fx["visits"].astype(np.uint32))
+    if int(fx["max_moves"]) < 0:
+        assert n_moves[game] == k and winners[game] == int(fx["winner"])
+    eng.close()
+
+
+def test_selfplay_synth_many_games_vs_oracle(cabi):
+    """64 concurrent games, each checked bit-exactly against the oracle on its own decision stream"""
+    B, A, sims, seed, G = 9, 81, 24, 77, 64
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=seed, eval_mode=cabi.AO_EVAL_SYNTH,
+                      noise_mode=cabi.AO_NOISE_TAPE)
+    tapes = [O.make_gamma_tape(seed, g, A + 2, A, 10 / A) for g in range(G)]
+    for g in range(G):
+        eng.set_gamma_tape(g, tapes[g])
+    eng.selfplay_begin(G, first_key=0)
+    st = eng.selfplay_rounds(1)
+    while st["running"]:
+        st = eng.selfplay_rounds(1)
+    assert st["errors"] == 0
+    moves, n_moves, winners, visits = eng.selfplay_fetch(G)
+    for g in range(0, G, 7):
+        ora = O.self_play_game(B, sims, lambda mv: synth_eval(mv, A), O.DecisionStream(seed, g, tapes[g]))
+        k = len(ora["moves"])
+        assert n_moves[g] == k and winners[g] == ora["winner"], g
+        assert list(moves[g, :k]) == ora["moves"], g
+        assert np.array_equal(visits[g, :k], np.asarray(ora["visits"], np.uint32)), g
+    assert st["sims"] > 0 and st["moves"] == int(n_moves.sum())
+    eng.close()
+
+
+def test_selfplay_pvnet_nn_replay_parity(cabi):
+    """Device search with the tcgen05 tower; the oracle replays the device's NN outputs: visit counts,
+    moves and winners must be bit-identical; the NN floats themselves are checked against torch fp32 at 1e-4."""
+    B, A, sims, seed, G = 9, 81, 40, 21, 4
+    sd = pvnet_ref.make_state_dict(0, 10, 5, 128, B)
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=seed, noise_mode=cabi.AO_NOISE_TAPE,
+                      nn_log_cap=(sims + 1) * 82)
+    eng.load_state_dict(sd)
+    tapes = [O.make_gamma_tape(seed, g, A + 2, A, 10 / A) for g in range(G)]
+    for g in range(G):
+        eng.set_gamma_tape(g, tapes[g])
+    eng.selfplay_begin(G, first_key=0)
+    st = eng.selfplay_rounds(64)
+    while st["running"]:
+        st = eng.selfplay_rounds(64)
+    assert st["errors"] == 0
+    moves, n_moves, winners, visits = eng.selfplay_fetch(G)
+    worst_p = worst_v = 0.0
+    for g in range(G):
+        pol, val = eng.nn_log(g, (sims + 1) * 82)
+        it = iter(range(len(val)))
+        leaves = []
+
+        def evaluate(mv, pol=pol, val=val, it=it, leaves=leaves):
+            k = next(it)
+            leaves.append(mv)
+            return pol[k], val[k]
+
+        ora = O.self_play_game(B, sims, evaluate, O.DecisionStream(seed, g, tapes[g]))
+        k = len(ora["moves"])
+        assert n_moves[g] == k and winners[g] == ora["winner"], g
+        assert list(moves[g, :k]) == ora["moves"], g
+        assert np.array_equal(visits[g, :k], np.asarray(ora["visits"], np.uint32)), g
+        assert len(leaves) == len(val)
+        sel = leaves[:: max(1, len(leaves) // 48)]
+        x = torch.from_numpy(np.stack([O.get_state_pt(m, B, 5) for m in sel]).astype(np.float32))
+        pr, vr = pvnet_ref.pvnet_forward(sd, x)
+        idx = list(range(0, len(leaves), max(1, len(leaves) // 48)))
+        worst_p = max(worst_p, float(np.abs(pol[idx] - pr.numpy()).max()))
+        worst_v = max(worst_v, float(np.abs(val[idx] - vr.numpy()).max()))
+    assert worst_p < TOL and worst_v < TOL, (worst_p, worst_v)
+    eng.close()
+
+
+def test_facade_search_tree_reuse_vs_oracle(cabi):
+    """ao_search (ZeroAgent.get_pi surface): real root, reused root two plies deeper (arena pattern), repeated root"""
+    B, A, sims, seed = 9, 81, 50, 5
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=2, seed=seed, eval_mode=cabi.AO_EVAL_SYNTH,
+                      noise_mode=cabi.AO_NOISE_TAPE)
+    tape = O.make_gamma_tape(seed, 1, A + 2, A, 10 / A)
+    eng.set_gamma_tape(1, tape)
+    eng.games_reset([1], keys=[1])
+    stream = O.DecisionStream(seed, 1, tape)
+    agent = O.OracleZeroAgent(B, sims, lambda mv: synth_eval(mv, A), stream, noise=True)
+    root = (0,)
+    for step in range(6):
+        vis, pri, real = eng.search([1], [root])
+        agent.get_pi(root, 1)
+        assert np.array_equal(vis[0], agent.visit.astype(np.uint32)), step
+        assert np.array_equal(pri[0], agent.policy), step
+        assert bool(real[0]) == agent.is_real_root
+        order = np.argsort(-vis[0].astype(np.int64), kind="stable")
+        if step == 2:
+            continue  # same root again: reused, re-noised
+        root = root + (int(order[0]), int(order[1]))  # own move + a reply that was visited
+    eng.close()
