@@ -62,6 +62,10 @@ struct ao_engine {
   size_t rec_bytes;
   int32_t* h_pinned;  // [0] n_active
   int selfplay_games;
+  // optional per-kernel timing (bench roofline): event pairs recorded around every launch of a timed call
+  bool timing;
+  std::vector<cudaEvent_t> ev;  // [tree_begin, tree_end(=tower_begin), tower_end] per round
+  unsigned long long launches;  // kernels launched by this engine (bench's gpu_launches)
 };
 
 namespace {
@@ -77,13 +81,19 @@ int ealloc(ao_engine* h, T** p, size_t count) {
 }
 
 // one lock-step round: tree step (consume NN output, select next leaf) then the tower on the emitted requests
-int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters) {
+int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int timed_slot = -1) {
   AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, sizeof(int32_t), h->stream));
   AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
+  if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 0], h->stream));
   AO_CUDA(ao::launch_tree_step(h->tp, ids_dev, n, max_iters, h->stream));
-  if (h->cfg.eval_mode == AO_EVAL_PVNET)
+  if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 1], h->stream));
+  h->launches += 1;
+  if (h->cfg.eval_mode == AO_EVAL_PVNET) {
     AO_CUDA(ao::launch_tower(h->tw, h->B, h->cfg.nn_precision, h->tp.nn_in, h->tp.nn_count, n, h->tp.nn_policy,
                              h->tp.nn_value, h->num_sms, h->stream));
+    h->launches += 1;
+  }
+  if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 2], h->stream));
   return 0;
 }
 
@@ -133,6 +143,9 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->num_sms = prop.multiProcessorCount;
   h->weights_loaded = false;
   h->selfplay_games = 0;
+  h->timing = false;
+  h->launches = 0;
+  h->h_pinned = nullptr;
   if (cfg->stream) {
     h->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
     h->own_stream = false;
@@ -202,6 +215,7 @@ extern "C" int ao_engine_destroy(ao_engine* h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -366,6 +380,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
   AO_CUDA(cudaMemcpyAsync(h->d_lens, root_lens, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(cudaMemcpyAsync(h->d_roots, roots, (size_t)n * (A + 1) * 2, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(ao::launch_set_roots(h->tp, h->d_ids, n, h->d_roots, h->d_lens, h->stream));
+  h->launches += 3;  // set_roots + export_roots + sum_counters
   const bool synth = h->cfg.eval_mode == AO_EVAL_SYNTH;
   const int max_iters = synth ? (1 << 30) : 64;
   int active = 1, rounds = 0;
@@ -442,10 +457,51 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   for (int r = 0; r < rounds; ++r)
     if ((rc = run_round(h, nullptr, h->selfplay_games, max_iters)) != 0) return rc;
   AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
+  h->launches += 1;
   unsigned long long c[5];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
   if (out5) for (int i = 0; i < 5; ++i) out5[i] = c[i];
+  return 0;
+}
+
+// Same as ao_selfplay_rounds but with CUDA events around every kernel launch: returns the summed device time of the
+// tree-step kernels and of the tower kernels (ms) - the per-kernel numbers behind bench.py's roofline object.
+extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5, float* tree_ms, float* tower_ms) {
+  if (!h) return fail(-1, "null engine");
+  if (h->selfplay_games <= 0) return fail(-1, "call ao_selfplay_begin first");
+  if (rounds < 1 || rounds > 4096) return fail(-1, "rounds out of range 1..4096");
+  while ((int)h->ev.size() < 3 * rounds) {
+    cudaEvent_t e;
+    AO_CUDA(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  const int max_iters = h->cfg.eval_mode == AO_EVAL_SYNTH ? (1 << 30) : 64;
+  int rc;
+  for (int r = 0; r < rounds; ++r)
+    if ((rc = run_round(h, nullptr, h->selfplay_games, max_iters, r)) != 0) return rc;
+  AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
+  h->launches += 1;
+  unsigned long long c[5];
+  AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  float t_tree = 0.f, t_tower = 0.f;
+  for (int r = 0; r < rounds; ++r) {
+    float a = 0.f, b = 0.f;
+    AO_CUDA(cudaEventElapsedTime(&a, h->ev[3 * r], h->ev[3 * r + 1]));
+    AO_CUDA(cudaEventElapsedTime(&b, h->ev[3 * r + 1], h->ev[3 * r + 2]));
+    t_tree += a;
+    t_tower += b;
+  }
+  if (tree_ms) *tree_ms = t_tree;
+  if (tower_ms) *tower_ms = t_tower;
+  if (out5) for (int i = 0; i < 5; ++i) out5[i] = c[i];
+  return 0;
+}
+
+extern "C" int ao_launch_count(ao_engine* h, uint64_t* out) {
+  if (!h || !out) return fail(-1, "null argument");
+  *out = h->launches;
   return 0;
 }
 

@@ -86,8 +86,11 @@ int ao_selfplay_begin(ao_engine* h, int n_games, uint32_t first_key);
 int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5);
 int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_moves, int8_t* winners,
                       uint32_t* visits);
-/* Same loop with HOST-supplied starting positions and host-visible results every call (the end-to-end bench leg):
- * uploads ids, searches one move for every game, downloads visits. */
+/* ao_selfplay_rounds with CUDA events around every launch: summed device milliseconds of the tree-step kernels and of
+ * the tower kernels over the `rounds` rounds (bench.py's roofline numbers). rounds <= 4096. */
+int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5, float* tree_ms, float* tower_ms);
+/* Number of kernels this engine has launched so far (bench.py's gpu_launches). */
+int ao_launch_count(ao_engine* h, uint64_t* out);
 
 /* NN-output log of one game (parity protocol: the oracle replays these floats): policy[count][A], value[count]. */
 int ao_get_nn_log(ao_engine* h, int game_id, float* policy, float* value, int32_t capacity, int32_t* count);
