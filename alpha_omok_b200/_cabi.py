@@ -27,7 +27,7 @@ class AoConfig(C.Structure):
 
 EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
-    "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_rounds",
+    "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
     "ao_selfplay_rounds_timed", "ao_launch_count", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
     "ao_encode_state", "ao_legal_actions", "ao_umma_probe",
 ]
@@ -58,6 +58,7 @@ def lib():
     L.ao_search.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.ao_nn_forward.argtypes = [vp, vp, i32, vp, vp]
     L.ao_selfplay_begin.argtypes = [vp, i32, u32]
+    L.ao_selfplay_begin_mode.argtypes = [vp, i32, u32, i32]
     L.ao_selfplay_rounds.argtypes = [vp, i32, vp]
     L.ao_selfplay_rounds_timed.argtypes = [vp, i32, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.ao_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -165,20 +166,26 @@ class Engine:
         check(lib().ao_nn_forward(self._h, ptr(s), n, ptr(p), ptr(v)))
         return p, v
 
-    def selfplay_begin(self, n_games, first_key=0):
-        check(lib().ao_selfplay_begin(self._h, n_games, first_key))
+    def selfplay_begin(self, n_games, first_key=0, recycle=False):
+        check(lib().ao_selfplay_begin_mode(self._h, n_games, first_key, int(recycle)))
+
+    @staticmethod
+    def _counters(out, **extra):
+        d = dict(sims=int(out[0]), running=int(out[1]), nn_evals=int(out[2]), errors=int(out[3]), moves=int(out[4]),
+                 games_finished=int(out[5]), terminal_sims=int(out[6]))
+        d.update(extra)
+        return d
 
     def selfplay_rounds(self, rounds):
-        out = np.zeros(5, np.uint64)
+        out = np.zeros(8, np.uint64)
         check(lib().ao_selfplay_rounds(self._h, rounds, ptr(out)))
-        return dict(sims=int(out[0]), running=int(out[1]), nn_evals=int(out[2]), errors=int(out[3]), moves=int(out[4]))
+        return self._counters(out)
 
     def selfplay_rounds_timed(self, rounds):
-        out = np.zeros(5, np.uint64)
+        out = np.zeros(8, np.uint64)
         a, b = C.c_float(0), C.c_float(0)
         check(lib().ao_selfplay_rounds_timed(self._h, rounds, ptr(out), C.byref(a), C.byref(b)))
-        return dict(sims=int(out[0]), running=int(out[1]), nn_evals=int(out[2]), errors=int(out[3]), moves=int(out[4]),
-                    tree_ms=a.value, tower_ms=b.value)
+        return self._counters(out, tree_ms=a.value, tower_ms=b.value)
 
     def launch_count(self):
         n = C.c_uint64(0)

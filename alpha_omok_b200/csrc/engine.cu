@@ -396,7 +396,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
   if (priors) AO_CUDA(cudaMemcpyAsync(priors, h->d_priors, (size_t)n * A * 8, cudaMemcpyDeviceToHost, h->stream));
   if (is_real_root) AO_CUDA(cudaMemcpyAsync(is_real_root, h->d_real_root, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(ao::launch_sum_counters(h->tp, h->G, h->d_counters, h->stream));
-  unsigned long long c[5];
+  unsigned long long c[8];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
   if (c[3] != 0) return fail(-7, "%llu game tree(s) overflowed their arena (raise node_cap)", c[3]);
@@ -434,7 +434,11 @@ extern "C" int ao_nn_forward(ao_engine* h, const float* states, int n, float* p,
 }
 
 // ---------------------------------------------------------------------------------------------------- self-play
+extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_key, int recycle);
 extern "C" int ao_selfplay_begin(ao_engine* h, int n_games, uint32_t first_key) {
+  return ao_selfplay_begin_mode(h, n_games, first_key, 0);
+}
+extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_key, int recycle) {
   if (!h) return fail(-1, "null engine");
   if (n_games < 1 || n_games > h->G) return fail(-1, "n_games = %d out of range 1..%d", n_games, h->G);
   int rc = require_weights(h);
@@ -442,7 +446,7 @@ extern "C" int ao_selfplay_begin(ao_engine* h, int n_games, uint32_t first_key) 
   std::vector<uint32_t> keys(n_games);
   for (int i = 0; i < n_games; ++i) keys[i] = first_key + (uint32_t)i;
   AO_CUDA(cudaMemcpyAsync(h->d_keys, keys.data(), (size_t)n_games * 4, cudaMemcpyHostToDevice, h->stream));
-  AO_CUDA(ao::launch_reset_games(h->tp, nullptr, n_games, h->d_keys, 1, h->stream));
+  AO_CUDA(ao::launch_reset_games(h->tp, nullptr, n_games, h->d_keys, recycle ? 2 : 1, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->selfplay_games = n_games;
   return 0;
@@ -458,10 +462,10 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
     if ((rc = run_round(h, nullptr, h->selfplay_games, max_iters)) != 0) return rc;
   AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
   h->launches += 1;
-  unsigned long long c[5];
+  unsigned long long c[8];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
-  if (out5) for (int i = 0; i < 5; ++i) out5[i] = c[i];
+  if (out5) for (int i = 0; i < 8; ++i) out5[i] = c[i];
   return 0;
 }
 
@@ -482,7 +486,7 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
     if ((rc = run_round(h, nullptr, h->selfplay_games, max_iters, r)) != 0) return rc;
   AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
   h->launches += 1;
-  unsigned long long c[5];
+  unsigned long long c[8];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
   float t_tree = 0.f, t_tower = 0.f;
@@ -495,7 +499,7 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
   }
   if (tree_ms) *tree_ms = t_tree;
   if (tower_ms) *tower_ms = t_tower;
-  if (out5) for (int i = 0; i < 5; ++i) out5[i] = c[i];
+  if (out5) for (int i = 0; i < 8; ++i) out5[i] = c[i];
   return 0;
 }
 

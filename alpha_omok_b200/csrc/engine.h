@@ -45,7 +45,7 @@ struct __align__(16) Game {
   int32_t winner;
   int32_t error;
   uint32_t nn_log_count;
-  unsigned long long sims_total, nn_evals, terminal_sims, moves_played;
+  unsigned long long sims_total, nn_evals, terminal_sims, moves_played, games_finished;
 };
 
 // NN request: the five input planes of utils.get_state_pt as row bit-masks

@@ -439,8 +439,25 @@ __device__ void play_move(Ctx& c, Regs& g) {
   if (c.lane == 0) c.gm->moves_played += 1ull;
   const int win = check_win_rows(g.rb, g.rw, P.B, g.n_moves, sm->rows, c.lane);
   if (win != 0) {
-    g.status = ST_FINISHED;
-    if (c.lane == 0) c.gm->winner = win;
+    if (c.lane == 0) {
+      c.gm->winner = win;
+      c.gm->games_finished += 1ull;
+    }
+    if (c.gm->auto_play != 2) {
+      g.status = ST_FINISHED;
+      return;
+    }
+    // bench mode (auto_play == 2): recycle the slot - a fresh episode with the next decision-stream key
+    g.rb = 0u; g.rw = 0u;
+    g.n_moves = 0; g.last1 = -1; g.last2 = -1;
+    g.root_node = CH_UNVISITED; g.root_n = 0u; g.root_w = 0.f; g.slot_count = 0u;
+    g.sims_done = 0; g.sims_target = P.num_mcts + 1;
+    g.rng_ctr = 0u; g.noise_draws = 0u;
+    if (c.lane == 0) {
+      c.gm->game_key += (uint32_t)P.G;
+      c.gm->is_real_root = 1;
+    }
+    __syncwarp();
     return;
   }
   // next search: reused root (agents.py:93-103) -> num_mcts sims, Dirichlet re-mixed into the existing priors
@@ -697,6 +714,7 @@ __global__ void reset_games_kernel(TreeParams P, const int32_t* __restrict__ ids
   gm->rng_ctr = 0u; gm->noise_draws = 0u; gm->game_key = keys ? keys[i] : (uint32_t)game;
   gm->leaf_depth = 0; gm->leaf_n_moves = 0; gm->nn_slot = 0; gm->winner = 0; gm->error = 0; gm->nn_log_count = 0u;
   gm->sims_total = 0ull; gm->nn_evals = 0ull; gm->terminal_sims = 0ull; gm->moves_played = 0ull;
+  gm->games_finished = 0ull;
 }
 
 // Facade root handling == `_init_mcts` (agents.py:82-103): is the requested root ID inside the stored tree?
@@ -786,12 +804,14 @@ __global__ void export_roots_kernel(TreeParams P, const int32_t* __restrict__ id
 }
 
 __global__ void sum_counters_kernel(TreeParams P, int n, unsigned long long* out) {
-  unsigned long long sims = 0, running = 0, evals = 0, errors = 0, moves = 0;
+  unsigned long long sims = 0, running = 0, evals = 0, errors = 0, moves = 0, fin = 0, term = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const Game* gm = &P.games[i];
     sims += gm->sims_total;
     evals += gm->nn_evals;
     moves += gm->moves_played;
+    fin += gm->games_finished;
+    term += gm->terminal_sims;
     running += (gm->status == ST_SEARCH || gm->status == ST_WAIT_NN) ? 1ull : 0ull;
     errors += gm->status == ST_ERROR ? 1ull : 0ull;
   }
@@ -800,6 +820,8 @@ __global__ void sum_counters_kernel(TreeParams P, int n, unsigned long long* out
   atomicAdd(&out[2], evals);
   atomicAdd(&out[3], errors);
   atomicAdd(&out[4], moves);
+  atomicAdd(&out[5], fin);
+  atomicAdd(&out[6], term);
 }
 
 // replay record slab: {int16 n_moves, int8 winner, int8 pad, int16 moves[A], (pad to 4) uint32 visits[A][A]}
@@ -847,7 +869,7 @@ cudaError_t launch_reset_games(const TreeParams& p, const int32_t* ids, int n, c
   return cudaGetLastError();
 }
 cudaError_t launch_sum_counters(const TreeParams& p, int n, unsigned long long* out5, cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(out5, 0, 5 * sizeof(unsigned long long), s);
+  cudaError_t e = cudaMemsetAsync(out5, 0, 8 * sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
   sum_counters_kernel<<<32, 128, 0, s>>>(p, n, out5);
   return cudaGetLastError();

@@ -1,0 +1,78 @@
+"""Replay records of a self-play round and their exchange between ranks.
+
+Games are sharded over ranks with no data-path collective; the ONE exchange step of the path is the all-gather of
+the (state, pi, z) records into every rank's replay buffer at the end of a round (main.py:250 `rep_memory.extend`).
+Records travel in the compact fixed-size form the device packs (csrc/tree.cu pack_records_kernel):
+    int16 n_moves | int8 winner | int8 pad | int16 moves[A] | pad to 4 | uint32 visits[A][A]
+(state planes and pi are re-derived from moves / visits by `decode_records`), as one padded slab per rank, so a plain
+all_gather_into_tensor over NCCL (NVLink / NVSwitch) is enough - no all-gather-v.  torch.distributed is plumbing here.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+
+def record_bytes(A: int) -> int:
+    return ((4 + 2 * A + 3) & ~3) + 4 * A * A
+
+
+class _DevSlab:
+    """__cuda_array_interface__ view of the engine-owned record slab (no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def device_records(engine, n_games) -> torch.Tensor:
+    """Pack the finished games of `engine` and return a uint8 CUDA tensor [n_games, record_bytes] aliasing the slab."""
+    engine.records_pack(n_games)
+    ptr, bpg = engine.records_dev()
+    t = torch.as_tensor(_DevSlab(ptr, n_games * bpg), device=torch.device("cuda", torch.cuda.current_device()))
+    return t.view(n_games, bpg)
+
+
+def allgather_records(local: torch.Tensor, group=None) -> torch.Tensor:
+    """[n_local, bytes] uint8 on every rank -> [world * n_local, bytes], rank-major (rank r's games at r*n_local...)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local.clone()
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+def decode_records(slab, board_size: int, tau_thres: int = 6, with_states: bool = True):
+    """uint8 [n, record_bytes] (torch or numpy) -> the reference's cur_memory list of (state, pi, z) (main.py:201-227)
+    plus the {'Black','White','Draw'} result counts."""
+    A = board_size * board_size
+    buf = slab.cpu().numpy() if isinstance(slab, torch.Tensor) else np.asarray(slab)
+    voff = (4 + 2 * A + 3) & ~3
+    memory, result = [], {"Black": 0, "White": 0, "Draw": 0}
+    for rec in buf:
+        k = int(rec[:2].view(np.int16)[0])
+        w = int(rec[2])
+        moves = rec[4:4 + 2 * A].view(np.int16)
+        visits = rec[voff:voff + 4 * A * A].view(np.uint32).reshape(A, A)
+        result["Black" if w == 1 else "White" if w == 2 else "Draw"] += 1
+        z_black = 1.0 if w == 1 else -1.0 if w == 2 else 0.0
+        ids = [(0,) + tuple(int(a) for a in moves[:t]) for t in range(k)]
+        states = _cabi.encode_state_batch(ids, board_size).astype(np.float64) if with_states and k else [None] * k
+        for t in range(k):
+            v = visits[t].astype(np.float64)
+            if t < tau_thres:
+                pi = v / v.sum()
+            else:
+                pi = np.zeros(A)
+                pi[moves[t]] = 1.0
+            memory.append((states[t] if with_states else ids[t], pi, z_black if t % 2 == 0 else -z_black))
+    return memory, result
+
+
+def shard_games(n_total: int, rank: int, world: int):
+    """game g -> rank g % world (per-game decision-stream keys are independent of the world size)."""
+    return list(range(rank, n_total, world))

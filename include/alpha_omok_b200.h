@@ -77,18 +77,22 @@ int ao_nn_forward(ao_engine* h, const float* states, int n, float* p, float* v);
 /* Batched twin of main.self_play (main.py:122-250): every game slot plays one episode on the device
  * (get_pi -> get_action -> env.step -> root advance), decisions from the per-game stream.
  *   ao_selfplay_begin : reset all slots [0, n_games) with game keys first_key + g.
+ *   ao_selfplay_begin_mode(recycle=1): a slot whose episode ends immediately starts the next one (key += max_games)
+ *                       - steady-state throughput runs; per-episode records are then not kept.
  *   ao_selfplay_rounds: run up to `rounds` lock-step rounds (select -> NN -> expand/backup [-> move]) and return
- *                       totals: out[0] simulations completed, out[1] games still running, out[2] NN evaluations,
- *                       out[3] games in error (tree arena overflow), out[4] moves played.
+ *                       totals in out[8]: [0] simulations completed, [1] games still running, [2] NN evaluations,
+ *                       [3] games in error (tree arena overflow), [4] moves played, [5] episodes finished,
+ *                       [6] terminal-leaf simulations, [7] reserved.
  *   ao_selfplay_fetch : moves[n][A] (int16, -1 padded), n_moves[n], winners[n] (0 running,1,2,3),
  *                       visits[n][A][A] uint32 per ply (may be NULL). */
 int ao_selfplay_begin(ao_engine* h, int n_games, uint32_t first_key);
-int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5);
+int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_key, int recycle);
+int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out8);
 int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_moves, int8_t* winners,
                       uint32_t* visits);
 /* ao_selfplay_rounds with CUDA events around every launch: summed device milliseconds of the tree-step kernels and of
  * the tower kernels over the `rounds` rounds (bench.py's roofline numbers). rounds <= 4096. */
-int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5, float* tree_ms, float* tower_ms);
+int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out8, float* tree_ms, float* tower_ms);
 /* Number of kernels this engine has launched so far (bench.py's gpu_launches). */
 int ao_launch_count(ao_engine* h, uint64_t* out);
 

@@ -1,0 +1,95 @@
+"""GPU tests of the drop-in surface: agents.ZeroAgent / utils / env / model used exactly like main.py and eval_main.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import omok_oracle as O
+from oracle import pvnet_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def test_utils_and_env_match_oracle():
+    from alpha_omok_b200 import utils
+    from alpha_omok_b200.env import env_regular, env_small
+    assert env_small.Return_BoardParams() == (9, 81) and env_regular.Return_BoardParams() == (15, 225)
+    rs = np.random.RandomState(0)
+    for B, mod in ((9, env_small), (15, env_regular)):
+        A = B * B
+        mv = (0,) + tuple(int(x) for x in rs.permutation(A)[:A - 9])
+        assert utils.legal_actions(mv, B) == O.legal_actions(mv, B)
+        assert np.array_equal(utils.get_state_pt(mv, B, 5), O.get_state_pt(mv, B, 5))
+        assert np.array_equal(utils.get_board(mv, B), O.get_board(mv, B))
+        env, ref = mod.GameState("text"), O.OracleGameState(B)
+        for a in [int(x) for x in rs.permutation(A)[:60]] + [3, 3]:
+            onehot = np.zeros(A)
+            onehot[a] = 1
+            got, exp = env.step(onehot), ref.step(onehot)
+            assert np.array_equal(got[0], exp[0]) and tuple(got[1:]) == tuple(exp[1:])
+
+
+def test_zero_agent_dropin_selfplay_loop():
+    """main.py:132-250 with our modules substituted for the reference's; checks the API contract and game sanity"""
+    from alpha_omok_b200 import agents, model, utils
+    from alpha_omok_b200.env import env_small as game
+    np.random.seed(0)
+    B, N_MCTS, IN_PLANES = game.Return_BoardParams()[0], 48, 5
+    Agent = agents.ZeroAgent(B, N_MCTS, IN_PLANES, noise=True)
+    Agent.model = model.PVNet(10, IN_PLANES, 128, B)
+    Agent.model.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, B), strict=False)
+    Agent.model.eval()
+    env = game.GameState("text")
+    root_id, win_index, t = (0,), 0, 0
+    while win_index == 0 and t < 12:
+        pi = Agent.get_pi(root_id, 1 if t < 6 else 0)
+        assert pi.shape == (81,) and pi.dtype == np.float64 and abs(pi.sum() - 1) < 1e-12
+        assert Agent.get_visit().sum() >= N_MCTS and Agent.root_id == root_id
+        assert Agent.is_real_root == (t == 0)
+        assert abs(Agent.get_policy().sum() - 1) < 1e-9
+        state = utils.get_state_pt(root_id, B, IN_PLANES)
+        with torch.no_grad():
+            p, v = Agent.model(torch.tensor(np.asarray([state])).float())  # main.py:176-180 through the CUDA tower
+        pr, vr = pvnet_ref.pvnet_forward(Agent.model.state_dict(), torch.tensor(np.asarray([state])).float())
+        assert torch.allclose(p, pr, atol=1e-4) and torch.allclose(v, vr, atol=1e-4)
+        action, action_index = utils.get_action(pi)
+        root_id += (int(action_index),)
+        board, valid, win_index, turn, _ = env.step(action)
+        assert valid
+        t += 1
+    p, v = Agent.get_pv(root_id)
+    assert p.shape == (81,) and abs(float(p.sum()) - 1) < 1e-5 and -1 <= float(v) <= 1
+    assert Agent.get_name() == "ZeroAgent"
+    Agent.reset()
+    assert Agent.root_id is None
+
+
+def test_batched_selfplay_records():
+    from alpha_omok_b200 import agents, model
+    net = model.PVNet(10, 5, 128, 9)
+    net.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, 9), strict=False)
+    mem, result = agents.self_play(net, 16, board_size=9, num_mcts=24, seed=4)
+    assert sum(result.values()) == 16 and len(mem) >= 16 * 9
+    s, pi, z = mem[0]
+    assert s.shape == (5, 9, 9) and s[:4].sum() == 0 and s[4].min() == 1 and abs(pi.sum() - 1) < 1e-12 and z in (-1.0, 0.0, 1.0)
+    # one-hot targets after TAU_THRES plies (main.py:150-166), interleaved colours with opposite z
+    assert any(np.count_nonzero(p) == 1 for _, p, _ in mem)
+    assert mem[0][2] == -mem[1][2]
+
+
+def test_replay_records_device_roundtrip():
+    from alpha_omok_b200 import _cabi, replay
+    B, A, G = 9, 81, 8
+    eng = _cabi.Engine(board_size=B, num_mcts=16, max_games=G, seed=2, eval_mode=_cabi.AO_EVAL_SYNTH)
+    eng.selfplay_begin(G)
+    st = eng.selfplay_rounds(1)
+    while st["running"]:
+        st = eng.selfplay_rounds(1)
+    moves, n_moves, winners, visits = eng.selfplay_fetch(G)
+    slab = replay.allgather_records(replay.device_records(eng, G))
+    mem, result = replay.decode_records(slab, B)
+    assert len(mem) == int(n_moves.sum()) and sum(result.values()) == G
+    k0 = int(n_moves[0])
+    assert np.array_equal(mem[0][0], O.get_state_pt((0,), B, 5))
+    assert np.array_equal(mem[k0 - 1][0], O.get_state_pt((0,) + tuple(int(a) for a in moves[0, :k0 - 1]), B, 5))
+    assert np.allclose(mem[0][1], visits[0, 0] / visits[0, 0].sum())
+    eng.close()
