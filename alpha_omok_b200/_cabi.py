@@ -28,7 +28,7 @@ class AoConfig(C.Structure):
 EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
     "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
-    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
+    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
     "ao_encode_state", "ao_legal_actions", "ao_umma_probe",
 ]
 
@@ -61,6 +61,7 @@ def lib():
     L.ao_selfplay_begin_mode.argtypes = [vp, i32, u32, i32]
     L.ao_selfplay_rounds.argtypes = [vp, i32, vp]
     L.ao_selfplay_rounds_timed.argtypes = [vp, i32, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.ao_tower_debug.argtypes = [vp, i32, vp]
     L.ao_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ao_selfplay_fetch.argtypes = [vp, i32, vp, vp, vp, vp]
     L.ao_get_nn_log.argtypes = [vp, i32, vp, vp, i32, C.POINTER(i32)]
@@ -186,6 +187,11 @@ class Engine:
         a, b = C.c_float(0), C.c_float(0)
         check(lib().ao_selfplay_rounds_timed(self._h, rounds, ptr(out), C.byref(a), C.byref(b)))
         return self._counters(out, tree_ms=a.value, tower_ms=b.value)
+
+    def tower_debug(self, enable=True):
+        out = np.zeros(8, np.uint64)
+        check(lib().ao_tower_debug(self._h, int(enable), ptr(out)))
+        return [int(x) for x in out]
 
     def launch_count(self):
         n = C.c_uint64(0)

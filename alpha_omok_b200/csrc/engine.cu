@@ -503,6 +503,24 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
   return 0;
 }
 
+// Cycle counters of CTA 0 of the tower kernel, accumulated over all launches since enabling:
+// [0] MMA-issuer total, [1] MMA waits for the epilogue (operand ready), [2] MMA waits for weights (TMA ring),
+// [3] launches, [4] epilogue thread 0 total, [5] epilogue waits for the accumulators, [6] heads.
+extern "C" int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8) {
+  if (!h) return fail(-1, "null engine");
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  if (out8 && h->tw.dbg) AO_CUDA(cudaMemcpy(out8, h->tw.dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (enable && !h->tw.dbg) {
+    unsigned long long* p = nullptr;
+    int rc = ealloc(h, &p, 8);
+    if (rc) return rc;
+    h->tw.dbg = p;
+  }
+  if (h->tw.dbg) AO_CUDA(cudaMemset(h->tw.dbg, 0, 8 * sizeof(uint64_t)));
+  if (!enable) h->tw.dbg = nullptr;
+  return 0;
+}
+
 extern "C" int ao_launch_count(ao_engine* h, uint64_t* out) {
   if (!h || !out) return fail(-1, "null argument");
   *out = h->launches;

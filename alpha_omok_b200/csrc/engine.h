@@ -100,6 +100,7 @@ struct TowerWeights {
   const float* vfc2_w;     // [128]
   float vfc2_b;
   int n_layers;            // 1 + 2*n_blocks
+  unsigned long long* dbg; // optional profiling counters of CTA 0 (null = off), see ao_tower_debug
 };
 
 // host-side launchers implemented in the .cu files

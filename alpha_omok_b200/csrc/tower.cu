@@ -132,41 +132,63 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       }
     }
   } else if (warp == 9) {
-    // =========================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    // =========================================================== MMA issuer
+    // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; one elected
+    // lane issues tcgen05.mma / commit.
+    {
       const uint32_t idesc = umma_idesc_f16_f32(128, 128);
-      const uint32_t a_base = smem_u32(s_act);
       const uint32_t lbo_a = (uint32_t)G::Rows * 16u;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_act), lbo_a);
+      const uint32_t desc_hi = umma_desc_hi(128u);
+      constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;  // two k-chunks further along K
+      constexpr uint32_t kBStep = (2u * kC * 16u) >> 4;
       uint32_t it = 0, act_phase = 0;
+      long long dbg_act_wait = 0, dbg_full_wait = 0;
+      const long long dbg_t0 = W.dbg ? clock64() : 0;
       for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
         for (int l = 0; l < n_layers; ++l) {
-          const int nk = l == 0 ? 1 : kC / 16;
           const bool to_b = (l & 1) == 0;           // stem and conv2 accumulate in accB
           const bool residual = to_b && l > 0;      // accB already holds the block input x
+          const long long t_a0 = W.dbg ? clock64() : 0;
           mbar_wait(bar_act, act_phase);
           act_phase ^= 1u;
           tc_fence_after_sync();
+          if (W.dbg) dbg_act_wait += clock64() - t_a0;
           for (int t = 0; t < 9; ++t, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
+            const long long t_f0 = W.dbg ? clock64() : 0;
             mbar_wait(&bar_full[s], ph);
             tc_fence_after_sync();
+            if (W.dbg) dbg_full_wait += clock64() - t_f0;
             const int shift = (t / 3 - 1) * G::S + (t % 3 - 1);
-            const uint32_t b_base = smem_u32(s_w + s * kStageBytes);
+            const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + s * kStageBytes), kC * 16u);
+            if (elect_one()) {
 #pragma unroll
-            for (int tile = 0; tile < kTiles; ++tile) {
-              const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
-              const uint32_t a_row = (uint32_t)(G::Halo + tile * kTileRows + shift);
-              for (int j = 0; j < nk; ++j) {
-                const uint64_t da = umma_desc_kmajor_noswz(a_base + (uint32_t)(2 * j) * lbo_a + a_row * 16u, lbo_a, 128u);
-                const uint64_t db = umma_desc_kmajor_noswz(b_base + (uint32_t)(2 * j) * (kC * 16u), kC * 16u, 128u);
-                umma_f16_ss(d_tmem, da, db, idesc, (residual || t > 0 || j > 0) ? 1u : 0u);
+              for (int tile = 0; tile < kTiles; ++tile) {
+                const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
+                const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);  // 16 B per row
+                if (l == 0) {
+                  umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, t > 0 ? 1u : 0u);
+                } else {
+                  umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || t > 0) ? 1u : 0u);
+#pragma unroll
+                  for (int j = 1; j < kC / 16; ++j)
+                    umma_f16_ss_lohi(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u);
+                }
               }
+              umma_commit(&bar_empty[s]);
+              if (t == 8) umma_commit(bar_acc);
             }
-            umma_commit(&bar_empty[s]);
+            __syncwarp();
           }
-          umma_commit(bar_acc);
         }
+      }
+      if (W.dbg && blockIdx.x == 0 && lane == 0) {  // profiling counters (ao_tower_debug): MMA-issuer view of CTA 0
+        atomicAdd(&W.dbg[0], (unsigned long long)(clock64() - dbg_t0));
+        atomicAdd(&W.dbg[1], (unsigned long long)dbg_act_wait);
+        atomicAdd(&W.dbg[2], (unsigned long long)dbg_full_wait);
+        atomicAdd(&W.dbg[3], 1ull);
       }
     }
   } else {
@@ -182,6 +204,9 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     const uint32_t chunk_stride = (uint32_t)G::Rows * 16u;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * 256);
     uint32_t acc_phase = 0;
+    long long dbg_acc_wait = 0, dbg_heads = 0;
+    const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    const long long dbg_e0 = dbg_on ? clock64() : 0;
 
     for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
       const int g0 = pass * G::GPC;
@@ -212,20 +237,26 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         const bool to_b = (l & 1) == 0;
         const bool last = l == n_layers - 1;
         const float* bias = s_bias + l * kC;
+        const long long t_w0 = dbg_on ? clock64() : 0;
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
+        if (dbg_on) dbg_acc_wait += clock64() - t_w0;
         const uint32_t acc_addr = lane_addr + (to_b ? 128u : 0u);
-#pragma unroll 1
-        for (int qd = 0; qd < 4; ++qd) {
-          uint32_t v[32];
-          tmem_ld32(acc_addr + (uint32_t)(qd * 32), v);
-          tmem_ld_wait();
+        // 4 chunks of 32 accumulator columns, TMEM loads double-buffered against the per-chunk math
+        auto process = [&](uint32_t (&v)[32], const int qd) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + qd * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float y = __uint_as_float(v[j]) + bias[qd * 32 + j];
-            y = fmaxf(y, 0.f);
-            v[j] = __float_as_uint(valid ? y : 0.f);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4];
+            const float y0 = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bb.x, 0.f);
+            const float y1 = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bb.y, 0.f);
+            const float y2 = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bb.z, 0.f);
+            const float y3 = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bb.w, 0.f);
+            v[j4 * 4 + 0] = __float_as_uint(valid ? y0 : 0.f);
+            v[j4 * 4 + 1] = __float_as_uint(valid ? y1 : 0.f);
+            v[j4 * 4 + 2] = __float_as_uint(valid ? y2 : 0.f);
+            v[j4 * 4 + 3] = __float_as_uint(valid ? y3 : 0.f);
           }
           if (!last) {
 #pragma unroll
@@ -253,6 +284,21 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
               hd2 = fmaf(x, s_headw[2 * kC + qd * 32 + j], hd2);
             }
           }
+        };
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld32(acc_addr, va);
+          tmem_ld_wait();
+          tmem_ld32(acc_addr + 32u, vb);
+          process(va, 0);
+          tmem_ld_wait();
+          tmem_ld32(acc_addr + 64u, va);
+          process(vb, 1);
+          tmem_ld_wait();
+          tmem_ld32(acc_addr + 96u, vb);
+          process(va, 2);
+          tmem_ld_wait();
+          process(vb, 3);
         }
         if (!last) {
           if (to_b) tmem_st_wait();
@@ -262,6 +308,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         }
       }
       // ---- heads (model.py:43-50, 63-73)
+      const long long t_h0 = dbg_on ? clock64() : 0;
       if (valid) {
         float* f = s_feat + g_local * 3 * G::A;
         f[0 * G::A + pos] = fmaxf(hd0 + W.head_b[0], 0.f);
@@ -276,7 +323,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         const float* f = s_feat + pg * 3 * G::A;
         float acc = W.pfc_b[po];
         const float* wt = W.pfc_wT + po;
-#pragma unroll 6
+#pragma unroll 18
         for (int k = 0; k < 2 * G::A; ++k) acc = fmaf(__ldg(wt + (size_t)k * G::A), f[k], acc);
         logit = acc;
         s_logits[pg * G::A + po] = acc;
@@ -286,7 +333,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         const float* f = s_feat + vg * 3 * G::A + 2 * G::A;
         float acc = W.vfc1_b[vj];
         const float* wt = W.vfc1_wT + vj;
-#pragma unroll 6
+#pragma unroll 27
         for (int k = 0; k < G::A; ++k) acc = fmaf(__ldg(wt + (size_t)k * kC), f[k], acc);
         s_hidden[vg * kC + vj] = fmaxf(acc, 0.f) * W.vfc2_w[vj];
       }
@@ -313,6 +360,12 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       epi_bar_sync();
       if (p_thread) policy[(size_t)(g0 + pg) * G::A + po] = expf(logit - s_red[pg * 2]) / s_red[pg * 2 + 1];
       // s_feat / s_logits are rewritten only after the next pass's 21 layers: no extra barrier needed
+      if (dbg_on) dbg_heads += clock64() - t_h0;
+    }
+    if (dbg_on) {
+      atomicAdd(&W.dbg[4], (unsigned long long)(clock64() - dbg_e0));
+      atomicAdd(&W.dbg[5], (unsigned long long)dbg_acc_wait);
+      atomicAdd(&W.dbg[6], (unsigned long long)dbg_heads);
     }
   }
   tc_fence_before_sync();

@@ -93,6 +93,8 @@ int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_move
 /* ao_selfplay_rounds with CUDA events around every launch: summed device milliseconds of the tree-step kernels and of
  * the tower kernels over the `rounds` rounds (bench.py's roofline numbers). rounds <= 4096. */
 int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out8, float* tree_ms, float* tower_ms);
+/* Profiling aid: cycle counters of CTA 0 of the tower kernel (see csrc/engine.cu); enable=1 starts / resets them. */
+int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8);
 /* Number of kernels this engine has launched so far (bench.py's gpu_launches). */
 int ao_launch_count(ao_engine* h, uint64_t* out);
 

@@ -21,6 +21,7 @@ eng = _cabi.Engine(board_size=a.board, num_mcts=a.sims, max_games=a.games, seed=
 eng.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, a.board))
 eng.selfplay_begin(a.games)
 prev = eng.selfplay_rounds(20)
+eng.tower_debug(True)
 for rep in range(a.reps):
     t0 = time.time()
     st = eng.selfplay_rounds_timed(a.rounds)
@@ -31,3 +32,7 @@ for rep in range(a.reps):
           f"tower TFLOP/s {de*(478.8e6 if a.board==9 else 1330.1e6)/st['tower_ms']/1e9:.1f}  running {st['running']} "
           f"moves {st['moves']} err {st['errors']}", flush=True)
     prev = st
+d = eng.tower_debug(False)
+if d[3]:
+    print("tower CTA0 cycles/launch: mma_total %.0f  wait_epilogue %.0f  wait_weights %.0f | epi_total %.0f  wait_acc %.0f  heads %.0f"
+          % (d[0] / d[3], d[1] / d[3], d[2] / d[3], d[4] / d[3], d[5] / d[3], d[6] / d[3]))
