@@ -124,6 +124,8 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   if (cfg->num_mcts < 1) return fail(-1, "num_mcts must be >= 1");
   if (cfg->eval_mode == AO_EVAL_PVNET && cfg->board_size != 9 && cfg->board_size != 15)
     return fail(-1, "the PVNet tower kernel is built for board_size 9 and 15 only");
+  if (cfg->eval_mode == AO_EVAL_PVNET && cfg->nn_precision == AO_NN_FP16X3 && cfg->board_size != 9)
+    return fail(-1, "nn_precision AO_NN_FP16X3 (hi/lo split) is implemented for board_size 9 only");
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);
   if (e0 != cudaSuccess || ndev == 0)

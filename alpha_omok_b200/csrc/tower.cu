@@ -45,11 +45,16 @@ struct Geo {
   static_assert(GPC >= 1, "board too large for a 256-row CTA tile");
 };
 
-template <int B, int STAGES>
+// X3 = error-compensated mode: activations and weights are split into fp16 hi + lo parts and every k-step issues
+// a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (fp32 accumulate) - ~22 significant bits per operand; needed for 1e-4 on
+// trained nets.  A weight stage is then half a tap: [hi 16 KB][lo 16 KB].
+template <int B, int STAGES, bool X3>
 struct SmemLayout {
   using G = Geo<B>;
   static constexpr int act = 0;
-  static constexpr int wring = (G::ActBytes + 1023) / 1024 * 1024;
+  static constexpr int act_pad = (G::ActBytes + 1023) / 1024 * 1024;
+  static constexpr int act_lo = act_pad;                                // only in X3 mode
+  static constexpr int wring = X3 ? 2 * act_pad : act_pad;
   static constexpr int bias = wring + STAGES * kStageBytes;            // [kMaxLayers][128] f32
   static constexpr int headw = bias + kMaxLayers * kC * 4;              // [3][128] f32
   static constexpr int feat = headw + 3 * kC * 4;                       // [GPC][3][A] f32 (p0, p1, v)
@@ -62,12 +67,12 @@ struct SmemLayout {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int B, int STAGES>
+template <int B, int STAGES, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
              float* __restrict__ policy, float* __restrict__ value) {
   using G = Geo<B>;
-  using SL = SmemLayout<B, STAGES>;
+  using SL = SmemLayout<B, STAGES, X3>;
   extern __shared__ __align__(1024) uint8_t smem[];
 
   int n = n_ptr ? *n_ptr : n_max;
@@ -76,6 +81,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
   if ((int)blockIdx.x >= n_pass) return;
 
   uint8_t* s_act = smem + SL::act;
+  uint8_t* s_act_lo = smem + SL::act_lo;  // X3 only
   uint8_t* s_w = smem + SL::wring;
   float* s_bias = reinterpret_cast<float*>(smem + SL::bias);
   float* s_headw = reinterpret_cast<float*>(smem + SL::headw);
@@ -94,6 +100,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
 
   // ---------------- one-time setup
   for (int i = tid; i < G::ActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0, 0, 0, 0);
+  if (X3)
+    for (int i = tid; i < G::ActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(s_act_lo)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < n_layers * kC; i += kThreads) s_bias[i] = W.bias[i];
   for (int i = tid; i < 3 * kC; i += kThreads) s_headw[i] = W.head_w[i];
   if (tid == 0) {
@@ -117,16 +125,19 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     if (lane == 0) {
       uint32_t it = 0;
       for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(W.conv_hi);
+        size_t off = 0;  // byte offset into the packed conv weights (same layout for the hi and lo buffers)
         for (int l = 0; l < n_layers; ++l) {
-          const uint32_t bytes = l == 0 ? kStemStageBytes : kStageBytes;
-          for (int t = 0; t < 9; ++t, ++it) {
+          const int n_st = (X3 && l > 0) ? 18 : 9;  // stages in this layer (X3: half taps)
+          const uint32_t part = l == 0 ? kStemStageBytes : (X3 ? kStageBytes / 2 : kStageBytes);
+          for (int st = 0; st < n_st; ++st, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(&bar_empty[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&bar_full[s], bytes);
-            bulk_g2s(s_w + s * kStageBytes, src, bytes, &bar_full[s]);
-            src += bytes;
+            mbar_arrive_expect_tx(&bar_full[s], X3 ? 2 * part : part);
+            bulk_g2s(s_w + s * kStageBytes, reinterpret_cast<const uint8_t*>(W.conv_hi) + off, part, &bar_full[s]);
+            if (X3)
+              bulk_g2s(s_w + s * kStageBytes + part, reinterpret_cast<const uint8_t*>(W.conv_lo) + off, part, &bar_full[s]);
+            off += part;
           }
         }
       }
@@ -154,13 +165,16 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
           act_phase ^= 1u;
           tc_fence_after_sync();
           if (W.dbg) dbg_act_wait += clock64() - t_a0;
-          for (int t = 0; t < 9; ++t, ++it) {
+          const int n_st = (X3 && l > 0) ? 18 : 9;
+          for (int st = 0; st < n_st; ++st, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             const long long t_f0 = W.dbg ? clock64() : 0;
             mbar_wait(&bar_full[s], ph);
             tc_fence_after_sync();
             if (W.dbg) dbg_full_wait += clock64() - t_f0;
+            const int t = (X3 && l > 0) ? st >> 1 : st;   // tap
+            const int kh = (X3 && l > 0) ? st & 1 : 0;    // which half of the 128 input channels (X3 only)
             const int shift = (t / 3 - 1) * G::S + (t % 3 - 1);
             const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + s * kStageBytes), kC * 16u);
             if (elect_one()) {
@@ -168,17 +182,32 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
               for (int tile = 0; tile < kTiles; ++tile) {
                 const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
                 const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);  // 16 B per row
-                if (l == 0) {
-                  umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, t > 0 ? 1u : 0u);
-                } else {
-                  umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || t > 0) ? 1u : 0u);
+                if (!X3) {
+                  if (l == 0) {
+                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, t > 0 ? 1u : 0u);
+                  } else {
+                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || t > 0) ? 1u : 0u);
 #pragma unroll
-                  for (int j = 1; j < kC / 16; ++j)
-                    umma_f16_ss_lohi(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u);
+                    for (int j = 1; j < kC / 16; ++j)
+                      umma_f16_ss_lohi(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u);
+                  }
+                } else {
+                  // hi/lo split: the lo activations live act_pad bytes above the hi ones, the lo weights `part`
+                  // bytes above the hi weights inside the stage
+                  constexpr uint32_t kALoOff = (uint32_t)SL::act_pad >> 4;
+                  const uint32_t w_lo_off = (l == 0 ? (uint32_t)kStemStageBytes : (uint32_t)kStageBytes / 2u) >> 4;
+                  const int nk = l == 0 ? 1 : 4;
+                  const uint32_t a0 = a_lo + (uint32_t)(kh * 4) * kAStep;
+                  for (int j = 0; j < nk; ++j) {
+                    const uint32_t aj = a0 + (uint32_t)j * kAStep, bj = b_lo0 + (uint32_t)j * kBStep;
+                    umma_f16_ss_lohi(d_tmem, aj, bj, desc_hi, idesc, (residual || st > 0 || j > 0) ? 1u : 0u);
+                    umma_f16_ss_lohi(d_tmem, aj, bj + w_lo_off, desc_hi, idesc, 1u);
+                    umma_f16_ss_lohi(d_tmem, aj + kALoOff, bj, desc_hi, idesc, 1u);
+                  }
                 }
               }
               umma_commit(&bar_empty[s]);
-              if (t == 8) umma_commit(bar_acc);
+              if (st == n_st - 1) umma_commit(bar_acc);
             }
             __syncwarp();
           }
@@ -227,6 +256,10 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         }
         *reinterpret_cast<uint4*>(s_act + row_off) = c0;
         *reinterpret_cast<uint4*>(s_act + chunk_stride + row_off) = make_uint4(0, 0, 0, 0);
+        if (X3) {  // {0,1} planes are exact in fp16: low parts are zero
+          *reinterpret_cast<uint4*>(s_act_lo + row_off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(s_act_lo + chunk_stride + row_off) = make_uint4(0, 0, 0, 0);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -272,6 +305,18 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
               h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
               pk.w = *reinterpret_cast<uint32_t*>(&h);
               *reinterpret_cast<uint4*>(s_act + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pk;
+              if (X3) {  // low parts: fp16(y - fp16(y))
+                uint4 pl;
+                const __half2* hh = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(hh[e]);
+                  const __half2 l2 = __floats2half2_rn(__uint_as_float(v[cc * 8 + 2 * e]) - f.x,
+                                                       __uint_as_float(v[cc * 8 + 2 * e + 1]) - f.y);
+                  reinterpret_cast<uint32_t*>(&pl)[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                *reinterpret_cast<uint4*>(s_act_lo + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pl;
+              }
             }
             if (to_b) tmem_st32(acc_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
           } else {
@@ -401,20 +446,21 @@ __global__ void pack_states_kernel(const float* __restrict__ st, int n, int B, i
   }
 }
 
-template <int B, int STAGES>
+template <int B, int STAGES, bool X3>
 cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
                            float* value, int num_sms, cudaStream_t s) {
-  using SL = SmemLayout<B, STAGES>;
+  using SL = SmemLayout<B, STAGES, X3>;
+  static_assert(SL::total <= 232448, "tower kernel exceeds 227 KB of shared memory");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tower_kernel<B, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
+    cudaError_t e = cudaFuncSetAttribute(tower_kernel<B, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int max_pass = (n_max + Geo<B>::GPC - 1) / Geo<B>::GPC;
   const int grid = max_pass < num_sms ? max_pass : num_sms;
   if (grid <= 0) return cudaSuccess;
-  tower_kernel<B, STAGES><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
+  tower_kernel<B, STAGES, X3><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
   return cudaGetLastError();
 }
 
@@ -423,9 +469,12 @@ cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_
 cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr, int n_max,
                          float* policy, float* value, int num_sms, cudaStream_t s) {
   if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
-  (void)precision;
-  if (B == 9) return launch_tower_t<9, 4>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-  if (B == 15) return launch_tower_t<15, 4>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (precision == AO_NN_FP16X3) {
+    if (B == 9) return launch_tower_t<9, 2, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    return cudaErrorInvalidValue;  // 15x15 split mode does not fit 227 KB of smem with this tiling (round 2)
+  }
+  if (B == 9) return launch_tower_t<9, 4, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (B == 15) return launch_tower_t<15, 4, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
   return cudaErrorInvalidValue;
 }
 

@@ -202,3 +202,33 @@ def test_facade_search_tree_reuse_vs_oracle(cabi):
             continue  # same root again: reused, re-noised
         root = root + (int(order[0]), int(order[1]))  # own move + a reply that was visited
     eng.close()
+
+
+def test_tower_split_precision_on_hard_weights(cabi):
+    """Weights scaled so that single-pass fp16 operands miss 1e-4 (like the shipped trained checkpoint):
+    the hi/lo split mode (AO_NN_FP16X3: a_hi*w_hi + a_hi*w_lo + a_lo*w_hi) must meet the tolerance."""
+    B = 9
+    sd = pvnet_ref.make_state_dict(5, 10, 5, 128, B, bn_jitter=True, gain=2.0)
+    rs = np.random.RandomState(0)
+    ids = [(0,) + tuple(int(a) for a in rs.permutation(81)[:rs.randint(0, 60)]) for _ in range(65)]
+    states = np.stack([O.get_state_pt(i, B, 5) for i in ids]).astype(np.float32)
+    pr, vr = pvnet_ref.pvnet_forward(sd, torch.from_numpy(states))
+    err = {}
+    for mode in (cabi.AO_NN_FP16, cabi.AO_NN_FP16X3):
+        eng = cabi.Engine(board_size=B, num_mcts=8, max_games=80, nn_precision=mode)
+        eng.load_state_dict(sd)
+        p, v = eng.nn_forward(states)
+        err[mode] = (float(np.abs(p - pr.numpy()).max()), float(np.abs(v - vr.numpy()).max()))
+        eng.close()
+    assert max(err[cabi.AO_NN_FP16X3]) < TOL, err
+    assert max(err[cabi.AO_NN_FP16]) > TOL, err  # documents why the split mode exists
+
+
+def test_selfplay_split_precision_runs(cabi):
+    sd = pvnet_ref.make_state_dict(0, 10, 5, 128, 9)
+    eng = cabi.Engine(board_size=9, num_mcts=32, max_games=16, seed=8, nn_precision=cabi.AO_NN_FP16X3)
+    eng.load_state_dict(sd)
+    eng.selfplay_begin(16)
+    st = eng.selfplay_rounds(200)
+    assert st["errors"] == 0 and st["sims"] >= 16 * 150
+    eng.close()

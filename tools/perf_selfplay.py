@@ -15,9 +15,10 @@ ap.add_argument("--sims", type=int, default=400)
 ap.add_argument("--rounds", type=int, default=100)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--node-cap", type=int, default=0)
+ap.add_argument("--x3", action="store_true")
 a = ap.parse_args()
 
-eng = _cabi.Engine(board_size=a.board, num_mcts=a.sims, max_games=a.games, seed=1, node_cap=a.node_cap)
+eng = _cabi.Engine(board_size=a.board, num_mcts=a.sims, max_games=a.games, seed=1, node_cap=a.node_cap, nn_precision=1 if a.x3 else 0)
 eng.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, a.board))
 eng.selfplay_begin(a.games)
 prev = eng.selfplay_rounds(20)
