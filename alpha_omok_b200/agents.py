@@ -176,14 +176,16 @@ class BatchedZeroAgent(_EngineOwner):
         if self._engine is not None:
             self._engine.games_reset(self._ids, keys=(self._ids + first_key).astype(np.uint32))
 
-    def search(self, root_ids):
+    def search(self, root_ids, game_ids=None):
+        """root_ids[i] is searched in engine slot game_ids[i] (default: slot i); each slot keeps its own tree."""
         eng = self._ensure_engine()
-        visits, priors, real = eng.search(self._ids[:len(root_ids)], root_ids)
+        ids = self._ids[:len(root_ids)] if game_ids is None else np.ascontiguousarray(game_ids, np.int32)
+        visits, priors, real = eng.search(ids, root_ids)
         self.visit, self.policy, self.is_real_root = visits.astype("float"), priors, real.astype(bool)
         return visits, priors
 
-    def get_pi(self, root_ids, taus):
-        visits, _ = self.search(root_ids)
+    def get_pi(self, root_ids, taus, game_ids=None):
+        visits, _ = self.search(root_ids, game_ids)
         pis = visits / visits.sum(axis=1, keepdims=True)
         for i, tau in enumerate(np.broadcast_to(taus, (len(root_ids),))):
             if tau == 0:

@@ -1,0 +1,57 @@
+"""Batched arena: many concurrent matches between two agents, the B200 twin of eval_main.main's match loop
+(eval_main.py:204-333; `Evaluator.get_action` :153-170).  Each side owns its own search trees (one engine slot per
+match), ZeroAgents search with noise=False and tau=0 and pick `utils.argmax_onehot(pi)`, colours alternate by match
+parity (eval_main.py:233,316).  ELO bookkeeping and the web dashboard feed stay out of scope."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi, agents, utils
+
+
+def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, num_mcts=800, inplanes=5, seed=0,
+                 enemy="zero", max_plies=None):
+    """player: ZeroAgent(player_model). enemy: 'zero' -> ZeroAgent(enemy_model), 'random' -> RandomAgent.
+    Returns dict(player_win, enemy_win, draw, black_win, white_win, plies)."""
+    B, A = board_size, board_size * board_size
+    sides = {}
+    sides["player"] = agents.BatchedZeroAgent(B, num_mcts, inplanes, n_matches, noise=False, seed=seed)
+    sides["player"].model = player_model
+    if enemy == "zero":
+        sides["enemy"] = agents.BatchedZeroAgent(B, num_mcts, inplanes, n_matches, noise=False, seed=seed + 1)
+        sides["enemy"].model = enemy_model
+    roots = [(0,) for _ in range(n_matches)]
+    boards = np.zeros((n_matches, A), np.int8)
+    winner = np.zeros(n_matches, np.int32)  # 0 running
+    player_is_black = (np.arange(n_matches) % 2) == 0
+    ply = 0
+    while (winner == 0).any() and (max_plies is None or ply < max_plies):
+        black_to_move = ply % 2 == 0
+        active = np.flatnonzero(winner == 0)
+        for name in ("player", "enemy"):
+            mine = active[(player_is_black[active] == black_to_move) == (name == "player")]
+            if len(mine) == 0:
+                continue
+            if name == "enemy" and enemy == "random":
+                acts = []
+                for m in mine:  # RandomAgent.get_pi + argmax_onehot (agents.py:637-657, eval_main.py:166-168)
+                    empty = (boards[m] == 0).astype("float")
+                    acts.append(int(utils.argmax_onehot(empty / empty.sum())[1]))
+            else:
+                pis = sides[name].get_pi([roots[m] for m in mine], 0, game_ids=mine)
+                acts = [int(np.argmax(pi)) for pi in pis]  # pi is already the tie-broken one-hot
+            for m, a in zip(mine, acts):
+                roots[m] = roots[m] + (a,)
+                boards[m, a] = 1 if black_to_move else -1
+        w = _cabi.check_win_batch(boards[active], B)
+        winner[active] = w
+        ply += 1
+    res = dict(player_win=0, enemy_win=0, draw=0, black_win=int((winner == 1).sum()), white_win=int((winner == 2).sum()),
+               plies=[len(r) - 1 for r in roots], unfinished=int((winner == 0).sum()))
+    for m in range(n_matches):
+        if winner[m] == 3:
+            res["draw"] += 1
+        elif winner[m] in (1, 2):
+            black_won = winner[m] == 1
+            res["player_win" if black_won == bool(player_is_black[m]) else "enemy_win"] += 1
+    return res

@@ -14,6 +14,13 @@ from oracle import omok_oracle as O
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_library_exports_every_declared_symbol():
     from alpha_omok_b200 import _cabi
     lib = _cabi.lib()
@@ -135,7 +142,7 @@ def test_allgather_records_gloo_world2(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(GLOO_WORKER.format(root=ROOT))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29511", str(script)]
+           "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout

@@ -93,3 +93,18 @@ def test_replay_records_device_roundtrip():
     assert np.array_equal(mem[k0 - 1][0], O.get_state_pt((0,) + tuple(int(a) for a in moves[0, :k0 - 1]), B, 5))
     assert np.allclose(mem[0][1], visits[0, 0] / visits[0, 0].sum())
     eng.close()
+
+
+def test_arena_batched_matches():
+    """config 5 shape at toy size: two ZeroAgents with different weights, alternating colours, own trees (2-ply root
+    advances = the arena's reused-root pattern); also the RandomAgent enemy of eval_main.py:70-72"""
+    from alpha_omok_b200 import arena, model
+    np.random.seed(1)
+    a, b = model.PVNet(10, 5, 128, 9), model.PVNet(10, 5, 128, 9)
+    a.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, 9), strict=False)
+    b.load_state_dict(pvnet_ref.make_state_dict(1, 10, 5, 128, 9), strict=False)
+    res = arena.play_matches(a, b, n_matches=12, num_mcts=40, seed=3)
+    assert res["unfinished"] == 0 and res["player_win"] + res["enemy_win"] + res["draw"] == 12
+    assert res["black_win"] + res["white_win"] + res["draw"] == 12 and min(res["plies"]) >= 9
+    res = arena.play_matches(a, None, n_matches=8, num_mcts=60, seed=3, enemy="random")
+    assert res["unfinished"] == 0 and res["player_win"] >= 6  # search beats uniform random play
