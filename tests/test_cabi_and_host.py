@@ -134,7 +134,8 @@ games = [replay.shard_games(10, r, world) for r in range(world)]
 assert sorted(sum(games, [])) == list(range(10))
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank%dok\n" % rank)
+sys.stdout.flush()
 """
 
 
@@ -145,4 +146,4 @@ def test_allgather_records_gloo_world2(tmp_path):
            "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+    assert "rank0ok" in res.stdout and "rank1ok" in res.stdout, res.stdout

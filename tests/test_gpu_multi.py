@@ -46,7 +46,8 @@ if rank == 0:
     assert sum(result.values()) == world * G and len(mem) > 0
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank%dok\n" % rank)
+sys.stdout.flush()
 """
 
 
@@ -58,4 +59,4 @@ def test_nccl_replay_allgather_two_gpus(tmp_path):
            "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+    assert "rank0ok" in res.stdout and "rank1ok" in res.stdout, res.stdout
