@@ -125,20 +125,34 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     if (lane == 0) {
       uint32_t it = 0;
       for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-        size_t off = 0;  // byte offset into the packed conv weights (same layout for the hi and lo buffers)
+        size_t off = 0;  // byte offset of the layer inside the packed conv weights (hi and lo buffers share the layout)
+        const uint8_t* w_hi = reinterpret_cast<const uint8_t*>(W.conv_hi);
+        const uint8_t* w_lo = reinterpret_cast<const uint8_t*>(W.conv_lo);
         for (int l = 0; l < n_layers; ++l) {
-          const int n_st = (X3 && l > 0) ? 18 : 9;  // stages in this layer (X3: half taps)
-          const uint32_t part = l == 0 ? kStemStageBytes : (X3 ? kStageBytes / 2 : kStageBytes);
+          // stages of this layer. plain: 9 taps. X3: stem 9 x [hi|lo]; residual layers 18 half-tap [hi|lo] stages
+          // (the small lo-terms are accumulated first, see the MMA issuer) followed by 9 full-tap hi stages.
+          const int n_st = !X3 ? 9 : (l == 0 ? 9 : 27);
+          const uint32_t layer_bytes = l == 0 ? 9u * kStemStageBytes : 9u * kStageBytes;
           for (int st = 0; st < n_st; ++st, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(&bar_empty[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&bar_full[s], X3 ? 2 * part : part);
-            bulk_g2s(s_w + s * kStageBytes, reinterpret_cast<const uint8_t*>(W.conv_hi) + off, part, &bar_full[s]);
-            if (X3)
-              bulk_g2s(s_w + s * kStageBytes + part, reinterpret_cast<const uint8_t*>(W.conv_lo) + off, part, &bar_full[s]);
-            off += part;
+            uint8_t* dst = s_w + s * kStageBytes;
+            if (!X3) {
+              const uint32_t part = l == 0 ? kStemStageBytes : kStageBytes;
+              mbar_arrive_expect_tx(&bar_full[s], part);
+              bulk_g2s(dst, w_hi + off + (size_t)st * part, part, &bar_full[s]);
+            } else if (l == 0 || st < 18) {
+              const uint32_t part = l == 0 ? kStemStageBytes : kStageBytes / 2;
+              mbar_arrive_expect_tx(&bar_full[s], 2 * part);
+              bulk_g2s(dst, w_hi + off + (size_t)st * part, part, &bar_full[s]);
+              bulk_g2s(dst + part, w_lo + off + (size_t)st * part, part, &bar_full[s]);
+            } else {
+              mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+              bulk_g2s(dst, w_hi + off + (size_t)(st - 18) * kStageBytes, kStageBytes, &bar_full[s]);
+            }
           }
+          off += layer_bytes;
         }
       }
     }
@@ -158,14 +172,16 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       const long long dbg_t0 = W.dbg ? clock64() : 0;
       for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
         for (int l = 0; l < n_layers; ++l) {
-          const bool to_b = (l & 1) == 0;           // stem and conv2 accumulate in accB
-          const bool residual = to_b && l > 0;      // accB already holds the block input x
+          // plain mode: stem and conv2 accumulate in accB, which already holds the block input x (residual);
+          // X3 mode: every layer accumulates in a fresh accA and accB is only the epilogue's fp32 stash of x
+          const bool to_b = !X3 && (l & 1) == 0;
+          const bool residual = to_b && l > 0;
           const long long t_a0 = W.dbg ? clock64() : 0;
           mbar_wait(bar_act, act_phase);
           act_phase ^= 1u;
           tc_fence_after_sync();
           if (W.dbg) dbg_act_wait += clock64() - t_a0;
-          const int n_st = (X3 && l > 0) ? 18 : 9;
+          const int n_st = !X3 ? 9 : (l == 0 ? 9 : 27);
           for (int st = 0; st < n_st; ++st, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
@@ -173,8 +189,9 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
             mbar_wait(&bar_full[s], ph);
             tc_fence_after_sync();
             if (W.dbg) dbg_full_wait += clock64() - t_f0;
-            const int t = (X3 && l > 0) ? st >> 1 : st;   // tap
-            const int kh = (X3 && l > 0) ? st & 1 : 0;    // which half of the 128 input channels (X3 only)
+            const bool lo_phase = X3 && l > 0 && st < 18;
+            const int t = !X3 || l == 0 ? st : (lo_phase ? st >> 1 : st - 18);  // tap
+            const int kh = lo_phase ? st & 1 : 0;  // which half of the 128 input channels
             const int shift = (t / 3 - 1) * G::S + (t % 3 - 1);
             const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + s * kStageBytes), kC * 16u);
             if (elect_one()) {
@@ -192,17 +209,26 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
                       umma_f16_ss_lohi(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u);
                   }
                 } else {
-                  // hi/lo split: the lo activations live act_pad bytes above the hi ones, the lo weights `part`
-                  // bytes above the hi weights inside the stage
-                  constexpr uint32_t kALoOff = (uint32_t)SL::act_pad >> 4;
-                  const uint32_t w_lo_off = (l == 0 ? (uint32_t)kStemStageBytes : (uint32_t)kStageBytes / 2u) >> 4;
-                  const int nk = l == 0 ? 1 : 4;
-                  const uint32_t a0 = a_lo + (uint32_t)(kh * 4) * kAStep;
-                  for (int j = 0; j < nk; ++j) {
-                    const uint32_t aj = a0 + (uint32_t)j * kAStep, bj = b_lo0 + (uint32_t)j * kBStep;
-                    umma_f16_ss_lohi(d_tmem, aj, bj, desc_hi, idesc, (residual || st > 0 || j > 0) ? 1u : 0u);
-                    umma_f16_ss_lohi(d_tmem, aj, bj + w_lo_off, desc_hi, idesc, 1u);
-                    umma_f16_ss_lohi(d_tmem, aj + kALoOff, bj, desc_hi, idesc, 1u);
+                  // The tensor core truncates (does not round) its fp32 accumulation: ~1.3 ulp(acc) lost per MMA
+                  // (tools/probe_accum.py).  So the lo-terms a_hi*w_lo + a_lo*w_hi are accumulated FIRST, while the
+                  // accumulator is still ~2^-11 of its final magnitude, and only the hi*hi MMAs run at full magnitude.
+                  constexpr uint32_t kALoOff = (uint32_t)SL::act_pad >> 4;  // lo activations sit above the hi ones
+                  if (l == 0) {       // stem: inputs are exact ({0,1}), a_lo == 0
+                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0 + ((uint32_t)kStemStageBytes >> 4), desc_hi, idesc, st > 0 ? 1u : 0u);
+                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, 1u);
+                  } else if (lo_phase) {
+                    const uint32_t a0 = a_lo + (uint32_t)(kh * 4) * kAStep;
+                    constexpr uint32_t kWLoOff = ((uint32_t)kStageBytes / 2u) >> 4;  // [hi 16 KB | lo 16 KB]
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const uint32_t aj = a0 + (uint32_t)j * kAStep, bj = b_lo0 + (uint32_t)j * kBStep;
+                      umma_f16_ss_lohi(d_tmem, aj, bj + kWLoOff, desc_hi, idesc, (st > 0 || j > 0) ? 1u : 0u);
+                      umma_f16_ss_lohi(d_tmem, aj + kALoOff, bj, desc_hi, idesc, 1u);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < kC / 16; ++j)
+                      umma_f16_ss_lohi(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u);
                   }
                 }
               }
@@ -275,10 +301,18 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         acc_phase ^= 1u;
         tc_fence_after_sync();
         if (dbg_on) dbg_acc_wait += clock64() - t_w0;
-        const uint32_t acc_addr = lane_addr + (to_b ? 128u : 0u);
+        const uint32_t stash_addr = lane_addr + 128u;                          // accB: fp32 block input x
+        const uint32_t acc_addr = (!X3 && to_b) ? stash_addr : lane_addr;      // X3 accumulates in accA only
         // 4 chunks of 32 accumulator columns, TMEM loads double-buffered against the per-chunk math
         auto process = [&](uint32_t (&v)[32], const int qd) {
           const float4* b4 = reinterpret_cast<const float4*>(bias + qd * 32);
+          if (X3 && to_b && l > 0) {  // residual add in fp32 round-to-nearest: out = conv2 + x (model.py:29)
+            uint32_t xr[32];
+            tmem_ld32(stash_addr + (uint32_t)(qd * 32), xr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(xr[j]));
+          }
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bb = b4[j4];
@@ -318,7 +352,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
                 *reinterpret_cast<uint4*>(s_act_lo + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pl;
               }
             }
-            if (to_b) tmem_st32(acc_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
+            if (to_b) tmem_st32(stash_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
           } else {
             // heads' 1x1 convolutions (model.py:44-46, 64-66) straight from the fp32 tower output
 #pragma unroll

@@ -232,3 +232,43 @@ def test_selfplay_split_precision_runs(cabi):
     st = eng.selfplay_rounds(200)
     assert st["errors"] == 0 and st["sims"] >= 16 * 150
     eng.close()
+
+
+def _trained_state_dict():
+    z = load("trained_9x9_180927")  # the reference's shipped checkpoint (data/180927_9400_297233_step_model.pickle)
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def test_tower_trained_checkpoint_split_precision(cabi):
+    """the shipped trained 9x9 net (config 5's player): hi/lo split tower within 1e-4 of model.PVNet fp32"""
+    B = 9
+    sd = _trained_state_dict()
+    rs = np.random.RandomState(0)
+    ids = [(0,) + tuple(int(a) for a in rs.permutation(81)[:rs.randint(0, 50)]) for _ in range(128)]
+    states = np.stack([O.get_state_pt(i, B, 5) for i in ids]).astype(np.float32)
+    pr, vr = pvnet_ref.pvnet_forward(sd, torch.from_numpy(states))
+    eng = cabi.Engine(board_size=B, num_mcts=8, max_games=128, nn_precision=cabi.AO_NN_FP16X3)
+    eng.load_state_dict(sd)
+    p, v = eng.nn_forward(states)
+    eng.close()
+    assert np.abs(p - pr.numpy()).max() < TOL and np.abs(v - vr.numpy()).max() < TOL
+
+
+def test_arena_trained_vs_random_agent():
+    """config 5 at toy size: trained ZeroAgent (split precision) against RandomAgent, alternating colours"""
+    from alpha_omok_b200 import agents, arena, model
+    np.random.seed(0)
+    net = model.PVNet(10, 5, 128, 9)
+    net.load_state_dict(_trained_state_dict(), strict=False)
+    orig = agents.BatchedZeroAgent.__init__
+
+    def patched(self, *a, **k):  # the arena's engines run the split-precision tower for the trained net
+        k["engine_kwargs"] = {"nn_precision": 1}
+        orig(self, *a, **k)
+
+    agents.BatchedZeroAgent.__init__ = patched
+    try:
+        res = arena.play_matches(net, None, n_matches=8, num_mcts=50, seed=1, enemy="random")
+    finally:
+        agents.BatchedZeroAgent.__init__ = orig
+    assert res["unfinished"] == 0 and res["player_win"] == 8, res
