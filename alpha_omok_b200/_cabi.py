@@ -29,7 +29,7 @@ EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
     "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
     "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
-    "ao_encode_state", "ao_legal_actions", "ao_umma_probe",
+    "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked",
 ]
 
 _lib = None
@@ -72,6 +72,7 @@ def lib():
     L.ao_encode_state.argtypes = [vp, vp, i32, i32, vp]
     L.ao_legal_actions.argtypes = [vp, vp, i32, i32, vp]
     L.ao_umma_probe.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]
+    L.ao_umma_probe_masked.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp]
     for name in EXPORTS:
         if name != "ao_last_error":
             getattr(L, name).restype = C.c_int

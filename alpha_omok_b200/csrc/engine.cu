@@ -270,9 +270,11 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
     for (int co = 0; co < C; ++co) {
       const float s = bn.g[co] / std::sqrt(bn.v[co] + 1e-5f);
       bias[(size_t)l * C + co] = bn.b[co] - bn.m[co] * s;
-      for (int t = 0; t < 9; ++t)
+      for (int ti = 0; ti < 9; ++ti)  // packed tap order: centre first (its MMA has no disabled rows), then row-major
         for (int ci = 0; ci < kpad; ++ci) {
-          const float v = ci < ci_n ? w[((size_t)co * ci_n + ci) * 9 + t] * s : 0.f;
+          const int t = ti;  // storage slot
+          const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);
+          const float v = ci < ci_n ? w[((size_t)co * ci_n + ci) * 9 + tap] * s : 0.f;
           const __half vh = __float2half_rn(v);
           const size_t idx = off + ((size_t)t * (kpad / 8) + ci / 8) * C * 8 + (size_t)co * 8 + (ci % 8);
           hi[idx] = vh;

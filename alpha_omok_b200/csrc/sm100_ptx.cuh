@@ -168,6 +168,20 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lb
 __device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);  // SBO, descriptor version 1 (bit 46), no swizzle
 }
+// Same with a disable-output-lane mask: bit r of {m0..m3} set => row (TMEM lane) r of D is NOT updated by this MMA.
+// Used to drop the contributions of 3x3 taps that fall off the board (no zero padding rows/columns needed).
+__device__ __forceinline__ void umma_f16_ss_lohi_masked(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                        uint32_t idesc, uint32_t accumulate, uint32_t m0, uint32_t m1,
+                                                        uint32_t m2, uint32_t m3) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, {%6, %7, %8, %9}, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
 // one lane of a converged warp (warp-uniform code keeps descriptors in uniform registers)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -35,11 +35,14 @@ constexpr int kMaxLayers = 21;            // 1 + 2*10 blocks (bias table lives i
 
 template <int B>
 struct Geo {
-  static constexpr int S = B + 1;
+  // Board cells are packed densely: row R of the CTA's position stream = cell (R % A) of game (R / A), row stride
+  // S = B.  Taps that fall off the board are dropped with tcgen05.mma's disable-output-lane masks instead of zero
+  // padding, so 3 games of 9x9 (243 rows) fill the two 128-row tiles to 95 % (1 game of 15x15: 88 %).
+  static constexpr int S = B;
   static constexpr int A = B * B;
-  static constexpr int GameRows = S * (B + 1);
+  static constexpr int GameRows = A;
   static constexpr int GPC = (kTiles * kTileRows) / GameRows;  // games per CTA pass
-  static constexpr int Halo = ((S + 1 + 7) / 8) * 8;
+  static constexpr int Halo = ((S + 1 + 7) / 8) * 8;           // rows addressed (never used) beyond the stream
   static constexpr int Rows = Halo + kTiles * kTileRows + Halo;
   static constexpr int ActBytes = 16 * Rows * 16;
   static_assert(GPC >= 1, "board too large for a 256-row CTA tile");
@@ -61,7 +64,8 @@ struct SmemLayout {
   static constexpr int logits = feat + G::GPC * 3 * G::A * 4;           // [GPC][A]
   static constexpr int hidden = logits + G::GPC * G::A * 4;             // [GPC][128]
   static constexpr int red = hidden + G::GPC * kC * 4;                  // [GPC][2]
-  static constexpr int bars = (red + G::GPC * 2 * 4 + 15) / 16 * 16;    // mbarriers
+  static constexpr int masks = (red + G::GPC * 2 * 4 + 15) / 16 * 16;   // [kTiles][9 taps][4] disable-output-lane words
+  static constexpr int bars = masks + kTiles * 9 * 4 * 4;               // mbarriers
   static constexpr int total = bars + (2 * STAGES + 2) * 8 + 16;
 };
 
@@ -89,6 +93,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
   float* s_logits = reinterpret_cast<float*>(smem + SL::logits);
   float* s_hidden = reinterpret_cast<float*>(smem + SL::hidden);
   float* s_red = reinterpret_cast<float*>(smem + SL::red);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + SL::masks);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SL::bars);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_act = bar_empty + STAGES;   // epilogue -> MMA: operand written, accumulators drained
@@ -104,6 +109,19 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     for (int i = tid; i < G::ActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(s_act_lo)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < n_layers * kC; i += kThreads) s_bias[i] = W.bias[i];
   for (int i = tid; i < 3 * kC; i += kThreads) s_headw[i] = W.head_w[i];
+  // disable-output-lane masks: bit r of s_mask[tile][tap] set <=> for stream row tile*128+r the tap's source cell is
+  // off the board (the MMA then leaves that accumulator row untouched = contributes zero)
+  for (int i = tid; i < kTiles * 9 * 4; i += kThreads) {
+    const int tile = i / 36, tap = (i / 4) % 9, word = i % 4;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int pos = (tile * kTileRows + word * 32 + b) % G::A;
+      const int y = pos / B + dy, x = pos % B + dx;
+      if (y < 0 || y >= B || x < 0 || x >= B) m |= 1u << b;
+    }
+    s_mask[i] = m;
+  }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bar_full[s], 1);
@@ -190,23 +208,28 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
             tc_fence_after_sync();
             if (W.dbg) dbg_full_wait += clock64() - t_f0;
             const bool lo_phase = X3 && l > 0 && st < 18;
-            const int t = !X3 || l == 0 ? st : (lo_phase ? st >> 1 : st - 18);  // tap
+            // the weights are packed with the centre tap first: it has no disabled rows, so the first MMA of a fresh
+            // accumulation (accumulate = 0) writes every accumulator row
+            const int ti = !X3 || l == 0 ? st : (lo_phase ? st >> 1 : st - 18);  // position in the packed tap order
+            const int t = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);                 // tap = (dy+1)*3 + (dx+1)
             const int kh = lo_phase ? st & 1 : 0;  // which half of the 128 input channels
             const int shift = (t / 3 - 1) * G::S + (t % 3 - 1);
             const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + s * kStageBytes), kC * 16u);
             if (elect_one()) {
 #pragma unroll
               for (int tile = 0; tile < kTiles; ++tile) {
+                const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
+                const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
                 const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
                 const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);  // 16 B per row
                 if (!X3) {
                   if (l == 0) {
-                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, t > 0 ? 1u : 0u);
+                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, st > 0 ? 1u : 0u, m0, m1, m2, m3);
                   } else {
-                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || t > 0) ? 1u : 0u);
+                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || st > 0) ? 1u : 0u, m0, m1, m2, m3);
 #pragma unroll
                     for (int j = 1; j < kC / 16; ++j)
-                      umma_f16_ss_lohi(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u);
+                      umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u, m0, m1, m2, m3);
                   }
                 } else {
                   // The tensor core truncates (does not round) its fp32 accumulation: ~1.3 ulp(acc) lost per MMA
@@ -214,21 +237,21 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
                   // accumulator is still ~2^-11 of its final magnitude, and only the hi*hi MMAs run at full magnitude.
                   constexpr uint32_t kALoOff = (uint32_t)SL::act_pad >> 4;  // lo activations sit above the hi ones
                   if (l == 0) {       // stem: inputs are exact ({0,1}), a_lo == 0
-                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0 + ((uint32_t)kStemStageBytes >> 4), desc_hi, idesc, st > 0 ? 1u : 0u);
-                    umma_f16_ss_lohi(d_tmem, a_lo, b_lo0, desc_hi, idesc, 1u);
+                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0 + ((uint32_t)kStemStageBytes >> 4), desc_hi, idesc, st > 0 ? 1u : 0u, m0, m1, m2, m3);
+                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, 1u, m0, m1, m2, m3);
                   } else if (lo_phase) {
                     const uint32_t a0 = a_lo + (uint32_t)(kh * 4) * kAStep;
                     constexpr uint32_t kWLoOff = ((uint32_t)kStageBytes / 2u) >> 4;  // [hi 16 KB | lo 16 KB]
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const uint32_t aj = a0 + (uint32_t)j * kAStep, bj = b_lo0 + (uint32_t)j * kBStep;
-                      umma_f16_ss_lohi(d_tmem, aj, bj + kWLoOff, desc_hi, idesc, (st > 0 || j > 0) ? 1u : 0u);
-                      umma_f16_ss_lohi(d_tmem, aj + kALoOff, bj, desc_hi, idesc, 1u);
+                      umma_f16_ss_lohi_masked(d_tmem, aj, bj + kWLoOff, desc_hi, idesc, (st > 0 || j > 0) ? 1u : 0u, m0, m1, m2, m3);
+                      umma_f16_ss_lohi_masked(d_tmem, aj + kALoOff, bj, desc_hi, idesc, 1u, m0, m1, m2, m3);
                     }
                   } else {
 #pragma unroll
                     for (int j = 0; j < kC / 16; ++j)
-                      umma_f16_ss_lohi(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u);
+                      umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u, m0, m1, m2, m3);
                   }
                 }
               }
@@ -250,11 +273,10 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     // =========================================================== epilogue warps (256 threads)
     const int tile = tid >> 7, r = tid & 127;
     const int R = tile * kTileRows + r;          // logical row in the CTA's padded position stream
-    const int g_local = R / G::GameRows;
-    const int q = R % G::GameRows;
-    const int yy = q / G::S, xx = q % G::S;
-    const bool geo_valid = g_local < G::GPC && yy >= 1 && xx < B;
-    const int pos = (yy - 1) * B + xx;
+    const int g_local = R / G::A;                // game of the pass
+    const int pos = R % G::A;                    // cell
+    const int yy = pos / B, xx = pos % B;
+    const bool geo_valid = g_local < G::GPC;
     const uint32_t row_off = (uint32_t)(G::Halo + R) * 16u;
     const uint32_t chunk_stride = (uint32_t)G::Rows * 16u;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * 256);
@@ -272,9 +294,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         uint4 c0 = make_uint4(0, 0, 0, 0);
         if (valid) {
           const LeafIn* li = &in[g0 + g_local];
-          const int y = yy - 1;
-          const uint32_t b0 = (li->plane[0][y] >> xx) & 1u, b1 = (li->plane[1][y] >> xx) & 1u;
-          const uint32_t b2 = (li->plane[2][y] >> xx) & 1u, b3 = (li->plane[3][y] >> xx) & 1u;
+          const uint32_t b0 = (li->plane[0][yy] >> xx) & 1u, b1 = (li->plane[1][yy] >> xx) & 1u;
+          const uint32_t b2 = (li->plane[2][yy] >> xx) & 1u, b3 = (li->plane[3][yy] >> xx) & 1u;
           const uint32_t b4 = li->colour & 1u;
           c0.x = (b0 ? 0x3C00u : 0u) | (b1 ? 0x3C000000u : 0u);
           c0.y = (b2 ? 0x3C00u : 0u) | (b3 ? 0x3C000000u : 0u);
@@ -407,14 +428,16 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         logit = acc;
         s_logits[pg * G::A + po] = acc;
       }
-      const int vg = tid / kC, vj = tid % kC;      // value FC1: thread = (game, hidden unit)
-      if (vg < ng && vg < G::GPC) {
-        const float* f = s_feat + vg * 3 * G::A + 2 * G::A;
-        float acc = W.vfc1_b[vj];
-        const float* wt = W.vfc1_wT + vj;
+      for (int vi = tid; vi < G::GPC * kC; vi += kEpiThreads) {  // value FC1: (game, hidden unit)
+        const int vg = vi / kC, vj = vi % kC;
+        if (vg < ng) {
+          const float* f = s_feat + vg * 3 * G::A + 2 * G::A;
+          float acc = W.vfc1_b[vj];
+          const float* wt = W.vfc1_wT + vj;
 #pragma unroll 27
-        for (int k = 0; k < G::A; ++k) acc = fmaf(__ldg(wt + (size_t)k * kC), f[k], acc);
-        s_hidden[vg * kC + vj] = fmaxf(acc, 0.f) * W.vfc2_w[vj];
+          for (int k = 0; k < G::A; ++k) acc = fmaf(__ldg(wt + (size_t)k * kC), f[k], acc);
+          s_hidden[vg * kC + vj] = fmaxf(acc, 0.f) * W.vfc2_w[vj];
+        }
       }
       epi_bar_sync();
       if (warp < ng) {  // warp g: softmax statistics and the value of game g

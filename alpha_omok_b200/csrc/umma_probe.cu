@@ -27,7 +27,7 @@ struct ProbeSmem {
 __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const __half* __restrict__ act, int rows, const __half* __restrict__ wpacked,
                   const float* __restrict__ init, float* __restrict__ out, int row0, int ntaps,
-                  const int* __restrict__ shifts) {
+                  const int* __restrict__ shifts, const uint32_t* __restrict__ masks) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_act = smem;                                   // 16 * rows * 16 B
   uint32_t act_bytes = (uint32_t)(kChunks * rows * 16);
@@ -96,7 +96,12 @@ umma_probe_kernel(const __half* __restrict__ act, int rows, const __half* __rest
       for (int j = 0; j < kC / 16; ++j) {
         uint64_t da = ao::umma_desc_kmajor_noswz(a_base + (uint32_t)(2 * j) * lbo_a + a_row * 16u, lbo_a, 128u);
         uint64_t db = ao::umma_desc_kmajor_noswz(b_base + (uint32_t)(2 * j) * (kC * 16u), kC * 16u, 128u);
-        ao::umma_f16_ss(tmem, da, db, idesc, acc);
+        if (masks == nullptr) {
+          ao::umma_f16_ss(tmem, da, db, idesc, acc);
+        } else {  // per-tap disable-output-lane mask (4 x 32 bits)
+          ao::umma_f16_ss_lohi_masked(tmem, (uint32_t)da, (uint32_t)db, (uint32_t)(da >> 32), idesc, acc,
+                                      masks[4 * t + 0], masks[4 * t + 1], masks[4 * t + 2], masks[4 * t + 3]);
+        }
         acc = 1u;
       }
       ao::umma_commit(&ctl->empty[s]);
@@ -123,12 +128,20 @@ umma_probe_kernel(const __half* __restrict__ act, int rows, const __half* __rest
 }  // namespace
 
 // Host entry (C ABI). All pointers are HOST pointers; returns 0 or a negative cudaError.
+extern "C" int ao_umma_probe_masked(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init,
+                                    float* out, int row0, int ntaps, const int* shifts, const uint32_t* masks);
 extern "C" int ao_umma_probe(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init,
                              float* out, int row0, int ntaps, const int* shifts) {
+  return ao_umma_probe_masked(act_f16, rows, wpacked_f16, init, out, row0, ntaps, shifts, nullptr);
+}
+// masks: optional [ntaps][4] uint32 disable-output-lane masks (bit r set: output row r is not updated by that tap)
+extern "C" int ao_umma_probe_masked(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init,
+                                    float* out, int row0, int ntaps, const int* shifts, const uint32_t* masks) {
   if (rows < 128 || rows > 320 || ntaps < 1 || ntaps > 64) return -1;
   __half *d_act = nullptr, *d_w = nullptr;
   float *d_init = nullptr, *d_out = nullptr;
   int* d_sh = nullptr;
+  uint32_t* d_mk = nullptr;
   cudaError_t e;
 #define CK(x)                     \
   do {                            \
@@ -145,6 +158,10 @@ extern "C" int ao_umma_probe(const uint16_t* act_f16, int rows, const uint16_t* 
   CK(cudaMemcpy(d_act, act_f16, (size_t)rows * kC * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_w, wpacked_f16, (size_t)ntaps * kC * kC * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_sh, shifts, ntaps * sizeof(int), cudaMemcpyHostToDevice));
+  if (masks) {
+    CK(cudaMalloc(&d_mk, ntaps * 4 * sizeof(uint32_t)));
+    CK(cudaMemcpy(d_mk, masks, ntaps * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
   if (init) {
     CK(cudaMalloc(&d_init, 128 * kC * 4));
     CK(cudaMemcpy(d_init, init, 128 * kC * 4, cudaMemcpyHostToDevice));
@@ -152,12 +169,13 @@ extern "C" int ao_umma_probe(const uint16_t* act_f16, int rows, const uint16_t* 
   uint32_t act_bytes = ((uint32_t)(kChunks * rows * 16) + 1023u) & ~1023u;
   size_t smem = act_bytes + kStages * kStageBytes + sizeof(ProbeSmem) + 64;
   CK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_probe_kernel<<<1, 128, smem>>>(d_act, rows, d_w, d_init, d_out, row0, ntaps, d_sh);
+  umma_probe_kernel<<<1, 128, smem>>>(d_act, rows, d_w, d_init, d_out, row0, ntaps, d_sh, d_mk);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, d_out, 128 * kC * 4, cudaMemcpyDeviceToHost));
   cudaFree(d_act); cudaFree(d_w); cudaFree(d_out); cudaFree(d_sh);
   if (d_init) cudaFree(d_init);
+  if (d_mk) cudaFree(d_mk);
 #undef CK
   return 0;
 }

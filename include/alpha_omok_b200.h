@@ -118,6 +118,9 @@ int ao_legal_actions(const int16_t* ids, const int32_t* lens, int n, int board_s
 /* tcgen05 building-block probe (csrc/umma_probe.cu). */
 int ao_umma_probe(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init, float* out,
                   int row0, int ntaps, const int* shifts);
+/* same with per-tap disable-output-lane masks [ntaps][4] (bit r set: output row r is not updated by that tap) */
+int ao_umma_probe_masked(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init, float* out,
+                         int row0, int ntaps, const int* shifts, const uint32_t* masks);
 
 #ifdef __cplusplus
 }
