@@ -71,6 +71,35 @@ struct SmemLayout {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Pass k of this CTA. Full waves: GPC games in both tiles. A ragged last wave of r <= gridDim.x games is spread as
+// ONE game (one 128-row tile, half the MMA work) per CTA instead of ceil(r/GPC) full passes, so that e.g. 4096 games
+// of 9x9 cost 9 + ~0.55 pass times instead of 10.  All warp roles call this with the same arguments.
+template <int GPC, int A>
+__device__ __forceinline__ bool get_pass(int k, int n, int& g0, int& ng, int& ntiles) {
+  const int grid = (int)gridDim.x, b = (int)blockIdx.x;
+  const int per_wave = GPC * grid;
+  const int W = n / per_wave, r = n - W * per_wave;
+  if (k < W) {
+    g0 = (k * grid + b) * GPC;
+    ng = GPC;
+    ntiles = kTiles;
+    return true;
+  }
+  if (k > W || r == 0) return false;
+  if (GPC > 1 && A <= kTileRows && r <= grid) {
+    if (b >= r) return false;
+    g0 = W * per_wave + b;
+    ng = 1;
+    ntiles = 1;
+    return true;
+  }
+  g0 = W * per_wave + b * GPC;
+  if (g0 >= n) return false;
+  ng = min(GPC, n - g0);
+  ntiles = kTiles;
+  return true;
+}
+
 template <int B, int STAGES, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
@@ -81,8 +110,10 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
 
   int n = n_ptr ? *n_ptr : n_max;
   if (n > n_max) n = n_max;
-  const int n_pass = (n + G::GPC - 1) / G::GPC;
-  if ((int)blockIdx.x >= n_pass) return;
+  {
+    int g0_, ng_, nt_;
+    if (!get_pass<G::GPC, G::A>(0, n, g0_, ng_, nt_)) return;  // nothing to do for this CTA
+  }
 
   uint8_t* s_act = smem + SL::act;
   uint8_t* s_act_lo = smem + SL::act_lo;  // X3 only
@@ -142,7 +173,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     // =========================================================== weight producer (one lane)
     if (lane == 0) {
       uint32_t it = 0;
-      for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+      int g0, ng, ntiles;
+      for (int k = 0; get_pass<G::GPC, G::A>(k, n, g0, ng, ntiles); ++k) {
         size_t off = 0;  // byte offset of the layer inside the packed conv weights (hi and lo buffers share the layout)
         const uint8_t* w_hi = reinterpret_cast<const uint8_t*>(W.conv_hi);
         const uint8_t* w_lo = reinterpret_cast<const uint8_t*>(W.conv_lo);
@@ -188,7 +220,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       uint32_t it = 0, act_phase = 0;
       long long dbg_act_wait = 0, dbg_full_wait = 0;
       const long long dbg_t0 = W.dbg ? clock64() : 0;
-      for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+      int g0, ng, ntiles;
+      for (int k = 0; get_pass<G::GPC, G::A>(k, n, g0, ng, ntiles); ++k) {
         for (int l = 0; l < n_layers; ++l) {
           // plain mode: stem and conv2 accumulate in accB, which already holds the block input x (residual);
           // X3 mode: every layer accumulates in a fresh accA and accB is only the epilogue's fp32 stash of x
@@ -218,6 +251,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
             if (elect_one()) {
 #pragma unroll
               for (int tile = 0; tile < kTiles; ++tile) {
+                if (tile >= ntiles) break;  // one-game tail pass: tile 1 holds no board
                 const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
                 const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
                 const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
@@ -285,9 +319,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0;
     const long long dbg_e0 = dbg_on ? clock64() : 0;
 
-    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-      const int g0 = pass * G::GPC;
-      const int ng = min(G::GPC, n - g0);
+    int g0, ng, ntiles;
+    for (int k = 0; get_pass<G::GPC, G::A>(k, n, g0, ng, ntiles); ++k) {
       const bool valid = geo_valid && g_local < ng;
       // ---- input planes (utils.get_state_pt) -> channels 0..4 of chunk 0; chunk 1 = 0
       {
@@ -514,8 +547,7 @@ cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int max_pass = (n_max + Geo<B>::GPC - 1) / Geo<B>::GPC;
-  const int grid = max_pass < num_sms ? max_pass : num_sms;
+  const int grid = n_max < num_sms ? n_max : num_sms;  // see get_pass: up to one game per CTA in a ragged wave
   if (grid <= 0) return cudaSuccess;
   tower_kernel<B, STAGES, X3><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
   return cudaGetLastError();
