@@ -12,7 +12,7 @@ from . import _build
 
 AO_EVAL_PVNET, AO_EVAL_SYNTH = 0, 1
 AO_NOISE_DEVICE, AO_NOISE_TAPE = 0, 1
-AO_NN_FP16, AO_NN_FP16X3 = 0, 1
+AO_NN_FP16, AO_NN_FP16X3, AO_NN_FP16_1CTA = 0, 1, 2
 
 
 class AoConfig(C.Structure):

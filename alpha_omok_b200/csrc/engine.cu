@@ -50,7 +50,7 @@ struct ao_engine {
   bool weights_loaded;
   std::vector<void*> allocs;
   // weights (device)
-  __half *d_conv_hi, *d_conv_lo;
+  __half *d_conv_hi, *d_conv_lo, *d_conv_pair;
   float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
   // staging
   int32_t *d_ids, *d_lens, *d_real_root;
@@ -251,7 +251,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   const int n_layers = 1 + 2 * nb;
   const size_t stem_halves = (size_t)9 * 16 * C, res_halves = (size_t)9 * C * C;
   const size_t total_halves = stem_halves + (size_t)(n_layers - 1) * res_halves;
-  std::vector<__half> hi(total_halves), lo(total_halves);
+  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves);
   std::vector<float> bias((size_t)n_layers * C);
   size_t off = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -279,6 +279,8 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
           const size_t idx = off + ((size_t)t * (kpad / 8) + ci / 8) * C * 8 + (size_t)co * 8 + (ci % 8);
           hi[idx] = vh;
           lo[idx] = __float2half_rn(v - __half2float(vh));
+          // CTA-pair layout: per tap [rank = co / 64][k-chunk][co % 64][8]
+          pr[off + (((size_t)t * 2 + co / 64) * (kpad / 8) + ci / 8) * 64 * 8 + (size_t)(co % 64) * 8 + (ci % 8)] = vh;
         }
     }
     off += l == 0 ? stem_halves : res_halves;
@@ -316,6 +318,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
 #define EA(p, cnt) if ((rc = ealloc(h, &(p), (cnt))) != 0) return rc;
     EA(h->d_conv_hi, total_halves);
     EA(h->d_conv_lo, total_halves);
+    EA(h->d_conv_pair, total_halves);
     EA(h->d_bias, bias.size());
     EA(h->d_head_w, head_w.size());
     EA(h->d_head_b, 4);
@@ -329,6 +332,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   AO_CUDA(cudaStreamSynchronize(h->stream));
   AO_CUDA(cudaMemcpy(h->d_conv_hi, hi.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_conv_lo, lo.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_conv_pair, pr.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
@@ -338,7 +342,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   AO_CUDA(cudaMemcpy(h->d_vfc1_b, v1b, (size_t)C * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_vfc2_w, v2w, (size_t)C * 4, cudaMemcpyHostToDevice));
   ao::TowerWeights& tw = h->tw;
-  tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
+  tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.conv_pair = h->d_conv_pair; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
   tw.pfc_wT = h->d_pfc_wT; tw.pfc_b = h->d_pfc_b; tw.vfc1_wT = h->d_vfc1_wT; tw.vfc1_b = h->d_vfc1_b; tw.vfc2_w = h->d_vfc2_w;
   tw.vfc2_b = v2b[0];
   tw.n_layers = n_layers;

@@ -66,7 +66,7 @@ struct SmemLayout {
   static constexpr int red = hidden + G::GPC * kC * 4;                  // [GPC][2]
   static constexpr int masks = (red + G::GPC * 2 * 4 + 15) / 16 * 16;   // [kTiles][9 taps][4] disable-output-lane words
   static constexpr int bars = masks + kTiles * 9 * 4 * 4;               // mbarriers
-  static constexpr int total = bars + (2 * STAGES + 2) * 8 + 16;
+  static constexpr int total = bars + (3 * 2 * STAGES + 2) * 8 + 16;  // room for the pair mode's 2*STAGES slots
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -75,8 +75,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 // ONE game (one 128-row tile, half the MMA work) per CTA instead of ceil(r/GPC) full passes, so that e.g. 4096 games
 // of 9x9 cost 9 + ~0.55 pass times instead of 10.  All warp roles call this with the same arguments.
 template <int GPC, int A>
-__device__ __forceinline__ bool get_pass(int k, int n, int& g0, int& ng, int& ntiles) {
-  const int grid = (int)gridDim.x, b = (int)blockIdx.x;
+__device__ __forceinline__ bool pass_of_cta(int b, int k, int n, int& g0, int& ng, int& ntiles) {
+  const int grid = (int)gridDim.x;
   const int per_wave = GPC * grid;
   const int W = n / per_wave, r = n - W * per_wave;
   if (k < W) {
@@ -85,22 +85,38 @@ __device__ __forceinline__ bool get_pass(int k, int n, int& g0, int& ng, int& nt
     ntiles = kTiles;
     return true;
   }
+  g0 = 0;
+  ng = 0;
+  const bool one_game_tail = GPC > 1 && A <= kTileRows && r <= grid;
+  ntiles = one_game_tail ? 1 : kTiles;
   if (k > W || r == 0) return false;
-  if (GPC > 1 && A <= kTileRows && r <= grid) {
+  if (one_game_tail) {
     if (b >= r) return false;
     g0 = W * per_wave + b;
     ng = 1;
-    ntiles = 1;
     return true;
   }
   g0 = W * per_wave + b * GPC;
   if (g0 >= n) return false;
   ng = min(GPC, n - g0);
-  ntiles = kTiles;
   return true;
 }
+// PAIR: the two CTAs of a cluster issue their MMAs together, so a pass exists for both as soon as either has games
+// (the other one then runs it with ng = 0).
+template <int GPC, int A, bool PAIR>
+__device__ __forceinline__ bool get_pass(int k, int n, int& g0, int& ng, int& ntiles) {
+  const int b = (int)blockIdx.x;
+  const bool mine = pass_of_cta<GPC, A>(b, k, n, g0, ng, ntiles);
+  if (!PAIR || mine) return mine;
+  int g0p, ngp, ntp;
+  return pass_of_cta<GPC, A>(b ^ 1, k, n, g0p, ngp, ntp);
+}
 
-template <int B, int STAGES, bool X3>
+// PAIR = CTA pairs (cluster of 2, tcgen05 cta_group::2, plain precision only): one M=256 MMA spans both CTAs' tiles,
+// each CTA stages only ITS half of the output channels of B (half the smem operand reads and half the L2 weight
+// traffic per SM); the leader CTA (cluster rank 0) issues, commits are multicast to both CTAs' barriers, and the
+// peer's warp 9 forwards "my weights landed" / "my epilogue is done" to the leader.
+template <int B, int STAGES, bool X3, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
              float* __restrict__ policy, float* __restrict__ value) {
@@ -112,7 +128,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
   if (n > n_max) n = n_max;
   {
     int g0_, ng_, nt_;
-    if (!get_pass<G::GPC, G::A>(0, n, g0_, ng_, nt_)) return;  // nothing to do for this CTA
+    if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) return;  // nothing to do for this CTA
   }
 
   uint8_t* s_act = smem + SL::act;
@@ -126,10 +142,20 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
   float* s_red = reinterpret_cast<float*>(smem + SL::red);
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + SL::masks);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SL::bars);
-  uint64_t* bar_empty = bar_full + STAGES;
-  uint64_t* bar_act = bar_empty + STAGES;   // epilogue -> MMA: operand written, accumulators drained
+  // ring slots: STAGES x 32 KB; the pair mode stages half taps (16 KB) and gets twice as many slots from the same bytes
+  constexpr int NSLOT = PAIR ? 2 * STAGES : STAGES;
+  constexpr uint32_t kSlotBytes = PAIR ? kStageBytes / 2 : kStageBytes;
+  uint64_t* bar_empty = bar_full + NSLOT;
+  uint64_t* bar_act = bar_empty + NSLOT;    // epilogue -> MMA: operand written, accumulators drained
   uint64_t* bar_acc = bar_act + 1;          // MMA -> epilogue: layer accumulated
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
+  uint64_t* bar_peer_full = bar_acc + 1;    // PAIR, leader only: the peer CTA's half of stage s has landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_peer_full + NSLOT);
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
+  // bytes of one tap of this CTA's B operand (PAIR: its 64 of the 128 output channels)
+  constexpr uint32_t kTapBytes = PAIR ? kStageBytes / 2 : kStageBytes;
+  constexpr uint32_t kStemTapBytes = PAIR ? kStemStageBytes / 2 : kStemStageBytes;
+  constexpr uint32_t kBRows = PAIR ? kC / 2 : kC;  // rows (output channels) of B in this CTA's smem
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_layers = W.n_layers;
@@ -154,18 +180,23 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     s_mask[i] = m;
   }
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    mbar_init(bar_act, kEpiThreads);
+    mbar_init(bar_act, (PAIR && leader) ? kEpiThreads + 1 : kEpiThreads);  // + the peer's forwarded arrival
     mbar_init(bar_acc, 1);
+    for (int s = 0; s < NSLOT; ++s) mbar_init(&bar_peer_full[s], 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(s_tmem);
+  if (warp == 9) {
+    if (PAIR) tmem_alloc_pair<512>(s_tmem);
+    else tmem_alloc<512>(s_tmem);
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after_sync();
   const uint32_t tmem = *s_tmem;
 
@@ -174,7 +205,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     if (lane == 0) {
       uint32_t it = 0;
       int g0, ng, ntiles;
-      for (int k = 0; get_pass<G::GPC, G::A>(k, n, g0, ng, ntiles); ++k) {
+      for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         size_t off = 0;  // byte offset of the layer inside the packed conv weights (hi and lo buffers share the layout)
         const uint8_t* w_hi = reinterpret_cast<const uint8_t*>(W.conv_hi);
         const uint8_t* w_lo = reinterpret_cast<const uint8_t*>(W.conv_lo);
@@ -184,11 +215,16 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
           const int n_st = !X3 ? 9 : (l == 0 ? 9 : 27);
           const uint32_t layer_bytes = l == 0 ? 9u * kStemStageBytes : 9u * kStageBytes;
           for (int st = 0; st < n_st; ++st, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
+            const int s = it % NSLOT;
+            const uint32_t ph = (it / NSLOT) & 1u;
             mbar_wait(&bar_empty[s], ph ^ 1u);
-            uint8_t* dst = s_w + s * kStageBytes;
-            if (!X3) {
+            uint8_t* dst = s_w + s * kSlotBytes;
+            if (PAIR) {  // conv_pair: per tap [cluster rank][16 k-chunks][64 co][8]
+              const uint32_t part = l == 0 ? kStemTapBytes : kTapBytes;
+              mbar_arrive_expect_tx(&bar_full[s], part);
+              bulk_g2s(dst, reinterpret_cast<const uint8_t*>(W.conv_pair) + off + ((size_t)st * 2 + cta_rank) * part, part,
+                       &bar_full[s]);
+            } else if (!X3) {
               const uint32_t part = l == 0 ? kStemStageBytes : kStageBytes;
               mbar_arrive_expect_tx(&bar_full[s], part);
               bulk_g2s(dst, w_hi + off + (size_t)st * part, part, &bar_full[s]);
@@ -210,34 +246,65 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     // =========================================================== MMA issuer
     // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; one elected
     // lane issues tcgen05.mma / commit.
-    {
-      const uint32_t idesc = umma_idesc_f16_f32(128, 128);
+    if (PAIR && !leader) {
+      // ---- peer CTA of a pair: no MMA issue; one lane forwards this CTA's readiness to the leader's barriers.
+      // Two independent event streams (operand-ready per layer, weights-landed per stage) are polled without
+      // blocking so that neither delays the other.
+      if (lane == 0) {
+        int g0, ng, ntiles, n_k = 0;
+        while (get_pass<G::GPC, G::A, PAIR>(n_k, n, g0, ng, ntiles)) ++n_k;
+        const uint32_t n_act = (uint32_t)(n_k * n_layers), n_stage = n_act * 9u;
+        uint32_t ai = 0, si = 0;
+        const uint64_t t0 = globaltimer_ns();
+        uint32_t spins = 0;
+        while (ai < n_act || si < n_stage) {
+          bool progress = false;
+          if (ai < n_act && mbar_test_wait(bar_act, ai & 1u)) {  // this CTA's 256 epilogue threads wrote the operand
+            mbar_arrive_remote(bar_act, 0u);
+            ++ai;
+            progress = true;
+          }
+          if (si < n_stage) {
+            const uint32_t s = si % NSLOT;
+            if (mbar_test_wait(&bar_full[s], (si / NSLOT) & 1u)) {  // this CTA's half of the stage has landed
+              mbar_arrive_remote(&bar_peer_full[s], 0u);
+              ++si;
+              progress = true;
+            }
+          }
+          if (!progress && (++spins & 0x3FFu) == 0u && globaltimer_ns() - t0 > 8000000000ull) __trap();
+        }
+      }
+    } else {
+      const uint32_t idesc = umma_idesc_f16_f32(PAIR ? 256 : 128, 128);
       const uint32_t lbo_a = (uint32_t)G::Rows * 16u;
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_act), lbo_a);
       const uint32_t desc_hi = umma_desc_hi(128u);
       constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;  // two k-chunks further along K
-      constexpr uint32_t kBStep = (2u * kC * 16u) >> 4;
+      constexpr uint32_t kBStep = (2u * kBRows * 16u) >> 4;
       uint32_t it = 0, act_phase = 0;
       long long dbg_act_wait = 0, dbg_full_wait = 0;
       const long long dbg_t0 = W.dbg ? clock64() : 0;
       int g0, ng, ntiles;
-      for (int k = 0; get_pass<G::GPC, G::A>(k, n, g0, ng, ntiles); ++k) {
+      for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         for (int l = 0; l < n_layers; ++l) {
           // plain mode: stem and conv2 accumulate in accB, which already holds the block input x (residual);
           // X3 mode: every layer accumulates in a fresh accA and accB is only the epilogue's fp32 stash of x
           const bool to_b = !X3 && (l & 1) == 0;
           const bool residual = to_b && l > 0;
           const long long t_a0 = W.dbg ? clock64() : 0;
-          mbar_wait(bar_act, act_phase);
+          if (PAIR) mbar_wait_cluster(bar_act, act_phase);  // 256 local arrivals + the peer's forwarded one
+          else mbar_wait(bar_act, act_phase);
           act_phase ^= 1u;
           tc_fence_after_sync();
           if (W.dbg) dbg_act_wait += clock64() - t_a0;
           const int n_st = !X3 ? 9 : (l == 0 ? 9 : 27);
           for (int st = 0; st < n_st; ++st, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
+            const int s = it % NSLOT;
+            const uint32_t ph = (it / NSLOT) & 1u;
             const long long t_f0 = W.dbg ? clock64() : 0;
             mbar_wait(&bar_full[s], ph);
+            if (PAIR) mbar_wait_cluster(&bar_peer_full[s], ph);
             tc_fence_after_sync();
             if (W.dbg) dbg_full_wait += clock64() - t_f0;
             const bool lo_phase = X3 && l > 0 && st < 18;
@@ -247,7 +314,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
             const int t = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);                 // tap = (dy+1)*3 + (dx+1)
             const int kh = lo_phase ? st & 1 : 0;  // which half of the 128 input channels
             const int shift = (t / 3 - 1) * G::S + (t % 3 - 1);
-            const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + s * kStageBytes), kC * 16u);
+            const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + s * kSlotBytes), kBRows * 16u);
             if (elect_one()) {
 #pragma unroll
               for (int tile = 0; tile < kTiles; ++tile) {
@@ -256,7 +323,14 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
                 const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
                 const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
                 const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);  // 16 B per row
-                if (!X3) {
+                if (PAIR) {  // one M=256 MMA over both CTAs' tiles; the peer's rows use the same geometry / masks
+                  umma_f16_ss_pair_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || st > 0) ? 1u : 0u, m0, m1, m2, m3);
+                  if (l > 0) {
+#pragma unroll
+                    for (int j = 1; j < kC / 16; ++j)
+                      umma_f16_ss_pair_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u, m0, m1, m2, m3);
+                  }
+                } else if (!X3) {
                   if (l == 0) {
                     umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, st > 0 ? 1u : 0u, m0, m1, m2, m3);
                   } else {
@@ -289,8 +363,13 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
                   }
                 }
               }
-              umma_commit(&bar_empty[s]);
-              if (st == n_st - 1) umma_commit(bar_acc);
+              if (PAIR) {
+                umma_commit_pair(&bar_empty[s]);
+                if (st == n_st - 1) umma_commit_pair(bar_acc);
+              } else {
+                umma_commit(&bar_empty[s]);
+                if (st == n_st - 1) umma_commit(bar_acc);
+              }
             }
             __syncwarp();
           }
@@ -320,7 +399,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     const long long dbg_e0 = dbg_on ? clock64() : 0;
 
     int g0, ng, ntiles;
-    for (int k = 0; get_pass<G::GPC, G::A>(k, n, g0, ng, ntiles); ++k) {
+    for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
       const bool valid = geo_valid && g_local < ng;
       // ---- input planes (utils.get_state_pt) -> channels 0..4 of chunk 0; chunk 1 = 0
       {
@@ -505,7 +584,11 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (PAIR) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner may still signal / use it
+  if (warp == 9) {
+    if (PAIR) tmem_dealloc_pair<512>(tmem);
+    else tmem_dealloc<512>(tmem);
+  }
 }
 
 // dense float states [n][C][B][B] -> LeafIn row masks
@@ -536,21 +619,36 @@ __global__ void pack_states_kernel(const float* __restrict__ st, int n, int B, i
   }
 }
 
-template <int B, int STAGES, bool X3>
+template <int B, int STAGES, bool X3, bool PAIR>
 cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
                            float* value, int num_sms, cudaStream_t s) {
   using SL = SmemLayout<B, STAGES, X3>;
   static_assert(SL::total <= 232448, "tower kernel exceeds 227 KB of shared memory");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tower_kernel<B, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
+    cudaError_t e = cudaFuncSetAttribute(tower_kernel<B, STAGES, X3, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int grid = n_max < num_sms ? n_max : num_sms;  // see get_pass: up to one game per CTA in a ragged wave
   if (grid <= 0) return cudaSuccess;
-  tower_kernel<B, STAGES, X3><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
-  return cudaGetLastError();
+  if (!PAIR) {
+    tower_kernel<B, STAGES, X3, PAIR><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((grid + 1) & ~1));  // whole CTA pairs
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SL::total;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tower_kernel<B, STAGES, X3, PAIR>, w, in, n_ptr, n_max, policy, value);
 }
 
 }  // namespace
@@ -559,11 +657,17 @@ cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const Leaf
                          float* policy, float* value, int num_sms, cudaStream_t s) {
   if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
   if (precision == AO_NN_FP16X3) {
-    if (B == 9) return launch_tower_t<9, 2, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    if (B == 9) return launch_tower_t<9, 2, true, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
     return cudaErrorInvalidValue;  // 15x15 split mode does not fit 227 KB of smem with this tiling (round 2)
   }
-  if (B == 9) return launch_tower_t<9, 4, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-  if (B == 15) return launch_tower_t<15, 4, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (precision == AO_NN_FP16_1CTA) {  // single-CTA variant (cta_group::1), kept for comparison
+    if (B == 9) return launch_tower_t<9, 4, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    if (B == 15) return launch_tower_t<15, 4, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    return cudaErrorInvalidValue;
+  }
+  // default: CTA pairs (cta_group::2)
+  if (B == 9) return launch_tower_t<9, 4, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (B == 15) return launch_tower_t<15, 4, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
   return cudaErrorInvalidValue;
 }
 

@@ -272,3 +272,30 @@ def test_arena_trained_vs_random_agent():
     finally:
         agents.BatchedZeroAgent.__init__ = orig
     assert res["unfinished"] == 0 and res["player_win"] == 8, res
+
+
+@pytest.mark.parametrize("name", ["nn_9_init", "nn_9_jitter", "nn_15_init", "nn_9_small"])
+def test_tower_single_cta_mode_vs_reference_model(cabi, name):
+    """same fixtures through the cta_group::1 variant of the tower (the default is CTA pairs / cta_group::2), plus
+    ragged batch sizes on both variants"""
+    fx = load(name)
+    B, nb = int(fx["B"]), int(fx["n_block"])
+    sd = pvnet_ref.make_state_dict(int(fx["seed"]), nb, 5, 128, B, bn_jitter=bool(fx["jitter"]))
+    ids = [unpad_id(r) for r in fx["ids"]]
+    states = np.stack([O.get_state_pt(i, B, 5) for i in ids]).astype(np.float32)
+    for mode in (cabi.AO_NN_FP16_1CTA, cabi.AO_NN_FP16):
+        eng = cabi.Engine(board_size=B, num_mcts=8, max_games=700, n_blocks=nb, nn_precision=mode)
+        eng.load_state_dict(sd)
+        for n in (len(ids), 1, 2, 5):
+            p, v = eng.nn_forward(states[:n])
+            assert np.abs(p - fx["p"][:n]).max() < TOL, (mode, n, np.abs(p - fx["p"][:n]).max())
+            assert np.abs(v - fx["v"][:n]).max() < TOL, (mode, n, np.abs(v - fx["v"][:n]).max())
+        if B == 9:  # more passes than CTAs, ragged tail
+            rs = np.random.RandomState(3)
+            big = [(0,) + tuple(int(x) for x in rs.permutation(81)[:rs.randint(0, 70)]) for _ in range(700)]
+            st = np.stack([O.get_state_pt(i, B, 5) for i in big]).astype(np.float32)
+            for n in (700, 449, 150):
+                p, v = eng.nn_forward(st[:n])
+                pr, vr = pvnet_ref.pvnet_forward(sd, torch.from_numpy(st[:n]))
+                assert np.abs(p - pr.numpy()).max() < TOL and np.abs(v - vr.numpy()).max() < TOL, (mode, n)
+        eng.close()
