@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_EXPANSION = {9: 478_800_004, 15: 1_330_129_156}  # one PVNet forward, 2*MAC, padded taps
-TOWER_DRAM_BYTES_PER_LAUNCH = {(9, 4096): 6_709_248}  # ncu capture, round 1 (profiles/r01_tower_kernel_ncu_full_summary.txt)
+TOWER_DRAM_BYTES_PER_LAUNCH = {(9, 4096): 6_692_352}  # ncu capture, round 1 (profiles/r01_tower_kernel_ncu_full_summary.txt)
 METRIC = "MCTS node-expansions/sec, 9x9 Omok self-play @400 sims/move"
 
 
