@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-episodes", action="store_true", help="skip the games/s leg (all games played to the end)")
     return ap.parse_args()
 
 
@@ -94,6 +95,15 @@ def cpu_oracle_throughput(board, sims, seconds, workers):
     return total / elapsed, total, elapsed
 
 
+def workload_config(a, world):
+    B, G, S = a.board, a.games, a.sims
+    return {"workload": f"{G} parallel {B}x{B} self-play games per GPU, {S} sims/move, PVNet 10x128 random-init (numpy seed 0)",
+            "games_per_gpu": G, "sims_per_move": S, "rounds_per_step": S,
+            "parallelism": f"dp{world} (games sharded, no data-path collective)",
+            "l2": "inputs larger than L2: per-GPU tree storage %.1f GB; 5.9 MB of fp16 weights are L2-resident by design"
+                  % (G * 2 * 2048 * B * B * 21 / 1e9)}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -115,7 +125,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "expansions/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / max(1, a.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{a.games} parallel {a.board}x{a.board} self-play games, {a.sims} sims/move (bounded CPU sample)"},
+        "config": workload_config(a, a.gpus),
         "cpu_baseline": {"value": value, "unit": "expansions/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -261,17 +271,34 @@ def run_ours(a):
         e2e = {"sims": e_sims, "ms": e_ms, "h2d": int(roots.nbytes + lens.nbytes + ids.nbytes), "d2h": int(vis.nbytes + real.nbytes),
                "steps": n_e2e_steps}
 
+    # ---------------- games/s: every game of the batch played to its end (ragged tail included)
+    full = None
+    if not a.no_full_episodes:
+        eng.selfplay_begin(G, first_key=rank * G + 7 * G, recycle=False)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            f0.record(stream)
+            fs = eng.selfplay_rounds(S)
+            while fs["running"]:
+                fs = eng.selfplay_rounds(S)
+            f1.record(stream)
+        torch.cuda.synchronize()
+        full = {"ms": f0.elapsed_time(f1), "games": G, "moves": fs["moves"], "sims": fs["sims"], "errors": fs["errors"]}
+
     # ---------------- reduce over ranks
     t = torch.tensor([ms, float(sims), float(evals), float(moves), float(games_done), tower_ms, tree_ms,
-                      float(launches), e2e["ms"] if e2e else 0.0, float(e2e["sims"]) if e2e else 0.0],
+                      float(launches), e2e["ms"] if e2e else 0.0, float(e2e["sims"]) if e2e else 0.0,
+                      full["ms"] if full else 0.0, float(full["games"]) if full else 0.0,
+                      float(full["moves"]) if full else 0.0, float(full["errors"]) if full else 0.0],
                      dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms_max, e_ms_max = tmax[0].item(), tmax[8].item()
+        ms_max, e_ms_max, f_ms_max = tmax[0].item(), tmax[8].item(), tmax[10].item()
     else:
-        ms_max, e_ms_max = t[0].item(), t[8].item()
+        ms_max, e_ms_max, f_ms_max = t[0].item(), t[8].item(), t[10].item()
     tot = t.cpu().numpy()
 
     if rank == 0:
@@ -284,9 +311,7 @@ def run_ours(a):
             "warmup": a.warmup, "ms_per_step": ms_max / max(1, a.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 (tensor-core inputs, f32 accumulate); tree: f32 w/q, f64 p/u",
             "data": "synthetic",
-            "config": {"workload": f"{G} parallel {B}x{B} self-play games per GPU, {S} sims/move, PVNet 10x128 random-init (numpy seed 0)",
-                       "games_per_gpu": G, "sims_per_move": S, "rounds_per_step": S, "parallelism": f"dp{world} (games sharded, no data-path collective)",
-                       "l2": "inputs larger than L2: per-GPU tree storage %.1f GB; 5.9 MB of fp16 weights are L2-resident by design" % (G * 2 * 2048 * A * 21 / 1e9)},
+            "config": workload_config(a, world),
             "moves_per_s": tot[3] / (ms_max * 1e-3), "games_finished_in_window": int(tot[4]),
             "gpu_launches": int(tot[7]),
             "roofline": {"bound": "tensor", "kernel": "tower_kernel", "achieved": achieved, "peak": sustained,
@@ -304,6 +329,10 @@ def run_ours(a):
             line["e2e"] = {"value": tot[9] / (e_ms_max * 1e-3), "unit": "expansions/s", "h2d_bytes_per_step": e2e["h2d"],
                            "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
                            "api": "Engine.search_raw == BatchedZeroAgent.get_pi (ao_search), pinned host buffers"}
+        if full:
+            line["selfplay_games_per_s"] = tot[11] / (f_ms_max * 1e-3)
+            line["full_episodes"] = {"games": int(tot[11]), "seconds": f_ms_max * 1e-3, "moves_per_game": tot[12] / tot[11],
+                                     "tree_overflows": int(tot[13])}
         if not a.no_cpu_baseline:
             cores = os.cpu_count() or 1
             workers = max(1, min(cores, 64))
