@@ -299,3 +299,86 @@ def test_tower_single_cta_mode_vs_reference_model(cabi, name):
                 pr, vr = pvnet_ref.pvnet_forward(sd, torch.from_numpy(st[:n]))
                 assert np.abs(p - pr.numpy()).max() < TOL and np.abs(v - vr.numpy()).max() < TOL, (mode, n)
         eng.close()
+
+
+def test_search_in_cpython_set_order_regime_vs_oracle(cabi):
+    """late-game roots (>= 63 stones on 9x9): child order is CPython's hash-table order, which decides which child a
+    tie-break index and a Dirichlet component refer to - visits and priors must still match the oracle bit for bit"""
+    B, A, sims, seed = 9, 81, 60, 31
+    rs = np.random.RandomState(4)
+    roots = []
+    while len(roots) < 6:
+        k = int(rs.randint(63, 76))
+        mv = (0,) + tuple(int(x) for x in rs.permutation(A)[:k])
+        if O.check_win(O.get_board(mv, B), 5) == 0:
+            roots.append(mv)
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=len(roots), seed=seed, eval_mode=cabi.AO_EVAL_SYNTH,
+                      noise_mode=cabi.AO_NOISE_TAPE)
+    tapes = [O.make_gamma_tape(seed, g, A + 2, A, 10 / A) for g in range(len(roots))]
+    for g, t in enumerate(tapes):
+        eng.set_gamma_tape(g, t)
+    eng.games_reset(list(range(len(roots))), keys=list(range(len(roots))))
+    vis, pri, real = eng.search(list(range(len(roots))), roots)
+    for g, mv in enumerate(roots):
+        assert O.legal_actions(mv, B) != sorted(O.legal_actions(mv, B))  # really in the non-ascending regime
+        agent = O.OracleZeroAgent(B, sims, lambda m: synth_eval(m, A), O.DecisionStream(seed, g, tapes[g]), noise=True)
+        agent.get_pi(mv, 1)
+        assert np.array_equal(vis[g], agent.visit.astype(np.uint32)), g
+        assert np.array_equal(pri[g], agent.policy), g
+    eng.close()
+
+
+def test_full_size_invariants_4096_games(cabi):
+    """BASELINE config 2 size (4096 games, 400 sims/move, real tower): size-independent properties of the search"""
+    B, A, sims, G = 9, 81, 400, 4096
+    sd = pvnet_ref.make_state_dict(0, 10, 5, 128, B)
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=99)
+    eng.load_state_dict(sd)
+    eng.selfplay_begin(G)
+    st = eng.selfplay_rounds(3 * sims + 8)  # a bit more than three moves for every game
+    assert st["errors"] == 0 and st["running"] == G and st["moves"] >= 3 * G
+    moves, n_moves, winners, visits = eng.selfplay_fetch(G)
+    assert (n_moves >= 3).all() and (winners == 0).all()
+    v0 = visits[:, 0].astype(np.int64)
+    assert (v0.sum(axis=1) == sims).all()            # real root: num_mcts+1 sims, the first only expands the root
+    v1, v2 = visits[:, 1].astype(np.int64), visits[:, 2].astype(np.int64)
+    g = np.arange(G)
+    assert (v1[g, moves[:, 0]] == 0).all() and (v2[g, moves[:, 0]] == 0).all() and (v2[g, moves[:, 1]] == 0).all()
+    assert (v0[g, moves[:, 0]] >= 1).all()           # the move played was visited (tau = 1 sampling)
+    # reused root: carried-over visits = n(child) - 1 of the previous search, plus num_mcts new simulations
+    assert (v1.sum(axis=1) == sims + v0[g, moves[:, 0]] - 1).all()
+    assert (v2.sum(axis=1) == sims + v1[g, moves[:, 1]] - 1).all()
+    assert len({tuple(m[:3]) for m in moves}) > G // 8  # independent decision streams: openings differ
+    eng.close()
+
+
+def test_selfplay_determinism_and_winner_consistency(cabi):
+    """same seeds -> identical episodes (also across the CTA-pair and single-CTA tower variants); the recorded winner
+    equals utils.check_win of the final position and no earlier position is terminal"""
+    B, A, sims, G = 9, 81, 64, 96
+    sd = pvnet_ref.make_state_dict(0, 10, 5, 128, B)
+    runs = []
+    for mode in (cabi.AO_NN_FP16, cabi.AO_NN_FP16, cabi.AO_NN_FP16_1CTA):
+        eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=5, nn_precision=mode)
+        eng.load_state_dict(sd)
+        eng.selfplay_begin(G)
+        st = eng.selfplay_rounds(256)
+        while st["running"]:
+            st = eng.selfplay_rounds(256)
+        assert st["errors"] == 0
+        runs.append(eng.selfplay_fetch(G))
+        eng.close()
+    for other in runs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(runs[0], other))
+    moves, n_moves, winners, visits = runs[0]
+    finals = np.zeros((G, A), np.int8)
+    prevs = np.zeros((G, A), np.int8)
+    for g in range(G):
+        for t in range(n_moves[g]):
+            if t == n_moves[g] - 1:
+                prevs[g] = finals[g]
+            finals[g, moves[g, t]] = 1 if t % 2 == 0 else -1
+    assert np.array_equal(cabi.check_win_batch(finals, B), winners.astype(np.uint8))
+    assert (cabi.check_win_batch(prevs, B) == 0).all()
+    assert np.array_equal(np.asarray([O.check_win(f.reshape(B, B).astype(np.float64), 5) for f in finals[:16]]),
+                          winners[:16])
