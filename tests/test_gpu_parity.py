@@ -382,3 +382,51 @@ def test_selfplay_determinism_and_winner_consistency(cabi):
     assert (cabi.check_win_batch(prevs, B) == 0).all()
     assert np.array_equal(np.asarray([O.check_win(f.reshape(B, B).astype(np.float64), 5) for f in finals[:16]]),
                           winners[:16])
+
+
+def test_device_dirichlet_noise_statistics(cabi):
+    """performance mode draws the root noise on the device (Philox + Marsaglia-Tsang gamma): recover eta from the
+    exported priors and check it is a Dirichlet(alpha = 10/81) sample (agents.py:191-204)"""
+    B, A, G = 9, 81, 2048
+    priors = {}
+    for noise in (False, True):
+        eng = cabi.Engine(board_size=B, num_mcts=2, max_games=G, seed=17, noise=noise, eval_mode=cabi.AO_EVAL_SYNTH)
+        eng.games_reset(list(range(G)), keys=list(range(G)))
+        _, pri, real = eng.search(list(range(G)), [(0,)] * G)
+        assert real.all()
+        priors[noise] = pri
+        eng.close()
+    eta = (priors[True] - 0.75 * priors[False]) / 0.25
+    assert np.abs(eta.sum(axis=1) - 1).max() < 1e-9 and eta.min() > -1e-12
+    a0 = 10.0
+    mean, var = 1 / A, (1 / A) * (1 - 1 / A) / (a0 + 1)
+    assert abs(eta.mean() - mean) < 1e-12 + 1e-9
+    assert abs(eta.var() - var) / var < 0.05            # 166k components
+    # alpha < 1 per component: most of the mass sits on a few cells (P(eta_i < 1e-3) is large)
+    frac_small = (eta < 1e-3).mean()
+    ref = np.random.default_rng(0).dirichlet(np.full(A, 10 / A), size=20000)
+    assert abs(frac_small - (ref < 1e-3).mean()) < 0.01
+    assert abs(np.sort(eta, axis=1)[:, -1].mean() - np.sort(ref, axis=1)[:, -1].mean()) < 0.01
+    # different games get different noise
+    assert len({tuple(np.round(e[:5], 12)) for e in eta[:64]}) == 64
+
+
+def test_tree_arena_overflow_is_reported(cabi):
+    eng = cabi.Engine(board_size=9, num_mcts=64, max_games=1, seed=1, eval_mode=cabi.AO_EVAL_SYNTH, node_cap=8)
+    eng.games_reset([0], keys=[0])
+    with pytest.raises(cabi.AoError, match="overflowed"):
+        eng.search([0], [(0,)])
+    eng.close()
+
+
+def test_missing_weights_and_bad_arguments_are_errors(cabi):
+    eng = cabi.Engine(board_size=9, num_mcts=8, max_games=2)
+    with pytest.raises(cabi.AoError, match="no weights"):
+        eng.search([0], [(0,)])
+    with pytest.raises(cabi.AoError, match="out of range"):
+        eng.games_reset([5])
+    with pytest.raises(cabi.AoError, match="missing"):
+        eng.load_state_dict({"conv1.weight": torch.zeros(128, 5, 3, 3)})
+    eng.close()
+    with pytest.raises(cabi.AoError, match="board_size"):
+        cabi.Engine(board_size=19, num_mcts=8, max_games=1)
