@@ -28,7 +28,7 @@ class AoConfig(C.Structure):
 EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
     "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
-    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
+    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
     "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked",
 ]
 
@@ -62,6 +62,7 @@ def lib():
     L.ao_selfplay_rounds.argtypes = [vp, i32, vp]
     L.ao_selfplay_rounds_timed.argtypes = [vp, i32, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.ao_tower_debug.argtypes = [vp, i32, vp]
+    L.ao_set_nn_precision.argtypes = [vp, i32]
     L.ao_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ao_selfplay_fetch.argtypes = [vp, i32, vp, vp, vp, vp]
     L.ao_get_nn_log.argtypes = [vp, i32, vp, vp, i32, C.POINTER(i32)]
@@ -108,6 +109,7 @@ class Engine:
                  nn_precision=AO_NN_FP16, nn_log_cap=0, c_puct=5.0, alpha=0.0, stream=None):
         self.B, self.A, self.G = board_size, board_size * board_size, max_games
         self.num_mcts = num_mcts
+        self.nn_precision = nn_precision
         cfg = AoConfig(device, board_size, inplanes, planes, n_blocks, num_mcts, int(bool(noise)), tau_thres,
                        max_games, node_cap, eval_mode, noise_mode, nn_precision, nn_log_cap, float(c_puct),
                        float(alpha), seed, stream)
@@ -135,6 +137,40 @@ class Engine:
         c_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
         c_numel = (C.c_int64 * n)(*[a.size for a in arrs])
         check(lib().ao_load_weights(self._h, n, c_names, c_ptrs, c_numel))
+
+    def set_nn_precision(self, mode):
+        check(lib().ao_set_nn_precision(self._h, mode))
+        self.nn_precision = mode
+
+    def choose_nn_precision(self, tol=5e-5, n_probe=48, seed=0):
+        """Pick the cheapest tower mode whose outputs agree with the hi/lo-split mode within `tol` on a set of probe
+        positions (the split mode is within 1e-4 of fp32 even on trained nets). Random-init nets stay on
+        the single-pass fp16 mode; trained nets switch to AO_NN_FP16X3. Boards without a split kernel keep fp16."""
+        if self.B != 9:
+            self.set_nn_precision(AO_NN_FP16)
+            return AO_NN_FP16
+        rs = np.random.RandomState(seed)
+        states = np.zeros((n_probe, 5, self.B, self.B), np.float32)
+        for i in range(n_probe):  # random legal-looking positions: k stones, alternating colours
+            k = int(rs.randint(0, self.A - 20))
+            cells = rs.permutation(self.A)[:k]
+            own, opp = cells[k % 2::2], cells[(k + 1) % 2::2]
+            states[i, 2].flat[own] = 1
+            states[i, 3].flat[opp] = 1
+            states[i, 0], states[i, 1] = states[i, 2], states[i, 3]
+            if len(own):
+                states[i, 0].flat[own[-1]] = 0
+            if len(opp):
+                states[i, 1].flat[opp[-1]] = 0
+            states[i, 4] = 1.0 if k % 2 == 0 else 0.0
+        self.set_nn_precision(AO_NN_FP16X3)
+        p3, v3 = self.nn_forward(states)
+        self.set_nn_precision(AO_NN_FP16)
+        p1, v1 = self.nn_forward(states)
+        err = max(float(np.abs(p1 - p3).max()), float(np.abs(v1 - v3).max()))
+        if err > tol:
+            self.set_nn_precision(AO_NN_FP16X3)
+        return self.nn_precision
 
     def games_reset(self, game_ids, keys=None):
         ids = np.ascontiguousarray(game_ids, np.int32)

@@ -50,6 +50,8 @@ class _EngineOwner:
         n_blocks = getattr(m, "n_block", None)
         if n_blocks is None:  # any nn.Module with the reference's parameter names
             n_blocks = len({k.split(".")[1] for k in m.state_dict() if k.startswith("layers.")})
+        if getattr(self, "nn_precision", "auto") != "auto":
+            kw.setdefault("nn_precision", self.nn_precision)
         return _cabi.Engine(board_size=self.board_size, num_mcts=self.num_mcts, max_games=max_games,
                             noise=self.noise, n_blocks=n_blocks, inplanes=self.inplanes, c_puct=self.c_puct,
                             alpha=self.alpha, **kw)
@@ -62,13 +64,17 @@ class _EngineOwner:
         if fp != self._fingerprint:
             self._engine.load_state_dict(sd)
             self._fingerprint = fp
+            if getattr(self, "nn_precision", "auto") == "auto":
+                # cheapest tower mode that keeps policy / value within the 1e-4 contract for THESE weights
+                self._engine.choose_nn_precision()
 
 
 class ZeroAgent(Agent, _EngineOwner):
     """agents.py:39-260.  One game per agent, exactly the reference's surface; the tree lives in HBM."""
 
-    def __init__(self, board_size, num_mcts, inplanes, noise=True, seed=0, engine_kwargs=None):
+    def __init__(self, board_size, num_mcts, inplanes, noise=True, seed=0, engine_kwargs=None, nn_precision="auto"):
         super(ZeroAgent, self).__init__(board_size)
+        self.nn_precision = nn_precision  # "auto": fp16 single pass unless the weights need the hi/lo split mode
         self.board_size = board_size
         self.num_mcts = num_mcts
         self.inplanes = inplanes
@@ -153,7 +159,9 @@ class BatchedZeroAgent(_EngineOwner):
     pis = agent.get_pi(root_ids, taus)                # float64 [n][A], reference arithmetic per row
     """
 
-    def __init__(self, board_size, num_mcts, inplanes, n_games, noise=True, seed=0, engine_kwargs=None):
+    def __init__(self, board_size, num_mcts, inplanes, n_games, noise=True, seed=0, engine_kwargs=None,
+                 nn_precision="auto"):
+        self.nn_precision = nn_precision
         self.board_size, self.num_mcts, self.inplanes, self.noise = board_size, num_mcts, inplanes, noise
         self.n_games = n_games
         self.alpha = 10 / board_size ** 2

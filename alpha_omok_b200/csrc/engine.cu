@@ -529,6 +529,17 @@ extern "C" int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8) {
   return 0;
 }
 
+// Switch the tower's operand mode at run time (AO_NN_*); the facades use it to pick the cheapest mode that meets the
+// 1e-4 contract for the loaded weights.
+extern "C" int ao_set_nn_precision(ao_engine* h, int mode) {
+  if (!h) return fail(-1, "null engine");
+  if (mode != AO_NN_FP16 && mode != AO_NN_FP16X3 && mode != AO_NN_FP16_1CTA) return fail(-1, "unknown nn_precision %d", mode);
+  if (mode == AO_NN_FP16X3 && h->B != 9) return fail(-1, "nn_precision AO_NN_FP16X3 (hi/lo split) is implemented for board_size 9 only");
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  h->cfg.nn_precision = mode;
+  return 0;
+}
+
 extern "C" int ao_launch_count(ao_engine* h, uint64_t* out) {
   if (!h || !out) return fail(-1, "null argument");
   *out = h->launches;

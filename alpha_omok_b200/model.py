@@ -93,6 +93,7 @@ class PVNet(nn.Module):
             self._ao_fingerprint = None
         if self._ao_fingerprint != fp:
             self._ao_engine.load_state_dict(self.state_dict())
+            self._ao_engine.choose_nn_precision()  # hi/lo split tower when these weights need it for 1e-4
             self._ao_fingerprint = fp
         return self._ao_engine
 

@@ -97,6 +97,8 @@ int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_move
 int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out8, float* tree_ms, float* tower_ms);
 /* Profiling aid: cycle counters of CTA 0 of the tower kernel (see csrc/engine.cu); enable=1 starts / resets them. */
 int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8);
+/* Switch the tower's operand mode (AO_NN_*) at run time. */
+int ao_set_nn_precision(ao_engine* h, int mode);
 /* Number of kernels this engine has launched so far (bench.py's gpu_launches). */
 int ao_launch_count(ao_engine* h, uint64_t* out);
 

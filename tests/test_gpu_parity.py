@@ -260,18 +260,30 @@ def test_arena_trained_vs_random_agent():
     np.random.seed(0)
     net = model.PVNet(10, 5, 128, 9)
     net.load_state_dict(_trained_state_dict(), strict=False)
-    orig = agents.BatchedZeroAgent.__init__
-
-    def patched(self, *a, **k):  # the arena's engines run the split-precision tower for the trained net
-        k["engine_kwargs"] = {"nn_precision": 1}
-        orig(self, *a, **k)
-
-    agents.BatchedZeroAgent.__init__ = patched
-    try:
-        res = arena.play_matches(net, None, n_matches=8, num_mcts=50, seed=1, enemy="random")
-    finally:
-        agents.BatchedZeroAgent.__init__ = orig
+    res = arena.play_matches(net, None, n_matches=8, num_mcts=50, seed=1, enemy="random")
     assert res["unfinished"] == 0 and res["player_win"] == 8, res
+
+
+def test_facade_picks_split_precision_for_trained_weights(cabi):
+    """nn_precision="auto" (facade default): random-init weights stay on single-pass fp16, the trained checkpoint
+    switches to the hi/lo split tower, and model(x) in eval/no_grad meets 1e-4 either way"""
+    from alpha_omok_b200 import agents, model
+    rs = np.random.RandomState(2)
+    ids = [(0,) + tuple(int(a) for a in rs.permutation(81)[:rs.randint(0, 50)]) for _ in range(40)]
+    x = torch.from_numpy(np.stack([O.get_state_pt(i, 9, 5) for i in ids]).astype(np.float32))
+    for sd, want in ((pvnet_ref.make_state_dict(0, 10, 5, 128, 9), cabi.AO_NN_FP16), (_trained_state_dict(), cabi.AO_NN_FP16X3)):
+        net = model.PVNet(10, 5, 128, 9)
+        net.load_state_dict(sd, strict=False)
+        net.eval()
+        with torch.no_grad():
+            p, v = net(x)
+        pr, vr = pvnet_ref.pvnet_forward(sd, x)
+        assert net._ao_engine.nn_precision == want
+        assert (p - pr).abs().max() < TOL and (v - vr).abs().max() < TOL
+        agent = agents.ZeroAgent(9, 16, 5, noise=False)
+        agent.model = net
+        agent.get_pi((0,), 0)
+        assert agent._engine.nn_precision == want
 
 
 @pytest.mark.parametrize("name", ["nn_9_init", "nn_9_jitter", "nn_15_init", "nn_9_small"])

@@ -11,11 +11,7 @@ np.random.seed(0)
 z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "trained_9x9_180927.npz"))
 player = model.PVNet(10, 5, 128, 9); player.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=False)
 enemy = model.PVNet(10, 5, 128, 9); enemy.load_state_dict(pvnet_ref.make_state_dict(1, 10, 5, 128, 9), strict=False)
-orig = agents.BatchedZeroAgent.__init__
-def patched(self, *a, **k):
-    k["engine_kwargs"] = {"nn_precision": 1}   # hi/lo split tower: 1e-4 on the trained net
-    orig(self, *a, **k)
-agents.BatchedZeroAgent.__init__ = patched
+# nn_precision="auto": the trained player's engine picks the hi/lo split tower, the random-init enemy's the fp16 one
 t0 = time.time()
 res = arena.play_matches(player, enemy, n_matches=n, num_mcts=sims, seed=1)
 dt = time.time() - t0
