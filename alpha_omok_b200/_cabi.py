@@ -145,10 +145,7 @@ class Engine:
     def choose_nn_precision(self, tol=5e-5, n_probe=48, seed=0):
         """Pick the cheapest tower mode whose outputs agree with the hi/lo-split mode within `tol` on a set of probe
         positions (the split mode is within 1e-4 of fp32 even on trained nets). Random-init nets stay on
-        the single-pass fp16 mode; trained nets switch to AO_NN_FP16X3. Boards without a split kernel keep fp16."""
-        if self.B != 9:
-            self.set_nn_precision(AO_NN_FP16)
-            return AO_NN_FP16
+        the single-pass fp16 mode; trained nets switch to AO_NN_FP16X3."""
         rs = np.random.RandomState(seed)
         states = np.zeros((n_probe, 5, self.B, self.B), np.float32)
         for i in range(n_probe):  # random legal-looking positions: k stones, alternating colours

@@ -50,7 +50,7 @@ struct ao_engine {
   bool weights_loaded;
   std::vector<void*> allocs;
   // weights (device)
-  __half *d_conv_hi, *d_conv_lo, *d_conv_pair;
+  __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo;
   float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
   // staging
   int32_t *d_ids, *d_lens, *d_real_root;
@@ -124,8 +124,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   if (cfg->num_mcts < 1) return fail(-1, "num_mcts must be >= 1");
   if (cfg->eval_mode == AO_EVAL_PVNET && cfg->board_size != 9 && cfg->board_size != 15)
     return fail(-1, "the PVNet tower kernel is built for board_size 9 and 15 only");
-  if (cfg->eval_mode == AO_EVAL_PVNET && cfg->nn_precision == AO_NN_FP16X3 && cfg->board_size != 9)
-    return fail(-1, "nn_precision AO_NN_FP16X3 (hi/lo split) is implemented for board_size 9 only");
+
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);
   if (e0 != cudaSuccess || ndev == 0)
@@ -251,7 +250,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   const int n_layers = 1 + 2 * nb;
   const size_t stem_halves = (size_t)9 * 16 * C, res_halves = (size_t)9 * C * C;
   const size_t total_halves = stem_halves + (size_t)(n_layers - 1) * res_halves;
-  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves);
+  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves), prl(total_halves);
   std::vector<float> bias((size_t)n_layers * C);
   size_t off = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -280,7 +279,9 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
           hi[idx] = vh;
           lo[idx] = __float2half_rn(v - __half2float(vh));
           // CTA-pair layout: per tap [rank = co / 64][k-chunk][co % 64][8]
-          pr[off + (((size_t)t * 2 + co / 64) * (kpad / 8) + ci / 8) * 64 * 8 + (size_t)(co % 64) * 8 + (ci % 8)] = vh;
+          const size_t idx_pair = off + (((size_t)t * 2 + co / 64) * (kpad / 8) + ci / 8) * 64 * 8 + (size_t)(co % 64) * 8 + (ci % 8);
+          pr[idx_pair] = vh;
+          prl[idx_pair] = lo[idx];
         }
     }
     off += l == 0 ? stem_halves : res_halves;
@@ -319,6 +320,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
     EA(h->d_conv_hi, total_halves);
     EA(h->d_conv_lo, total_halves);
     EA(h->d_conv_pair, total_halves);
+    EA(h->d_conv_pair_lo, total_halves);
     EA(h->d_bias, bias.size());
     EA(h->d_head_w, head_w.size());
     EA(h->d_head_b, 4);
@@ -333,6 +335,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   AO_CUDA(cudaMemcpy(h->d_conv_hi, hi.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_conv_lo, lo.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_conv_pair, pr.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(h->d_conv_pair_lo, prl.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
@@ -342,7 +345,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   AO_CUDA(cudaMemcpy(h->d_vfc1_b, v1b, (size_t)C * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_vfc2_w, v2w, (size_t)C * 4, cudaMemcpyHostToDevice));
   ao::TowerWeights& tw = h->tw;
-  tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.conv_pair = h->d_conv_pair; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
+  tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.conv_pair = h->d_conv_pair; tw.conv_pair_lo = h->d_conv_pair_lo; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
   tw.pfc_wT = h->d_pfc_wT; tw.pfc_b = h->d_pfc_b; tw.vfc1_wT = h->d_vfc1_wT; tw.vfc1_b = h->d_vfc1_b; tw.vfc2_w = h->d_vfc2_w;
   tw.vfc2_b = v2b[0];
   tw.n_layers = n_layers;
@@ -534,7 +537,6 @@ extern "C" int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8) {
 extern "C" int ao_set_nn_precision(ao_engine* h, int mode) {
   if (!h) return fail(-1, "null engine");
   if (mode != AO_NN_FP16 && mode != AO_NN_FP16X3 && mode != AO_NN_FP16_1CTA) return fail(-1, "unknown nn_precision %d", mode);
-  if (mode == AO_NN_FP16X3 && h->B != 9) return fail(-1, "nn_precision AO_NN_FP16X3 (hi/lo split) is implemented for board_size 9 only");
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->cfg.nn_precision = mode;
   return 0;

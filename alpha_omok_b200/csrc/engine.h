@@ -91,6 +91,7 @@ struct TowerWeights {
   const __half* conv_hi;   // packed UMMA B operands: stem [9][2][128][8] then 2*n_blocks x [9][16][128][8]
   const __half* conv_lo;   // low parts for the split (x3) mode, same layout (null in single-pass mode)
   const __half* conv_pair; // hi parts for CTA pairs: per layer and tap [2 cluster ranks][k-chunks][64 co][8]
+  const __half* conv_pair_lo;  // low parts in the CTA-pair layout (split mode)
   const float* bias;       // [1 + 2*n_blocks][128]  BN-folded bias per conv layer
   const float* head_w;     // [3][128] policy c0, policy c1, value conv (BN scale folded)
   const float* head_b;     // [3]

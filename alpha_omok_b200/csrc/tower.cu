@@ -51,14 +51,14 @@ struct Geo {
 // X3 = error-compensated mode: activations and weights are split into fp16 hi + lo parts and every k-step issues
 // a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (fp32 accumulate) - ~22 significant bits per operand; needed for 1e-4 on
 // trained nets.  A weight stage is then half a tap: [hi 16 KB][lo 16 KB].
-template <int B, int STAGES, bool X3>
+template <int B, int RING16, bool X3>  // RING16: size of the weight ring in 16 KB units
 struct SmemLayout {
   using G = Geo<B>;
   static constexpr int act = 0;
   static constexpr int act_pad = (G::ActBytes + 1023) / 1024 * 1024;
   static constexpr int act_lo = act_pad;                                // only in X3 mode
   static constexpr int wring = X3 ? 2 * act_pad : act_pad;
-  static constexpr int bias = wring + STAGES * kStageBytes;            // [kMaxLayers][128] f32
+  static constexpr int bias = wring + RING16 * (kStageBytes / 2);      // [kMaxLayers][128] f32
   static constexpr int headw = bias + kMaxLayers * kC * 4;              // [3][128] f32
   static constexpr int feat = headw + 3 * kC * 4;                       // [GPC][3][A] f32 (p0, p1, v)
   static constexpr int logits = feat + G::GPC * 3 * G::A * 4;           // [GPC][A]
@@ -66,7 +66,7 @@ struct SmemLayout {
   static constexpr int red = hidden + G::GPC * kC * 4;                  // [GPC][2]
   static constexpr int masks = (red + G::GPC * 2 * 4 + 15) / 16 * 16;   // [kTiles][9 taps][4] disable-output-lane words
   static constexpr int bars = masks + kTiles * 9 * 4 * 4;               // mbarriers
-  static constexpr int total = bars + (3 * 2 * STAGES + 2) * 8 + 16;  // room for the pair mode's 2*STAGES slots
+  static constexpr int total = bars + (3 * RING16 + 2) * 8 + 16;  // full / empty / peer_full per slot + act + acc
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -116,12 +116,12 @@ __device__ __forceinline__ bool get_pass(int k, int n, int& g0, int& ng, int& nt
 // each CTA stages only ITS half of the output channels of B (half the smem operand reads and half the L2 weight
 // traffic per SM); the leader CTA (cluster rank 0) issues, commits are multicast to both CTAs' barriers, and the
 // peer's warp 9 forwards "my weights landed" / "my epilogue is done" to the leader.
-template <int B, int STAGES, bool X3, bool PAIR>
+template <int B, int RING16, bool X3, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
              float* __restrict__ policy, float* __restrict__ value) {
   using G = Geo<B>;
-  using SL = SmemLayout<B, STAGES, X3>;
+  using SL = SmemLayout<B, RING16, X3>;
   extern __shared__ __align__(1024) uint8_t smem[];
 
   int n = n_ptr ? *n_ptr : n_max;
@@ -142,8 +142,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
   float* s_red = reinterpret_cast<float*>(smem + SL::red);
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + SL::masks);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SL::bars);
-  // ring slots: STAGES x 32 KB; the pair mode stages half taps (16 KB) and gets twice as many slots from the same bytes
-  constexpr int NSLOT = PAIR ? 2 * STAGES : STAGES;
+  // ring slots: 32 KB each, or 16 KB in the pair mode (a CTA stages only its half of the output channels)
+  constexpr int NSLOT = PAIR ? RING16 : RING16 / 2;
   constexpr uint32_t kSlotBytes = PAIR ? kStageBytes / 2 : kStageBytes;
   uint64_t* bar_empty = bar_full + NSLOT;
   uint64_t* bar_act = bar_empty + NSLOT;    // epilogue -> MMA: operand written, accumulators drained
@@ -219,7 +219,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
             const uint32_t ph = (it / NSLOT) & 1u;
             mbar_wait(&bar_empty[s], ph ^ 1u);
             uint8_t* dst = s_w + s * kSlotBytes;
-            if (PAIR) {  // conv_pair: per tap [cluster rank][16 k-chunks][64 co][8]
+            if (PAIR && !X3) {  // conv_pair: per tap [cluster rank][16 k-chunks][64 co][8]
               const uint32_t part = l == 0 ? kStemTapBytes : kTapBytes;
               mbar_arrive_expect_tx(&bar_full[s], part);
               bulk_g2s(dst, reinterpret_cast<const uint8_t*>(W.conv_pair) + off + ((size_t)st * 2 + cta_rank) * part, part,
@@ -228,14 +228,34 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
               const uint32_t part = l == 0 ? kStemStageBytes : kStageBytes;
               mbar_arrive_expect_tx(&bar_full[s], part);
               bulk_g2s(dst, w_hi + off + (size_t)st * part, part, &bar_full[s]);
-            } else if (l == 0 || st < 18) {
-              const uint32_t part = l == 0 ? kStemStageBytes : kStageBytes / 2;
-              mbar_arrive_expect_tx(&bar_full[s], 2 * part);
-              bulk_g2s(dst, w_hi + off + (size_t)st * part, part, &bar_full[s]);
-              bulk_g2s(dst + part, w_lo + off + (size_t)st * part, part, &bar_full[s]);
-            } else {
-              mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
-              bulk_g2s(dst, w_hi + off + (size_t)(st - 18) * kStageBytes, kStageBytes, &bar_full[s]);
+            } else if (!PAIR) {
+              if (l == 0 || st < 18) {
+                const uint32_t part = l == 0 ? kStemStageBytes : kStageBytes / 2;
+                mbar_arrive_expect_tx(&bar_full[s], 2 * part);
+                bulk_g2s(dst, w_hi + off + (size_t)st * part, part, &bar_full[s]);
+                bulk_g2s(dst + part, w_lo + off + (size_t)st * part, part, &bar_full[s]);
+              } else {
+                mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+                bulk_g2s(dst, w_hi + off + (size_t)(st - 18) * kStageBytes, kStageBytes, &bar_full[s]);
+              }
+            } else {  // X3 in pair mode: this CTA's 64 output channels; per tap [rank][16 k-chunks][64][8]
+              const uint8_t* p_hi = reinterpret_cast<const uint8_t*>(W.conv_pair) + off;
+              const uint8_t* p_lo = reinterpret_cast<const uint8_t*>(W.conv_pair_lo) + off;
+              if (l == 0) {                      // [hi 2 KB | lo 2 KB]
+                const size_t o = ((size_t)st * 2 + cta_rank) * kStemTapBytes;
+                mbar_arrive_expect_tx(&bar_full[s], 2 * kStemTapBytes);
+                bulk_g2s(dst, p_hi + o, kStemTapBytes, &bar_full[s]);
+                bulk_g2s(dst + kStemTapBytes, p_lo + o, kStemTapBytes, &bar_full[s]);
+              } else if (st < 18) {              // lo phase: half a tap, [hi 8 KB | lo 8 KB]
+                const size_t o = ((size_t)(st >> 1) * 2 + cta_rank) * kTapBytes + (size_t)(st & 1) * (kTapBytes / 2);
+                mbar_arrive_expect_tx(&bar_full[s], kTapBytes);
+                bulk_g2s(dst, p_hi + o, kTapBytes / 2, &bar_full[s]);
+                bulk_g2s(dst + kTapBytes / 2, p_lo + o, kTapBytes / 2, &bar_full[s]);
+              } else {                           // hi phase: a whole tap of hi weights, 16 KB
+                const size_t o = ((size_t)(st - 18) * 2 + cta_rank) * kTapBytes;
+                mbar_arrive_expect_tx(&bar_full[s], kTapBytes);
+                bulk_g2s(dst, p_hi + o, kTapBytes, &bar_full[s]);
+              }
             }
           }
           off += layer_bytes;
@@ -253,7 +273,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       if (lane == 0) {
         int g0, ng, ntiles, n_k = 0;
         while (get_pass<G::GPC, G::A, PAIR>(n_k, n, g0, ng, ntiles)) ++n_k;
-        const uint32_t n_act = (uint32_t)(n_k * n_layers), n_stage = n_act * 9u;
+        const uint32_t n_act = (uint32_t)(n_k * n_layers);
+        const uint32_t n_stage = X3 ? (uint32_t)n_k * (9u + (uint32_t)(n_layers - 1) * 27u) : n_act * 9u;
         uint32_t ai = 0, si = 0;
         const uint64_t t0 = globaltimer_ns();
         uint32_t spins = 0;
@@ -323,43 +344,38 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
                 const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
                 const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
                 const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);  // 16 B per row
-                if (PAIR) {  // one M=256 MMA over both CTAs' tiles; the peer's rows use the same geometry / masks
-                  umma_f16_ss_pair_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || st > 0) ? 1u : 0u, m0, m1, m2, m3);
+                // one MMA = M128 of this CTA, or M256 over the same tile of both CTAs of a pair (same geometry / masks)
+                auto mma = [&](uint32_t a, uint32_t b, uint32_t acc) {
+                  if (PAIR) umma_f16_ss_pair_masked(d_tmem, a, b, desc_hi, idesc, acc, m0, m1, m2, m3);
+                  else umma_f16_ss_lohi_masked(d_tmem, a, b, desc_hi, idesc, acc, m0, m1, m2, m3);
+                };
+                if (!X3) {
+                  mma(a_lo, b_lo0, (residual || st > 0) ? 1u : 0u);
                   if (l > 0) {
 #pragma unroll
-                    for (int j = 1; j < kC / 16; ++j)
-                      umma_f16_ss_pair_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u, m0, m1, m2, m3);
-                  }
-                } else if (!X3) {
-                  if (l == 0) {
-                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, st > 0 ? 1u : 0u, m0, m1, m2, m3);
-                  } else {
-                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, (residual || st > 0) ? 1u : 0u, m0, m1, m2, m3);
-#pragma unroll
-                    for (int j = 1; j < kC / 16; ++j)
-                      umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u, m0, m1, m2, m3);
+                    for (int j = 1; j < kC / 16; ++j) mma(a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, 1u);
                   }
                 } else {
                   // The tensor core truncates (does not round) its fp32 accumulation: ~1.3 ulp(acc) lost per MMA
                   // (tools/probe_accum.py).  So the lo-terms a_hi*w_lo + a_lo*w_hi are accumulated FIRST, while the
                   // accumulator is still ~2^-11 of its final magnitude, and only the hi*hi MMAs run at full magnitude.
-                  constexpr uint32_t kALoOff = (uint32_t)SL::act_pad >> 4;  // lo activations sit above the hi ones
+                  constexpr uint32_t kALoOff = (uint32_t)SL::act_pad >> 4;      // lo activations sit above the hi ones
+                  constexpr uint32_t kWLoStem = kStemTapBytes >> 4;            // stage = [hi | lo]
+                  constexpr uint32_t kWLoHalf = (kTapBytes / 2u) >> 4;
                   if (l == 0) {       // stem: inputs are exact ({0,1}), a_lo == 0
-                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0 + ((uint32_t)kStemStageBytes >> 4), desc_hi, idesc, st > 0 ? 1u : 0u, m0, m1, m2, m3);
-                    umma_f16_ss_lohi_masked(d_tmem, a_lo, b_lo0, desc_hi, idesc, 1u, m0, m1, m2, m3);
+                    mma(a_lo, b_lo0 + kWLoStem, st > 0 ? 1u : 0u);
+                    mma(a_lo, b_lo0, 1u);
                   } else if (lo_phase) {
                     const uint32_t a0 = a_lo + (uint32_t)(kh * 4) * kAStep;
-                    constexpr uint32_t kWLoOff = ((uint32_t)kStageBytes / 2u) >> 4;  // [hi 16 KB | lo 16 KB]
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const uint32_t aj = a0 + (uint32_t)j * kAStep, bj = b_lo0 + (uint32_t)j * kBStep;
-                      umma_f16_ss_lohi_masked(d_tmem, aj, bj + kWLoOff, desc_hi, idesc, (st > 0 || j > 0) ? 1u : 0u, m0, m1, m2, m3);
-                      umma_f16_ss_lohi_masked(d_tmem, aj + kALoOff, bj, desc_hi, idesc, 1u, m0, m1, m2, m3);
+                      mma(aj, bj + kWLoHalf, (st > 0 || j > 0) ? 1u : 0u);
+                      mma(aj + kALoOff, bj, 1u);
                     }
                   } else {
 #pragma unroll
-                    for (int j = 0; j < kC / 16; ++j)
-                      umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc, 1u, m0, m1, m2, m3);
+                    for (int j = 0; j < kC / 16; ++j) mma(a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, 1u);
                   }
                 }
               }
@@ -619,21 +635,21 @@ __global__ void pack_states_kernel(const float* __restrict__ st, int n, int B, i
   }
 }
 
-template <int B, int STAGES, bool X3, bool PAIR>
+template <int B, int RING16, bool X3, bool PAIR>
 cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
                            float* value, int num_sms, cudaStream_t s) {
-  using SL = SmemLayout<B, STAGES, X3>;
+  using SL = SmemLayout<B, RING16, X3>;
   static_assert(SL::total <= 232448, "tower kernel exceeds 227 KB of shared memory");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tower_kernel<B, STAGES, X3, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
+    cudaError_t e = cudaFuncSetAttribute(tower_kernel<B, RING16, X3, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int grid = n_max < num_sms ? n_max : num_sms;  // see get_pass: up to one game per CTA in a ragged wave
   if (grid <= 0) return cudaSuccess;
   if (!PAIR) {
-    tower_kernel<B, STAGES, X3, PAIR><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
+    tower_kernel<B, RING16, X3, PAIR><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
@@ -648,7 +664,7 @@ cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tower_kernel<B, STAGES, X3, PAIR>, w, in, n_ptr, n_max, policy, value);
+  return cudaLaunchKernelEx(&cfg, tower_kernel<B, RING16, X3, PAIR>, w, in, n_ptr, n_max, policy, value);
 }
 
 }  // namespace
@@ -657,17 +673,18 @@ cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const Leaf
                          float* policy, float* value, int num_sms, cudaStream_t s) {
   if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
   if (precision == AO_NN_FP16X3) {
-    if (B == 9) return launch_tower_t<9, 2, true, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-    return cudaErrorInvalidValue;  // 15x15 split mode does not fit 227 KB of smem with this tiling (round 2)
+    if (B == 9) return launch_tower_t<9, 4, true, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    if (B == 15) return launch_tower_t<15, 3, true, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    return cudaErrorInvalidValue;
   }
   if (precision == AO_NN_FP16_1CTA) {  // single-CTA variant (cta_group::1), kept for comparison
-    if (B == 9) return launch_tower_t<9, 4, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-    if (B == 15) return launch_tower_t<15, 4, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    if (B == 9) return launch_tower_t<9, 8, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    if (B == 15) return launch_tower_t<15, 8, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
     return cudaErrorInvalidValue;
   }
   // default: CTA pairs (cta_group::2)
-  if (B == 9) return launch_tower_t<9, 4, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-  if (B == 15) return launch_tower_t<15, 4, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (B == 9) return launch_tower_t<9, 8, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (B == 15) return launch_tower_t<15, 8, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
   return cudaErrorInvalidValue;
 }
 

@@ -23,7 +23,7 @@ typedef struct ao_engine ao_engine;
 enum { AO_EVAL_PVNET = 0, AO_EVAL_SYNTH = 1 };    /* synthetic hash "network": exact floats, used by parity tests */
 enum { AO_NOISE_DEVICE = 0, AO_NOISE_TAPE = 1 };  /* Dirichlet gammas: on-device Philox generator, or host tape    */
 enum { AO_NN_FP16 = 0,       /* fp16 operands, one MMA per k-step, issued by CTA pairs (tcgen05 cta_group::2) */
-       AO_NN_FP16X3 = 1,     /* hi/lo split operands, 3 MMAs per k-step (1e-4 on trained nets), 9x9 only       */
+       AO_NN_FP16X3 = 1,     /* hi/lo split operands, 3 MMAs per k-step (1e-4 on trained nets), CTA pairs       */
        AO_NN_FP16_1CTA = 2 };/* as AO_NN_FP16 but one CTA per MMA (cta_group::1); kept for comparison          */
 
 /* Mirrors the module-level constants of main.py:26-45 / eval_main.py:22-51 and ZeroAgent.__init__ (agents.py:39-53). */

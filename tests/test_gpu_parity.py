@@ -442,3 +442,22 @@ def test_missing_weights_and_bad_arguments_are_errors(cabi):
     eng.close()
     with pytest.raises(cabi.AoError, match="board_size"):
         cabi.Engine(board_size=19, num_mcts=8, max_games=1)
+
+
+def test_tower_split_precision_15x15(cabi):
+    """hi/lo split tower on the 15x15 board (CTA-pair kernel with a 48 KB weight ring)"""
+    B = 15
+    sd = pvnet_ref.make_state_dict(5, 10, 5, 128, B, bn_jitter=True, gain=1.8)
+    rs = np.random.RandomState(0)
+    ids = [(0,) + tuple(int(a) for a in rs.permutation(225)[:rs.randint(0, 150)]) for _ in range(21)]
+    states = np.stack([O.get_state_pt(i, B, 5) for i in ids]).astype(np.float32)
+    pr, vr = pvnet_ref.pvnet_forward(sd, torch.from_numpy(states))
+    err = {}
+    for mode in (cabi.AO_NN_FP16, cabi.AO_NN_FP16X3):
+        eng = cabi.Engine(board_size=B, num_mcts=8, max_games=32, nn_precision=mode)
+        eng.load_state_dict(sd)
+        p, v = eng.nn_forward(states)
+        err[mode] = (float(np.abs(p - pr.numpy()).max()), float(np.abs(v - vr.numpy()).max()))
+        eng.close()
+    assert max(err[cabi.AO_NN_FP16X3]) < TOL, err
+    assert max(err[cabi.AO_NN_FP16]) > max(err[cabi.AO_NN_FP16X3]), err
