@@ -214,6 +214,7 @@ __device__ void compact_subtree(Ctx& c, Regs& g, int32_t old_root, int L0) {
   }
   __syncwarp();
   uint32_t head = 0, tail = 1, dcount = (uint32_t)L0;
+  bool overflow = false;
   while (head < tail) {
     const uint32_t packed = q_old[head];
     const uint32_t noff = q_new[head];
@@ -243,11 +244,16 @@ __device__ void compact_subtree(Ctx& c, Regs& g, int32_t old_root, int L0) {
       }
       if (i < L) P.slot_child[dst + noff + i] = ch;
       const uint32_t cnt = __popc(bal);
+      if (tail + cnt > P.gc_cap) overflow = true;  // more expanded nodes than queue entries: report, never corrupt
       tail += cnt;
       dcount += cnt * (uint32_t)Lc;
     }
     __syncwarp();
-    if (tail > P.gc_cap) tail = P.gc_cap;  // cannot happen when gc_cap >= expanded nodes; guards the queue
+    if (overflow) break;
+  }
+  if (overflow) {
+    g.status = ST_ERROR;
+    if (c.lane == 0) c.gm->error = 2;
   }
   g.arena ^= 1;
   c.abase = dst;
@@ -769,7 +775,7 @@ set_roots_kernel(TreeParams P, const int32_t* __restrict__ ids, int n, const int
     if (P.noise && g.root_node >= 0) remix_root_noise(c, g.root_node, P.A - g.n_moves, g.noise_draws);
   }
   g.sims_done = 0;
-  g.status = ST_SEARCH;
+  if (g.status != ST_ERROR || !in_tree) g.status = ST_SEARCH;  // a compaction-queue overflow stays reported
   if (c.lane == 0) {
     gm->is_real_root = in_tree ? 0 : 1;
     gm->auto_play = 0;
