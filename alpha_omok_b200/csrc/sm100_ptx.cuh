@@ -219,6 +219,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+// Same without release semantics: used to forward "the TMA bytes of this stage have landed in MY shared memory".
+// Nothing this thread wrote needs to be published - the data was written by the async proxy and is consumed by
+// this SM's own tensor core; the arrive only carries the fact that the phase completed (CUTLASS's 2-SM TMA loads
+// signal the leader's barrier in the same fence-free way). Avoids a GPU-scope MEMBAR + L1 invalidate per stage.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 // wait with acquire at cluster scope (the arrivals may come from the peer CTA)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -288,7 +288,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
           if (si < n_stage) {
             const uint32_t s = si % NSLOT;
             if (mbar_test_wait(&bar_full[s], (si / NSLOT) & 1u)) {  // this CTA's half of the stage has landed
-              mbar_arrive_remote(&bar_peer_full[s], 0u);
+              mbar_arrive_remote_relaxed(&bar_peer_full[s], 0u);
               ++si;
               progress = true;
             }
