@@ -192,6 +192,7 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, G, S = a.board, a.games, a.sims
     A = B * B
