@@ -192,7 +192,7 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, G, S = a.board, a.games, a.sims
     A = B * B
@@ -286,20 +286,33 @@ def run_ours(a):
             f1.record(stream)
         torch.cuda.synchronize()
         full = {"ms": f0.elapsed_time(f1), "games": G, "moves": fs["moves"], "sims": fs["sims"], "errors": fs["errors"]}
+        # the one exchange step of the path: all-gather of this round's replay records into every rank
+        from alpha_omok_b200 import replay
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        local = replay.device_records(eng, G)          # pack kernel on the engine stream (synchronised inside)
+        gathered = replay.allgather_records(local)     # NCCL all_gather_into_tensor of the fixed-size slabs
+        g1.record()
+        torch.cuda.synchronize()
+        full.update(allgather_ms=g0.elapsed_time(g1), allgather_bytes=int(gathered.numel()),
+                    allgather_ok=bool(torch.equal(gathered[rank * G:(rank + 1) * G], local)))
+        del gathered
 
     # ---------------- reduce over ranks
     t = torch.tensor([ms, float(sims), float(evals), float(moves), float(games_done), tower_ms, tree_ms,
                       float(launches), e2e["ms"] if e2e else 0.0, float(e2e["sims"]) if e2e else 0.0,
                       full["ms"] if full else 0.0, float(full["games"]) if full else 0.0,
-                      float(full["moves"]) if full else 0.0, float(full["errors"]) if full else 0.0],
+                      float(full["moves"]) if full else 0.0, float(full["errors"]) if full else 0.0,
+                      full["allgather_ms"] if full else 0.0, float(full["allgather_ok"]) if full else 1.0],
                      dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms_max, e_ms_max, f_ms_max = tmax[0].item(), tmax[8].item(), tmax[10].item()
+        ms_max, e_ms_max, f_ms_max, ag_ms_max = tmax[0].item(), tmax[8].item(), tmax[10].item(), tmax[14].item()
     else:
-        ms_max, e_ms_max, f_ms_max = t[0].item(), t[8].item(), t[10].item()
+        ms_max, e_ms_max, f_ms_max, ag_ms_max = t[0].item(), t[8].item(), t[10].item(), t[14].item()
     tot = t.cpu().numpy()
 
     if rank == 0:
@@ -334,6 +347,9 @@ def run_ours(a):
             line["selfplay_games_per_s"] = tot[11] / (f_ms_max * 1e-3)
             line["full_episodes"] = {"games": int(tot[11]), "seconds": f_ms_max * 1e-3, "moves_per_game": tot[12] / tot[11],
                                      "tree_overflows": int(tot[13])}
+            line["replay_allgather"] = {"ms": ag_ms_max, "bytes_gathered_per_rank": full["allgather_bytes"],
+                                        "records": "pack kernel + NCCL all_gather_into_tensor of fixed-size record slabs",
+                                        "verified_own_shard": bool(tot[15] == world)}
         if not a.no_cpu_baseline:
             cores = os.cpu_count() or 1
             workers = max(1, min(cores, 64))
