@@ -28,7 +28,7 @@ class AoConfig(C.Structure):
 EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
     "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
-    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_synchronize", "ao_check_win",
+    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_augment_records_dev", "ao_synchronize", "ao_check_win",
     "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked",
 ]
 
@@ -68,6 +68,7 @@ def lib():
     L.ao_get_nn_log.argtypes = [vp, i32, vp, vp, i32, C.POINTER(i32)]
     L.ao_records_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.ao_records_pack.argtypes = [vp, i32]
+    L.ao_augment_records_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.c_longlong, C.POINTER(C.c_longlong), vp]
     L.ao_synchronize.argtypes = [vp]
     L.ao_check_win.argtypes = [vp, i32, i32, vp]
     L.ao_encode_state.argtypes = [vp, vp, i32, i32, vp]
@@ -114,12 +115,14 @@ class Engine:
                        max_games, node_cap, eval_mode, noise_mode, nn_precision, nn_log_cap, float(c_puct),
                        float(alpha), seed, stream)
         self._h = C.c_void_p()
-        check(lib().ao_engine_create(C.byref(cfg), C.byref(self._h)))
+        self._lib = lib()  # keep the library alive for __del__ at interpreter shutdown
+        check(self._lib.ao_engine_create(C.byref(cfg), C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            lib().ao_engine_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and getattr(self, "_lib", None) is not None:
+            self._lib.ao_engine_destroy(h)
+            self._h = None
 
     __del__ = close
 

@@ -76,3 +76,26 @@ def decode_records(slab, board_size: int, tau_thres: int = 6, with_states: bool 
 def shard_games(n_total: int, rank: int, world: int):
     """game g -> rank g % world (per-game decision-stream keys are independent of the world size)."""
     return list(range(rank, n_total, world))
+
+
+def augmented_tensors(slab: torch.Tensor, board_size: int, tau_thres: int = 6):
+    """Record slab on the GPU (uint8 [n, record_bytes], e.g. the output of allgather_records) -> the 8-fold augmented
+    training set as CUDA float32 tensors (states [N,5,B,B], pi [N,A], z [N]), N = 8 * plies, in the order of
+    `utils.augment_dataset(cur_memory)` (main.py:250).  One kernel, nothing leaves the device."""
+    import ctypes as C
+    assert slab.is_cuda and slab.dtype == torch.uint8 and slab.is_contiguous()
+    A = board_size * board_size
+    n = slab.shape[0]
+    cnt = C.c_longlong(0)
+    lib = _cabi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    _cabi.check(lib.ao_augment_records_dev(slab.data_ptr(), n, board_size, tau_thres, None, None, None, 0, C.byref(cnt),
+                                           stream))
+    N = cnt.value
+    states = torch.empty((N, 5, board_size, board_size), dtype=torch.float32, device=slab.device)
+    pi = torch.empty((N, A), dtype=torch.float32, device=slab.device)
+    z = torch.empty((N,), dtype=torch.float32, device=slab.device)
+    if N:
+        _cabi.check(lib.ao_augment_records_dev(slab.data_ptr(), n, board_size, tau_thres, states.data_ptr(),
+                                               pi.data_ptr(), z.data_ptr(), N, C.byref(cnt), stream))
+    return states, pi, z

@@ -110,6 +110,14 @@ int ao_get_nn_log(ao_engine* h, int game_id, float* policy, float* value, int32_
 int ao_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_game);
 int ao_records_pack(ao_engine* h, int n_games);
 
+/* utils.augment_dataset + the (state, pi, z) assembly of main.self_play on the device (utils.py:226-239,
+ * main.py:155-227): record slab (device, n_games records, e.g. the all-gathered one) -> float32 training tensors
+ * states_dev [8*plies][5][B][B], pi_dev [8*plies][A], z_dev [8*plies] (DEVICE pointers, caller-allocated, capacity in
+ * samples; pass NULL outputs to only count). *n_samples_out (host) = 8 * total plies. `stream`: cudaStream_t or NULL. */
+int ao_augment_records_dev(const void* slab_dev, int n_games, int board_size, int tau_thres, float* states_dev,
+                           float* pi_dev, float* z_dev, long long capacity_samples, long long* n_samples_out,
+                           void* stream);
+
 int ao_synchronize(ao_engine* h);
 
 /* Stateless unit-test entry points (device 0 unless an engine was created).

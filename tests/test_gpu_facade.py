@@ -108,3 +108,27 @@ def test_arena_batched_matches():
     assert res["black_win"] + res["white_win"] + res["draw"] == 12 and min(res["plies"]) >= 9
     res = arena.play_matches(a, None, n_matches=8, num_mcts=60, seed=3, enemy="random")
     assert res["unfinished"] == 0 and res["player_win"] >= 6  # search beats uniform random play
+
+
+def test_device_augmentation_matches_utils_augment_dataset():
+    """records -> (state, pi, z) + 8-fold dihedral augmentation on the device, float32, in the order of
+    utils.augment_dataset(cur_memory); compared element for element with the oracle's host restatement"""
+    from alpha_omok_b200 import _cabi, replay
+    for B, G, sims in ((9, 12, 20), (15, 3, 12)):
+        eng = _cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=6, eval_mode=_cabi.AO_EVAL_SYNTH)
+        eng.selfplay_begin(G)
+        st = eng.selfplay_rounds(1)
+        while st["running"]:
+            st = eng.selfplay_rounds(1)
+        slab = replay.device_records(eng, G).clone()
+        states, pi, z = replay.augmented_tensors(slab, B, tau_thres=6)
+        mem, _ = replay.decode_records(slab, B, tau_thres=6)
+        ref = O.augment_dataset(mem, B)
+        assert states.shape[0] == len(ref) == 8 * len(mem)
+        s_ref = np.stack([r[0] for r in ref]).astype(np.float32)
+        p_ref = np.stack([r[1] for r in ref]).astype(np.float32)
+        z_ref = np.asarray([r[2] for r in ref], np.float32)
+        assert np.array_equal(states.cpu().numpy(), s_ref)
+        assert np.array_equal(pi.cpu().numpy(), p_ref)
+        assert np.array_equal(z.cpu().numpy(), z_ref)
+        eng.close()
