@@ -28,7 +28,7 @@ class AoConfig(C.Structure):
 EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
     "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
-    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_augment_records_dev", "ao_synchronize", "ao_check_win",
+    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_augment_records_dev", "ao_replay_extend_dev", "ao_replay_gather_dev", "ao_synchronize", "ao_check_win",
     "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked",
 ]
 
@@ -69,6 +69,9 @@ def lib():
     L.ao_records_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.ao_records_pack.argtypes = [vp, i32]
     L.ao_augment_records_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.c_longlong, C.POINTER(C.c_longlong), vp]
+    ll, pll = C.c_longlong, C.POINTER(C.c_longlong)
+    L.ao_replay_extend_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, ll, pll, pll, pll, vp]
+    L.ao_replay_gather_dev.argtypes = [vp, vp, vp, ll, ll, vp, ll, i32, vp, vp, vp, vp]
     L.ao_synchronize.argtypes = [vp]
     L.ao_check_win.argtypes = [vp, i32, i32, vp]
     L.ao_encode_state.argtypes = [vp, vp, i32, i32, vp]

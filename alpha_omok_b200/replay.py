@@ -99,3 +99,88 @@ def augmented_tensors(slab: torch.Tensor, board_size: int, tau_thres: int = 6):
         _cabi.check(lib.ao_augment_records_dev(slab.data_ptr(), n, board_size, tau_thres, states.data_ptr(),
                                                pi.data_ptr(), z.data_ptr(), N, C.byref(cnt), stream))
     return states, pi, z
+
+
+class DeviceReplayBuffer:
+    """`rep_memory = deque(maxlen=MEMORY_SIZE)` of main.py:66 kept on the GPU as float32 rings (states [M,5,B,B],
+    pi [M,A], z [M]); logical item i (0 = oldest) lives in slot (head + i) % M.
+
+    * `extend_records(slab)`  = `rep_memory.extend(utils.augment_dataset(cur_memory, BOARD_SIZE))` (main.py:250): the
+      record slab (this rank's, or the all-gathered one) is decoded, augmented 8-fold and written into the ring by one
+      kernel (csrc/augment.cu); `cur_len` is then `len(cur_memory)` of that round (plies before augmentation).
+    * `sample(k)`             = `random.sample(rep_memory, k)` (main.py:263-264): the indices come from Python's
+      `random` module exactly as the reference draws them (sampling `range(len)` consumes the generator like sampling
+      the deque), the rows are gathered on the device.
+    * `to_list()` / `extend_list()` speak the reference's pickle format of save_dataset / load_data (main.py:345-365).
+    """
+
+    def __init__(self, board_size: int, maxlen: int = 30000, tau_thres: int = 6, device=None):
+        self.B, self.A, self.maxlen, self.tau_thres = board_size, board_size * board_size, int(maxlen), tau_thres
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.states = torch.zeros((self.maxlen, 5, board_size, board_size), dtype=torch.float32, device=dev)
+        self.pi = torch.zeros((self.maxlen, self.A), dtype=torch.float32, device=dev)
+        self.z = torch.zeros((self.maxlen,), dtype=torch.float32, device=dev)
+        self.head, self.len, self.cur_len = 0, 0, 0
+
+    def __len__(self):
+        return self.len
+
+    def extend_records(self, slab: torch.Tensor) -> int:
+        import ctypes as C
+        assert slab.is_cuda and slab.dtype == torch.uint8 and slab.is_contiguous()
+        head, ln, n = C.c_longlong(self.head), C.c_longlong(self.len), C.c_longlong(0)
+        stream = torch.cuda.current_stream().cuda_stream
+        _cabi.check(_cabi.lib().ao_replay_extend_dev(slab.data_ptr(), slab.shape[0], self.B, self.tau_thres,
+                                                     self.states.data_ptr(), self.pi.data_ptr(), self.z.data_ptr(),
+                                                     self.maxlen, C.byref(head), C.byref(ln), C.byref(n), stream))
+        self.head, self.len = head.value, ln.value
+        self.cur_len = n.value // 8
+        return n.value
+
+    def sample_indices(self, k: int, rng=None):
+        import random as _random
+        return (rng or _random).sample(range(self.len), k)  # ValueError if k > len, like the reference
+
+    def gather(self, indices):
+        """logical deque indices -> (states [k,5,B,B], pi [k,A], z [k]) CUDA float32, in that order."""
+        k = len(indices)
+        dev = self.states.device
+        idx = torch.as_tensor(np.asarray(indices, np.int64)).to(dev, non_blocking=False)
+        if k and (int(idx.min()) < 0 or int(idx.max()) >= self.len):
+            raise IndexError("replay index out of range")
+        s = torch.empty((k, 5, self.B, self.B), dtype=torch.float32, device=dev)
+        p = torch.empty((k, self.A), dtype=torch.float32, device=dev)
+        z = torch.empty((k,), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        _cabi.check(_cabi.lib().ao_replay_gather_dev(self.states.data_ptr(), self.pi.data_ptr(), self.z.data_ptr(),
+                                                     self.maxlen, self.head, idx.data_ptr(), k, self.B, s.data_ptr(),
+                                                     p.data_ptr(), z.data_ptr(), stream))
+        return s, p, z
+
+    def sample(self, k: int, rng=None):
+        return self.gather(self.sample_indices(k, rng))
+
+    def to_list(self):
+        """The deque's content as the reference's list of (state f64 [5,B,B], pi f64 [A], z) (save_dataset)."""
+        order = (torch.arange(self.len, device=self.states.device) + self.head) % self.maxlen
+        s = self.states[order].cpu().numpy().astype(np.float64)
+        p = self.pi[order].cpu().numpy().astype(np.float64)
+        z = self.z[order].cpu().numpy().astype(np.float64)
+        return [(s[i], p[i], float(z[i])) for i in range(self.len)]
+
+    def extend_list(self, memory):
+        """deque.extend of host (state, pi, z) tuples (load_data's pickle, main.py:362-365)."""
+        memory = list(memory)[-self.maxlen:]
+        if not memory:
+            return
+        dev = self.states.device
+        s = torch.as_tensor(np.stack([np.asarray(m[0], np.float32) for m in memory])).to(dev)
+        p = torch.as_tensor(np.stack([np.asarray(m[1], np.float32) for m in memory])).to(dev)
+        z = torch.as_tensor(np.asarray([m[2] for m in memory], np.float32)).to(dev)
+        n = len(memory)
+        slots = (torch.arange(n, device=dev) + self.head + self.len) % self.maxlen
+        self.states[slots], self.pi[slots], self.z[slots] = s, p, z
+        over = self.len + n - self.maxlen
+        if over > 0:
+            self.head = (self.head + over) % self.maxlen
+        self.len = min(self.len + n, self.maxlen)

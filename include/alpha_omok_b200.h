@@ -118,6 +118,20 @@ int ao_augment_records_dev(const void* slab_dev, int n_games, int board_size, in
                            float* pi_dev, float* z_dev, long long capacity_samples, long long* n_samples_out,
                            void* stream);
 
+/* rep_memory = deque(maxlen=MEMORY_SIZE); rep_memory.extend(utils.augment_dataset(cur_memory, BOARD_SIZE))
+ * (main.py:66,250) on the device: the augmented samples of the record slab go straight into a caller-allocated ring
+ * ring_states_dev [cap][5][B][B], ring_pi_dev [cap][A], ring_z_dev [cap] (DEVICE).  *head_io / *len_io (HOST) are the
+ * deque's state - logical item i (0 = oldest) lives in slot (head + i) % cap - and are updated with deque semantics
+ * (the oldest items fall out).  *n_samples_out (host) = samples appended by this call. */
+int ao_replay_extend_dev(const void* slab_dev, int n_games, int board_size, int tau_thres, float* ring_states_dev,
+                         float* ring_pi_dev, float* ring_z_dev, long long ring_cap, long long* head_io,
+                         long long* len_io, long long* n_samples_out, void* stream);
+/* train_memory = random.sample(rep_memory, k) (main.py:263-264) as a device gather: idx_dev[k] (DEVICE, int64) are the
+ * logical deque indices drawn on the host; out_* (DEVICE) receive the samples in that order. Asynchronous on `stream`. */
+int ao_replay_gather_dev(const float* ring_states_dev, const float* ring_pi_dev, const float* ring_z_dev,
+                         long long ring_cap, long long head, const long long* idx_dev, long long k, int board_size,
+                         float* out_states_dev, float* out_pi_dev, float* out_z_dev, void* stream);
+
 int ao_synchronize(ao_engine* h);
 
 /* Stateless unit-test entry points (device 0 unless an engine was created).

@@ -132,3 +132,53 @@ def test_device_augmentation_matches_utils_augment_dataset():
         assert np.array_equal(pi.cpu().numpy(), p_ref)
         assert np.array_equal(z.cpu().numpy(), z_ref)
         eng.close()
+
+
+@pytest.mark.gpu
+def test_device_replay_ring_matches_deque_and_random_sample():
+    """rep_memory = deque(maxlen) .extend(augment_dataset(cur_memory)) + random.sample(rep_memory, k)
+    (main.py:66,250,263-264) on the device ring: same items, same order, same draws as the reference's host objects,
+    across several self-play rounds incl. wrap-around and an extend larger than maxlen."""
+    import random
+    from collections import deque
+    from alpha_omok_b200 import _cabi, replay
+    B, G = 9, 6
+    for maxlen in (700, 150):  # 700: wraps after a few rounds; 150: a single extend overflows the deque
+        buf = replay.DeviceReplayBuffer(B, maxlen=maxlen, tau_thres=6)
+        rep_memory = deque(maxlen=maxlen)
+        for rnd in range(4):
+            eng = _cabi.Engine(board_size=B, num_mcts=12, max_games=G, seed=20 + rnd, eval_mode=_cabi.AO_EVAL_SYNTH)
+            eng.selfplay_begin(G)
+            st = eng.selfplay_rounds(1)
+            while st["running"]:
+                st = eng.selfplay_rounds(1)
+            slab = replay.device_records(eng, G).clone()
+            eng.close()
+            cur_memory, _ = replay.decode_records(slab, B, tau_thres=6)
+            rep_memory.extend(O.augment_dataset(cur_memory, B))
+            n = buf.extend_records(slab)
+            assert n == 8 * len(cur_memory) and buf.cur_len == len(cur_memory) and len(buf) == len(rep_memory)
+            # whole content in deque order
+            got = buf.to_list()
+            for (s, p, z), (s2, p2, z2) in zip(got, rep_memory):
+                assert np.array_equal(s.astype(np.float32), np.asarray(s2, np.float32))
+                assert np.array_equal(p.astype(np.float32), np.asarray(p2, np.float32)) and np.float32(z) == np.float32(z2)
+            # train_memory = random.sample(rep_memory, BATCH_SIZE * len(cur_memory)) under the same generator state
+            k = min(len(rep_memory), 32 * 3)
+            random.seed(5 + rnd)
+            ref = random.sample(rep_memory, k)
+            state_after = random.getstate()
+            random.seed(5 + rnd)
+            s, p, z = buf.sample(k)
+            assert random.getstate() == state_after  # consumed the generator exactly like the reference
+            assert np.array_equal(s.cpu().numpy(), np.stack([r[0] for r in ref]).astype(np.float32))
+            assert np.array_equal(p.cpu().numpy(), np.stack([r[1] for r in ref]).astype(np.float32))
+            assert np.array_equal(z.cpu().numpy(), np.asarray([r[2] for r in ref], np.float32))
+        with pytest.raises(ValueError):
+            buf.sample(len(buf) + 1)
+        # save_dataset / load_data round trip (main.py:345-365)
+        buf2 = replay.DeviceReplayBuffer(B, maxlen=maxlen)
+        buf2.extend_list(buf.to_list())
+        assert len(buf2) == len(buf)
+        a, b = buf.gather(list(range(len(buf)))), buf2.gather(list(range(len(buf2))))
+        assert all(torch.equal(x, y) for x, y in zip(a, b))

@@ -21,3 +21,27 @@ for rep in range(3):
     print(f"rep {rep}: {states.shape[0]} samples from {G} games: {ms:.2f} ms incl. allocation + count pass, "
           f"{out_bytes/1e9:.2f} GB written + {in_bytes/1e9:.2f} GB read -> {(out_bytes+in_bytes)/ms/1e6:.0f} GB/s")
     del states, pi, z
+
+# device replay ring (deque(maxlen) semantics) + random.sample gather
+import random
+M = states_n = None
+buf = replay.DeviceReplayBuffer(9, maxlen=2_000_000)
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = buf.extend_records(slab)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"ring extend rep {rep}: {n} samples, len {len(buf)}: {ms:.2f} ms -> {(n*1948+slab.numel())/ms/1e6:.0f} GB/s")
+k = 32 * buf.cur_len
+idx = buf.sample_indices(k)
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    s, p, z = buf.gather(idx)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"gather rep {rep}: k={k} samples ({k*1948/1e9:.2f} GB read + written each): {ms:.2f} ms incl. index upload + allocation "
+          f"-> {2*k*1948/ms/1e6:.0f} GB/s")
+    del s, p, z
