@@ -12,7 +12,7 @@ from . import _build
 
 AO_EVAL_PVNET, AO_EVAL_SYNTH = 0, 1
 AO_NOISE_DEVICE, AO_NOISE_TAPE = 0, 1
-AO_NN_FP16, AO_NN_FP16X3, AO_NN_FP16_1CTA = 0, 1, 2
+AO_NN_FP16, AO_NN_FP16X3, AO_NN_FP16_1CTA, AO_NN_FP16_LOCKSTEP = 0, 1, 2, 3
 
 
 class AoConfig(C.Structure):
@@ -29,7 +29,7 @@ EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
     "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
     "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_augment_records_dev", "ao_replay_extend_dev", "ao_replay_gather_dev", "ao_synchronize", "ao_check_win",
-    "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked",
+    "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked", "ao_umma_rate",
 ]
 
 _lib = None

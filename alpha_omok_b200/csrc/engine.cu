@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
@@ -345,6 +346,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   AO_CUDA(cudaMemcpy(h->d_vfc1_b, v1b, (size_t)C * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_vfc2_w, v2w, (size_t)C * 4, cudaMemcpyHostToDevice));
   ao::TowerWeights& tw = h->tw;
+  tw.xflags = getenv("AO_TOWER_XFLAGS") ? atoi(getenv("AO_TOWER_XFLAGS")) : 0;
   tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.conv_pair = h->d_conv_pair; tw.conv_pair_lo = h->d_conv_pair_lo; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
   tw.pfc_wT = h->d_pfc_wT; tw.pfc_b = h->d_pfc_b; tw.vfc1_wT = h->d_vfc1_wT; tw.vfc1_b = h->d_vfc1_b; tw.vfc2_w = h->d_vfc2_w;
   tw.vfc2_b = v2b[0];
@@ -536,7 +538,7 @@ extern "C" int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8) {
 // 1e-4 contract for the loaded weights.
 extern "C" int ao_set_nn_precision(ao_engine* h, int mode) {
   if (!h) return fail(-1, "null engine");
-  if (mode != AO_NN_FP16 && mode != AO_NN_FP16X3 && mode != AO_NN_FP16_1CTA) return fail(-1, "unknown nn_precision %d", mode);
+  if (mode != AO_NN_FP16 && mode != AO_NN_FP16X3 && mode != AO_NN_FP16_1CTA && mode != AO_NN_FP16_LOCKSTEP) return fail(-1, "unknown nn_precision %d", mode);
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->cfg.nn_precision = mode;
   return 0;

@@ -103,6 +103,7 @@ struct TowerWeights {
   float vfc2_b;
   int n_layers;            // 1 + 2*n_blocks
   unsigned long long* dbg; // optional profiling counters of CTA 0 (null = off), see ao_tower_debug
+  int xflags;              // timing experiments only (env AO_TOWER_XFLAGS, results become wrong): see tower_stag_kernel
 };
 
 // host-side launchers implemented in the .cu files
@@ -118,6 +119,8 @@ cudaError_t launch_pack_records(const TreeParams& p, int n, uint8_t* out, size_t
 
 cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr,
                          int n_max, float* policy, float* value, int num_sms, cudaStream_t s);
+cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const int32_t* n_ptr, int n_max,
+                              float* policy, float* value, int num_sms, cudaStream_t s);
 cudaError_t tower_configure(int B, int precision);
 cudaError_t launch_pack_states(const float* states_dev, int n, int B, int inplanes, LeafIn* out, int* bad_flag_dev,
                                cudaStream_t s);

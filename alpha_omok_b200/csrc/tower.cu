@@ -20,33 +20,11 @@
 #include "engine.h"
 #include "sm100_ptx.cuh"
 
+#include "tower_common.cuh"
+
 namespace ao {
 
 namespace {
-
-constexpr int kC = 128;
-constexpr int kTileRows = 128;
-constexpr int kTiles = 2;
-constexpr int kEpiThreads = 256;
-constexpr int kThreads = 320;
-constexpr int kStageBytes = kC * kC * 2;  // one tap, 128 in-channels: 32 KB
-constexpr int kStemStageBytes = 16 * kC * 2;
-constexpr int kMaxLayers = 21;            // 1 + 2*10 blocks (bias table lives in shared memory)
-
-template <int B>
-struct Geo {
-  // Board cells are packed densely: row R of the CTA's position stream = cell (R % A) of game (R / A), row stride
-  // S = B.  Taps that fall off the board are dropped with tcgen05.mma's disable-output-lane masks instead of zero
-  // padding, so 3 games of 9x9 (243 rows) fill the two 128-row tiles to 95 % (1 game of 15x15: 88 %).
-  static constexpr int S = B;
-  static constexpr int A = B * B;
-  static constexpr int GameRows = A;
-  static constexpr int GPC = (kTiles * kTileRows) / GameRows;  // games per CTA pass
-  static constexpr int Halo = ((S + 1 + 7) / 8) * 8;           // rows addressed (never used) beyond the stream
-  static constexpr int Rows = Halo + kTiles * kTileRows + Halo;
-  static constexpr int ActBytes = 16 * Rows * 16;
-  static_assert(GPC >= 1, "board too large for a 256-row CTA tile");
-};
 
 // X3 = error-compensated mode: activations and weights are split into fp16 hi + lo parts and every k-step issues
 // a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (fp32 accumulate) - ~22 significant bits per operand; needed for 1e-4 on
@@ -68,49 +46,6 @@ struct SmemLayout {
   static constexpr int bars = masks + kTiles * 9 * 4 * 4;               // mbarriers
   static constexpr int total = bars + (3 * RING16 + 2) * 8 + 16;  // full / empty / peer_full per slot + act + acc
 };
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// Pass k of this CTA. Full waves: GPC games in both tiles. A ragged last wave of r <= gridDim.x games is spread as
-// ONE game (one 128-row tile, half the MMA work) per CTA instead of ceil(r/GPC) full passes, so that e.g. 4096 games
-// of 9x9 cost 9 + ~0.55 pass times instead of 10.  All warp roles call this with the same arguments.
-template <int GPC, int A>
-__device__ __forceinline__ bool pass_of_cta(int b, int k, int n, int& g0, int& ng, int& ntiles) {
-  const int grid = (int)gridDim.x;
-  const int per_wave = GPC * grid;
-  const int W = n / per_wave, r = n - W * per_wave;
-  if (k < W) {
-    g0 = (k * grid + b) * GPC;
-    ng = GPC;
-    ntiles = kTiles;
-    return true;
-  }
-  g0 = 0;
-  ng = 0;
-  const bool one_game_tail = GPC > 1 && A <= kTileRows && r <= grid;
-  ntiles = one_game_tail ? 1 : kTiles;
-  if (k > W || r == 0) return false;
-  if (one_game_tail) {
-    if (b >= r) return false;
-    g0 = W * per_wave + b;
-    ng = 1;
-    return true;
-  }
-  g0 = W * per_wave + b * GPC;
-  if (g0 >= n) return false;
-  ng = min(GPC, n - g0);
-  return true;
-}
-// PAIR: the two CTAs of a cluster issue their MMAs together, so a pass exists for both as soon as either has games
-// (the other one then runs it with ng = 0).
-template <int GPC, int A, bool PAIR>
-__device__ __forceinline__ bool get_pass(int k, int n, int& g0, int& ng, int& ntiles) {
-  const int b = (int)blockIdx.x;
-  const bool mine = pass_of_cta<GPC, A>(b, k, n, g0, ng, ntiles);
-  if (!PAIR || mine) return mine;
-  int g0p, ngp, ntp;
-  return pass_of_cta<GPC, A>(b ^ 1, k, n, g0p, ngp, ntp);
-}
 
 // PAIR = CTA pairs (cluster of 2, tcgen05 cta_group::2, plain precision only): one M=256 MMA spans both CTAs' tiles,
 // each CTA stages only ITS half of the output channels of B (half the smem operand reads and half the L2 weight
@@ -682,7 +617,10 @@ cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const Leaf
     if (B == 15) return launch_tower_t<15, 8, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
     return cudaErrorInvalidValue;
   }
-  // default: CTA pairs (cta_group::2)
+  if (precision == AO_NN_FP16)  // default: CTA pairs with staggered tiles (tower_stag.cu)
+    return launch_tower_stag(w, B, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (precision != AO_NN_FP16_LOCKSTEP) return cudaErrorInvalidValue;
+  // CTA pairs (cta_group::2), MMA and epilogue in lock-step
   if (B == 9) return launch_tower_t<9, 8, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
   if (B == 15) return launch_tower_t<15, 8, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
   return cudaErrorInvalidValue;

@@ -1,0 +1,521 @@
+// PVNet.forward (model.py:97-104): staggered-tile CTA-pair tower kernel (AO_NN_FP16, the default).
+//
+// Same data layout and MMAs as the CTA-pair kernel of tower.cu (dense board packing, tap = shifted start row of the
+// activation buffer, disable-output-lane masks for off-board taps, tcgen05 cta_group::2 M256 N128 K16, fp32 accumulators
+// and fp32 residual stream in TMEM), but the two 128-row tiles of a pass run half a layer apart so that the epilogue of
+// one tile (TMEM -> bias/ReLU -> fp16 operand rows in smem) runs while the tensor core works on the other tile,
+// instead of MMA and epilogue taking turns:
+//
+//   MMA issue order of a layer:  T0[c, neg taps]  T0[pos taps]  T1[c, neg taps]  commit(acc T0)  T1[pos taps]  commit(acc T1)
+//   needs (previous layer):        epi T0           epi T1        (both)                            -
+//
+// With dense packing the tiles depend on each other only through the +-(B+1) boundary rows: taps with a negative row
+// shift read rows below, so T0's centre/negative taps need T0's own epilogue only and its positive taps also T1's first
+// rows; T1's negative taps read T0's last rows, which is why acc T0 is committed (and T0's rows are overwritten in
+// place by its epilogue) only after them.  All 8 epilogue warps work on ONE tile at a time (64 accumulator columns per
+// thread).  Both tiles use every tap, so the weight ring holds exactly one layer of this CTA's half of B (9 slots x
+// 16 KB): T0 reads a slot, T1 reads it again and releases it, and the next layer's tap streams in behind it.
+//
+// Warp roles (448 threads): 0-7 epilogue, 8 weight/bias producer, 9 MMA issuer (leader CTA) or weights-landed
+// forwarder (peer CTA), 10-13 heads (1x1 conv outputs -> FC/softmax/tanh of the PREVIOUS pass while the tower of the
+// next pass is already running).
+#include <cuda_fp16.h>
+#include <stdio.h>
+
+#include "tower_common.cuh"
+
+namespace ao {
+namespace {
+
+constexpr int kStagThreads = 448;
+constexpr int kHeadThreads = 128;
+
+template <int B>
+struct StagSmem {
+  using G = Geo<B>;
+  static constexpr int kSlots = 9;
+  static constexpr int kSlotBytes = kStageBytes / 2;
+  static constexpr int act = 0;
+  static constexpr int wring = G::ActBytes;
+  static constexpr int bias2 = wring + kSlots * kSlotBytes;           // [2][128] f32: bias of the layer in flight
+  static constexpr int headw = bias2 + 2 * kC * 4;                    // [3][128] f32
+  static constexpr int feat = headw + 3 * kC * 4;                     // [GPC][3][A] f32
+  static constexpr int logits = feat + G::GPC * 3 * G::A * 4;         // [GPC][A]
+  static constexpr int hidden = logits + G::GPC * G::A * 4;           // [GPC][128]
+  static constexpr int red = hidden + G::GPC * kC * 4;                // [GPC][2]
+  static constexpr int masks = (red + G::GPC * 2 * 4 + 15) / 16 * 16; // [kTiles][9][4]
+  static constexpr int bars = masks + kTiles * 9 * 4 * 4;
+  static constexpr int kBars = 3 * kSlots + 4 + 2 + 2 + 2;
+  static constexpr int total = bars + kBars * 8 + 16;
+  static_assert(G::ActBytes % 1024 == 0, "weight ring alignment");
+};
+
+__device__ __forceinline__ void head_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+template <int B>
+__global__ void __launch_bounds__(kStagThreads, 1)
+tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
+                  float* __restrict__ policy, float* __restrict__ value) {
+  using G = Geo<B>;
+  using SL = StagSmem<B>;
+  constexpr bool PAIR = true;
+  constexpr int NSLOT = SL::kSlots;
+  constexpr uint32_t kSlotBytes = SL::kSlotBytes;
+  constexpr uint32_t kTapBytes = kStageBytes / 2, kStemTapBytes = kStemStageBytes / 2, kBRows = kC / 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  int n = n_ptr ? *n_ptr : n_max;
+  if (n > n_max) n = n_max;
+  {
+    int g0_, ng_, nt_;
+    if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) return;
+  }
+  uint8_t* s_act = smem + SL::act;
+  uint8_t* s_w = smem + SL::wring;
+  float* s_bias2 = reinterpret_cast<float*>(smem + SL::bias2);
+  float* s_headw = reinterpret_cast<float*>(smem + SL::headw);
+  float* s_feat = reinterpret_cast<float*>(smem + SL::feat);
+  float* s_logits = reinterpret_cast<float*>(smem + SL::logits);
+  float* s_hidden = reinterpret_cast<float*>(smem + SL::hidden);
+  float* s_red = reinterpret_cast<float*>(smem + SL::red);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + SL::masks);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SL::bars);
+  uint64_t* bar_empty = bar_full + NSLOT;
+  uint64_t* bar_peer_full = bar_empty + NSLOT;  // leader only: the peer CTA's half of slot s has landed
+  uint64_t* bar_act = bar_peer_full + NSLOT;    // [tile][column group] leader only: epilogue warps of BOTH CTAs -> MMA issuer
+  uint64_t* bar_acc = bar_act + 4;              // [tile] MMA -> epilogue: the tile's layer is accumulated
+  uint64_t* bar_bias = bar_acc + 2;             // [slot] producer -> epilogue: the layer's bias has landed
+  uint64_t* bar_feat_full = bar_bias + 2;       // epilogue -> heads: 1x1-conv sums of the pass are complete
+  uint64_t* bar_feat_free = bar_feat_full + 1;  // heads -> epilogue: s_feat is consumed and zeroed again
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_feat_free + 1);
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_layers = W.n_layers;
+
+  // ---------------- one-time setup
+  for (int i = tid; i < G::ActBytes / 16; i += kStagThreads) reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 3 * kC; i += kStagThreads) s_headw[i] = W.head_w[i];
+  for (int i = tid; i < G::GPC * 3 * G::A; i += kStagThreads) s_feat[i] = 0.f;
+  for (int i = tid; i < kTiles * 9 * 4; i += kStagThreads) {
+    const int tile = i / 36, tap = (i / 4) % 9, word = i % 4;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int pos = (tile * kTileRows + word * 32 + b) % G::A;
+      const int y = pos / B + dy, x = pos % B + dx;
+      if (y < 0 || y >= B || x < 0 || x >= B) m |= 1u << b;
+    }
+    s_mask[i] = m;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_peer_full[s], 1);
+    }
+    for (int t = 0; t < 4; ++t) mbar_init(&bar_act[t], 16);  // lane 0 of the 8 epilogue warps of each CTA of the pair
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_acc[t], 1);
+      mbar_init(&bar_bias[t], 1);
+    }
+    mbar_init(bar_feat_full, 8);
+    mbar_init(bar_feat_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc_pair<512>(s_tmem);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 8) {
+    // =========================================================== weight + bias producer: slot = tap, one layer in flight
+    if (lane == 0) {
+      uint32_t lc = 0;
+      int g0, ng, ntiles;
+      for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+        size_t off = 0;
+        for (int l = 0; l < n_layers; ++l, ++lc) {
+          const uint32_t part = (W.xflags & 8) ? 64u : (l == 0 ? kStemTapBytes : kTapBytes);
+          for (int st = 0; st < 9; ++st) {
+            mbar_wait(&bar_empty[st], (lc & 1u) ^ 1u);
+            if (st == 0) {
+              // slot 0 of layer l is free => layer l-1 is fully issued => the epilogue of layer l-2 (last reader of
+              // this bias slot) has finished long ago
+              mbar_arrive_expect_tx(&bar_bias[lc & 1u], kC * 4);
+              bulk_g2s(s_bias2 + (lc & 1u) * kC, W.bias + l * kC, kC * 4, &bar_bias[lc & 1u]);
+            }
+            mbar_arrive_expect_tx(&bar_full[st], part);
+            bulk_g2s(s_w + st * kSlotBytes,
+                     reinterpret_cast<const uint8_t*>(W.conv_pair) + off + ((size_t)st * 2 + cta_rank) * part, part,
+                     &bar_full[st]);
+          }
+          off += l == 0 ? 9u * kStemStageBytes : 9u * kStageBytes;
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (!leader) {
+      // ---- peer CTA: forward "my half of slot s has landed" to the leader (the operand-ready arrivals go there directly)
+      if (lane == 0) {
+        int g0, ng, ntiles, n_k = 0;
+        while (get_pass<G::GPC, G::A, PAIR>(n_k, n, g0, ng, ntiles)) ++n_k;
+        const uint32_t n_stage = (uint32_t)(n_k * n_layers) * 9u;
+        for (uint32_t si = 0; si < n_stage; ++si) {
+          const uint32_t s = si % 9u;
+          mbar_wait(&bar_full[s], (si / 9u) & 1u);
+          mbar_arrive_remote_relaxed(&bar_peer_full[s], 0u);
+        }
+      }
+    } else {
+      // =========================================================== MMA issuer (leader CTA)
+      const uint32_t idesc = umma_idesc_f16_f32(256, 128);
+      const uint32_t lbo_a = (uint32_t)G::Rows * 16u;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_act), lbo_a);
+      const uint32_t desc_hi = umma_desc_hi(128u);
+      constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;
+      constexpr uint32_t kBStep = (2u * kBRows * 16u) >> 4;
+      uint32_t lc = 0, act_ph = 0;
+      long long dbg_act_wait = 0, dbg_full_wait = 0;
+      const long long dbg_t0 = W.dbg ? clock64() : 0;
+      int g0, ng, ntiles;
+      for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+        for (int l = 0; l < n_layers; ++l, ++lc) {
+          const bool to_b = (l & 1) == 0;      // stem and conv2 accumulate in accB (holds the block input x)
+          const bool residual = to_b && l > 0;
+          const uint32_t full_ph = lc & 1u;
+          const int nk = l == 0 ? 1 : kC / 16;
+          // taps [st_lo, st_hi) of `tile`, k-steps of column group `grp` (0: k-steps {0,1,4,5} = the accumulator
+          // columns every epilogue thread converts first, 1: {2,3,6,7}, 2: all); first_use: wait for the slot's
+          // weights; release: hand the slot back
+          auto issue = [&](const int tile, const int st_lo, const int st_hi, const int grp, const bool first_use,
+                           const bool release) {
+            if (nk == 1 && grp == 1) return;  // stem: a single k-step
+            for (int st = st_lo; st < st_hi; ++st) {
+              if (first_use) {
+                const long long t_f0 = W.dbg ? clock64() : 0;
+                mbar_wait(&bar_full[st], full_ph);
+                mbar_wait_cluster(&bar_peer_full[st], full_ph);
+                tc_fence_after_sync();
+                if (W.dbg) dbg_full_wait += clock64() - t_f0;
+              }
+              const int t = st == 0 ? 4 : (st <= 4 ? st - 1 : st);  // packed order: centre, 4 negative, 4 positive shifts
+              const int shift = (W.xflags & 1) ? 0 : (t / 3 - 1) * G::S + (t % 3 - 1);
+              const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + st * kSlotBytes), kBRows * 16u);
+              if (elect_one()) {
+                const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
+                const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
+                const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
+                const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);
+                // the very first MMA of a fresh accumulation is (centre tap, k-step 0): it writes every row
+                uint32_t acc = (residual || st > 0 || grp == 1) ? 1u : 0u;
+#pragma unroll
+                for (int j = 0; j < kC / 16; ++j) {
+                  if (j >= nk) break;
+                  if (grp != 2 && ((j >> 1) & 1) != grp) continue;
+                  umma_f16_ss_pair_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc,
+                                          acc, m0, m1, m2, m3);
+                  acc = 1u;
+                }
+                if (release) umma_commit_pair(&bar_empty[st]);
+              }
+              __syncwarp();
+            }
+          };
+          auto wait_act = [&](const int idx) {  // idx = tile * 2 + column group
+            const long long t_a0 = W.dbg ? clock64() : 0;
+            mbar_wait_cluster(&bar_act[idx], (act_ph >> idx) & 1u);
+            act_ph ^= 1u << idx;
+            tc_fence_after_sync();
+            if (W.dbg) dbg_act_wait += clock64() - t_a0;
+          };
+          auto commit_acc = [&](const int tile) {
+            if (elect_one()) umma_commit_pair(&bar_acc[tile]);
+            __syncwarp();
+          };
+          if (ntiles == kTiles) {
+            wait_act(0);
+            issue(0, 0, 5, 0, true, false);
+            wait_act(1);
+            issue(0, 0, 5, 1, false, false);
+            wait_act(2);
+            issue(0, 5, 9, 0, true, false);
+            wait_act(3);
+            issue(0, 5, 9, 1, false, false);
+            issue(1, 0, 5, 2, false, true);
+            commit_acc(0);
+            issue(1, 5, 9, 2, false, true);
+            commit_acc(1);
+          } else {  // one-game tail pass: tile 0 only
+            wait_act(0);
+            wait_act(1);
+            issue(0, 0, 9, 2, true, true);
+            commit_acc(0);
+          }
+        }
+      }
+      if (W.dbg && blockIdx.x == 0 && lane == 0) {
+        atomicAdd(&W.dbg[0], (unsigned long long)(clock64() - dbg_t0));
+        atomicAdd(&W.dbg[1], (unsigned long long)dbg_act_wait);
+        atomicAdd(&W.dbg[2], (unsigned long long)dbg_full_wait);
+        atomicAdd(&W.dbg[3], 1ull);
+      }
+    }
+  } else if (warp < 8) {
+    // =========================================================== epilogue: all 8 warps on one tile at a time
+    const int q = warp & 3, half = warp >> 2;   // TMEM lane quarter, accumulator column half
+    const int r = q * 32 + lane;                // row of the tile this thread owns
+    const uint32_t chunk_stride = (uint32_t)G::Rows * 16u;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    // input planes: thread (half, r) writes row r of tile `half` (256 threads <-> 256 rows)
+    const int R_in = half * kTileRows + r;
+    const int gl_in = R_in / G::A, pos_in = R_in % G::A;
+    uint32_t acc_ph0 = 0, acc_ph1 = 0, lc = 0, pass_ph = 0;
+    long long dbg_acc_wait = 0, dbg_heads = 0;
+    const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    const long long dbg_e0 = dbg_on ? clock64() : 0;
+    // "this warp's rows of tile t are written": all lanes fence, lane 0 arrives on the LEADER's barrier
+    auto arrive_act = [&](const int idx) {  // idx = tile * 2 + column group
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&bar_act[idx]);
+        else mbar_arrive_remote(&bar_act[idx], 0u);
+      }
+    };
+
+    int g0, ng, ntiles;
+    for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+      {
+        uint4 c0 = make_uint4(0, 0, 0, 0);
+        if (gl_in < G::GPC && gl_in < ng) {
+          const LeafIn* li = &in[g0 + gl_in];
+          const int yy = pos_in / B, xx = pos_in % B;
+          const uint32_t b0 = (li->plane[0][yy] >> xx) & 1u, b1 = (li->plane[1][yy] >> xx) & 1u;
+          const uint32_t b2 = (li->plane[2][yy] >> xx) & 1u, b3 = (li->plane[3][yy] >> xx) & 1u;
+          const uint32_t b4 = li->colour & 1u;
+          c0.x = (b0 ? 0x3C00u : 0u) | (b1 ? 0x3C000000u : 0u);
+          c0.y = (b2 ? 0x3C00u : 0u) | (b3 ? 0x3C000000u : 0u);
+          c0.z = (b4 ? 0x3C00u : 0u);
+        }
+        const uint32_t ro = (uint32_t)(G::Halo + R_in) * 16u;
+        *reinterpret_cast<uint4*>(s_act + ro) = c0;
+        *reinterpret_cast<uint4*>(s_act + chunk_stride + ro) = make_uint4(0, 0, 0, 0);
+      }
+      // every warp wrote rows of ONE tile only, but both barriers expect all 16 warps
+      arrive_act(0);
+      arrive_act(1);
+      if (ntiles == kTiles) {
+        arrive_act(2);
+        arrive_act(3);
+      }
+
+      for (int l = 0; l < n_layers; ++l, ++lc) {
+        const bool to_b = (l & 1) == 0;
+        const bool last = l == n_layers - 1;
+        const float* bias = s_bias2 + (lc & 1u) * kC;
+        mbar_wait(&bar_bias[lc & 1u], (lc >> 1) & 1u);
+        for (int t = 0; t < ntiles; ++t) {
+          const int R = t * kTileRows + r;
+          const int g_local = R / G::A, pos = R % G::A;
+          const bool valid = g_local < G::GPC && g_local < ng;
+          const uint32_t row_off = (uint32_t)(G::Halo + R) * 16u;
+          const long long t_w0 = dbg_on ? clock64() : 0;
+          mbar_wait(&bar_acc[t], t ? acc_ph1 : acc_ph0);
+          if (t) acc_ph1 ^= 1u;
+          else acc_ph0 ^= 1u;
+          tc_fence_after_sync();
+          if (dbg_on) dbg_acc_wait += clock64() - t_w0;
+          const uint32_t lane_addr = lane_base + (uint32_t)(t * 256);
+          const uint32_t stash_addr = lane_addr + 128u;
+          const uint32_t acc_addr = to_b ? stash_addr : lane_addr;
+          float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
+          auto process = [&](uint32_t (&v)[32], const int qd) {  // qd: 32-column group of the 128 channels
+            const float4* b4 = reinterpret_cast<const float4*>(bias + qd * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              const float y0 = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bb.x, 0.f);
+              const float y1 = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bb.y, 0.f);
+              const float y2 = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bb.z, 0.f);
+              const float y3 = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bb.w, 0.f);
+              // rows beyond the pass's games hold finite garbage: no on-board tap of a real row ever reads them
+              v[j4 * 4 + 0] = __float_as_uint(y0);
+              v[j4 * 4 + 1] = __float_as_uint(y1);
+              v[j4 * 4 + 2] = __float_as_uint(y2);
+              v[j4 * 4 + 3] = __float_as_uint(y3);
+            }
+            if (!last) {
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                uint4 pk;
+                __half2 h;
+                h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 0]), __uint_as_float(v[cc * 8 + 1]));
+                pk.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 2]), __uint_as_float(v[cc * 8 + 3]));
+                pk.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 4]), __uint_as_float(v[cc * 8 + 5]));
+                pk.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
+                pk.w = *reinterpret_cast<uint32_t*>(&h);
+                *reinterpret_cast<uint4*>(s_act + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pk;
+              }
+              if (to_b) tmem_st32(stash_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = __uint_as_float(v[j]);
+                hd0 = fmaf(x, s_headw[0 * kC + qd * 32 + j], hd0);
+                hd1 = fmaf(x, s_headw[1 * kC + qd * 32 + j], hd1);
+                hd2 = fmaf(x, s_headw[2 * kC + qd * 32 + j], hd2);
+              }
+            }
+          };
+          if (!(W.xflags & 4) || last) {
+            uint32_t va[32], vb[32];
+            tmem_ld32(acc_addr + (uint32_t)(half * 64), va);
+            tmem_ld32(acc_addr + (uint32_t)(half * 64 + 32), vb);
+            tmem_ld_wait();
+            process(va, half * 2);
+            if (!last) arrive_act(t * 2);  // k-steps {0,1} / {4,5} of the next layer can start
+            process(vb, half * 2 + 1);
+          } else if (!last) {
+            arrive_act(t * 2);
+          }
+          if (!last) {
+            if (to_b) tmem_st_wait();
+            arrive_act(t * 2 + 1);
+          } else {
+            // heads' 1x1 convolutions (model.py:44-46, 64-66): the two column halves of a row add up in shared memory
+            // (two commutative float adds onto 0: the result does not depend on their order)
+            if (t == 0) mbar_wait(bar_feat_free, pass_ph ^ 1u);  // the head warps are done with the previous pass
+            if (valid) {
+              float* f = s_feat + g_local * 3 * G::A;
+              atomicAdd(&f[0 * G::A + pos], hd0);
+              atomicAdd(&f[1 * G::A + pos], hd1);
+              atomicAdd(&f[2 * G::A + pos], hd2);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_feat_full);
+      pass_ph ^= 1u;
+    }
+    if (dbg_on) {
+      atomicAdd(&W.dbg[4], (unsigned long long)(clock64() - dbg_e0));
+      atomicAdd(&W.dbg[5], (unsigned long long)dbg_acc_wait);
+      atomicAdd(&W.dbg[6], (unsigned long long)dbg_heads);
+    }
+  } else {
+    // =========================================================== heads (model.py:43-50, 63-73), one pass behind the tower
+    const int ht = tid - 10 * 32, hw = warp - 10;
+    uint32_t pass_ph = 0;
+    int g0, ng, ntiles;
+    for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+      mbar_wait_sleep(bar_feat_full, pass_ph, 2000);  // a whole tower pass (~100 us) between two head jobs
+      pass_ph ^= 1u;
+      for (int i = ht; i < G::GPC * 3 * G::A; i += kHeadThreads)
+        s_feat[i] = fmaxf(s_feat[i] + W.head_b[(i / G::A) % 3], 0.f);
+      head_bar_sync();
+      for (int o = ht; o < G::GPC * G::A; o += kHeadThreads) {  // policy FC: (game, output)
+        const int pg = o / G::A, po = o % G::A;
+        if (pg < ng) {
+          const float* f = s_feat + pg * 3 * G::A;
+          float acc = W.pfc_b[po];
+          const float* wt = W.pfc_wT + po;
+#pragma unroll 18
+          for (int kk = 0; kk < 2 * G::A; ++kk) acc = fmaf(__ldg(wt + (size_t)kk * G::A), f[kk], acc);
+          s_logits[o] = acc;
+        }
+      }
+      for (int vi = ht; vi < G::GPC * kC; vi += kHeadThreads) {  // value FC1: (game, hidden unit)
+        const int vg = vi / kC, vj = vi % kC;
+        if (vg < ng) {
+          const float* f = s_feat + vg * 3 * G::A + 2 * G::A;
+          float acc = W.vfc1_b[vj];
+          const float* wt = W.vfc1_wT + vj;
+#pragma unroll 27
+          for (int kk = 0; kk < G::A; ++kk) acc = fmaf(__ldg(wt + (size_t)kk * kC), f[kk], acc);
+          s_hidden[vi] = fmaxf(acc, 0.f) * W.vfc2_w[vj];
+        }
+      }
+      head_bar_sync();
+      if (hw < ng) {  // head warp g: softmax statistics and the value of game g (GPC <= 3 games per pass)
+        float mx = -3.0e38f;
+        for (int kk = lane; kk < G::A; kk += 32) mx = fmaxf(mx, s_logits[hw * G::A + kk]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float sum = 0.f;
+        for (int kk = lane; kk < G::A; kk += 32) sum += expf(s_logits[hw * G::A + kk] - mx);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        float hv = 0.f;
+        for (int kk = lane; kk < kC; kk += 32) hv += s_hidden[hw * kC + kk];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) hv += __shfl_xor_sync(0xFFFFFFFFu, hv, o);
+        if (lane == 0) {
+          s_red[hw * 2 + 0] = mx;
+          s_red[hw * 2 + 1] = sum;
+          value[g0 + hw] = tanhf(hv + W.vfc2_b);
+        }
+      }
+      for (int i = ht; i < G::GPC * 3 * G::A; i += kHeadThreads) s_feat[i] = 0.f;  // ready for the next pass's sums
+      head_bar_sync();
+      for (int o = ht; o < G::GPC * G::A; o += kHeadThreads) {
+        const int pg = o / G::A, po = o % G::A;
+        if (pg < ng) policy[(size_t)(g0 + pg) * G::A + po] = expf(s_logits[o] - s_red[pg * 2]) / s_red[pg * 2 + 1];
+      }
+      head_bar_sync();  // s_logits / s_red are rewritten by the next pass only after this
+      if (lane == 0) mbar_arrive(bar_feat_free);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner may still signal / use it
+  if (warp == 9) tmem_dealloc_pair<512>(tmem);
+}
+
+template <int B>
+cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
+                                float* value, int num_sms, cudaStream_t s) {
+  using SL = StagSmem<B>;
+  static_assert(SL::total <= 232448, "staggered tower kernel exceeds 227 KB of shared memory");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tower_stag_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = n_max < num_sms ? n_max : num_sms;  // see get_pass: up to one game per CTA in a ragged wave
+  if (grid <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((grid + 1) & ~1));  // whole CTA pairs
+  cfg.blockDim = dim3(kStagThreads);
+  cfg.dynamicSmemBytes = SL::total;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tower_stag_kernel<B>, w, in, n_ptr, n_max, policy, value);
+}
+
+}  // namespace
+
+cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const int32_t* n_ptr, int n_max,
+                              float* policy, float* value, int num_sms, cudaStream_t s) {
+  if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
+  if (B == 9) return launch_tower_stag_t<9>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (B == 15) return launch_tower_stag_t<15>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace ao

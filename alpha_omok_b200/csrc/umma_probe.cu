@@ -179,3 +179,172 @@ extern "C" int ao_umma_probe_masked(const uint16_t* act_f16, int rows, const uin
 #undef CK
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Raw tcgen05.mma throughput probe: every CTA (pair) issues `iters` back-to-back M128(/256) N128 K16 kind::f16 MMAs on
+// zero-filled shared-memory operands in the tower's layout and reports cycles per MMA.  Flavours:
+//   0 cta_group::1 unmasked   1 cta_group::1 masked (zero masks)   2 cta_group::2 unmasked   3 cta_group::2 masked
+//   +4: A start row cycles through the nine 3x3 tap shifts (unaligned core-matrix rows) instead of staying aligned
+//   +8: 8 warps stream st.shared.v4 into an unrelated smem region meanwhile (epilogue-like smem write pressure)
+namespace {
+
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+constexpr int kRateRows = 288;
+constexpr int kRateAct = 16 * kRateRows * 16;  // 73728
+constexpr int kRateW = 32768;
+constexpr int kRateScratch = 32768;
+
+template <bool PAIR>
+__global__ void __launch_bounds__(320, 1) umma_rate_kernel(int flavour, int iters, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_act = smem;
+  uint8_t* s_w = smem + kRateAct;
+  uint8_t* s_scr = s_w + kRateW;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_scr + kRateScratch);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 2);
+  volatile int* s_stop = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (kRateAct + kRateW + kRateScratch) / 16; i += 320) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    ao::mbar_init(&bar[0], 1);
+    *s_stop = 0;
+    ao::fence_mbar_init();
+  }
+  if (warp == 9) {
+    if (PAIR) ao::tmem_alloc_pair<512>(s_tmem);
+    else ao::tmem_alloc<512>(s_tmem);
+  }
+  ao::fence_proxy_async_smem();
+  ao::tc_fence_before_sync();
+  __syncthreads();
+  if (PAIR) ao::cluster_sync_all();
+  ao::tc_fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+  const bool leader = !PAIR || ao::cluster_ctarank() == 0u;
+  const bool masked = flavour & 1, shifted = flavour & 4, pressure = flavour & 8;
+  if (warp == 9) {
+    if (leader) {
+      const int N = (flavour & 16) ? 64 : ((flavour & 64) ? 256 : 128);
+      const uint32_t idesc = ao::umma_idesc_f16_f32(PAIR ? 256 : 128, N);
+      const uint32_t brows = (uint32_t)(PAIR ? N / 2 : N);
+      const uint32_t a_lo0 = ao::umma_desc_lo(ao::smem_u32(s_act), kRateRows * 16u);
+      const uint32_t b_lo0 = ao::umma_desc_lo(ao::smem_u32(s_w), brows * 16u);
+      const bool sw128 = (flavour & 128) != 0;  // 128-byte swizzled K-major operands (timing only: zero data)
+      const uint32_t desc_hi = sw128 ? (ao::umma_desc_hi(1024u) | (2u << 29)) : ao::umma_desc_hi(128u);
+      const uint32_t kAStep = (2u * kRateRows * 16u) >> 4, kBStep = (2u * brows * 16u) >> 4;
+      const long long t0 = clock64();
+      if (ao::elect_one()) {
+        for (int it = 0; it < iters; ++it) {
+          const int tap = it % 9;
+          const int shift = shifted ? (tap / 3 - 1) * 9 + (tap % 3 - 1) : 0;
+          const uint32_t a = a_lo0 + (uint32_t)(16 + ((it / 9) & 1) * 128 + shift);
+          const uint32_t d0 = tmem + (uint32_t)((flavour & 64) ? ((it / 9) & 1) * 256 : ((it / 9) & 3) * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t d = (flavour & 32) ? tmem + (uint32_t)((j & 3) * 128) : d0;
+            if (sw128) {  // [k-block of 64][row][128 B]: k-step j = block j/4, +32 B per step; tap shift = whole rows
+              const uint32_t as = (ao::smem_u32(s_act) >> 4) + (uint32_t)(j >> 2) * (kRateRows * 8u) + (uint32_t)(j & 3) * 2u +
+                                  (uint32_t)(16 + ((it / 9) & 1) * 128 + shift) * 8u;
+              const uint32_t bs = (ao::smem_u32(s_w) >> 4) + (uint32_t)(j >> 2) * (brows * 8u) + (uint32_t)(j & 3) * 2u;
+              const uint32_t hi = desc_hi | ((as >> 3) & 7u) << 17;  // base_offset for a start that is not 1024 B aligned
+              const uint32_t alo = (as & 0x3FFFu) | (1u << 16), blo = (bs & 0x3FFFu) | (1u << 16);
+              if (PAIR) {
+                if (masked) ao::umma_f16_ss_pair_masked(d, alo, blo, hi, idesc, 1u, 0, 0, 0, 0);
+                else umma_f16_ss_pair(d, alo, blo, hi, idesc, 1u);
+              } else {
+                if (masked) ao::umma_f16_ss_lohi_masked(d, alo, blo, hi, idesc, 1u, 0, 0, 0, 0);
+                else ao::umma_f16_ss_lohi(d, alo, blo, hi, idesc, 1u);
+              }
+              continue;
+            }
+            if (PAIR) {
+              if (masked) ao::umma_f16_ss_pair_masked(d, a + j * kAStep, b_lo0 + j * kBStep, desc_hi, idesc, 1u, 0, 0, 0, 0);
+              else umma_f16_ss_pair(d, a + j * kAStep, b_lo0 + j * kBStep, desc_hi, idesc, 1u);
+            } else {
+              if (masked) ao::umma_f16_ss_lohi_masked(d, a + j * kAStep, b_lo0 + j * kBStep, desc_hi, idesc, 1u, 0, 0, 0, 0);
+              else ao::umma_f16_ss_lohi(d, a + j * kAStep, b_lo0 + j * kBStep, desc_hi, idesc, 1u);
+            }
+          }
+        }
+        if (PAIR) ao::umma_commit_pair(&bar[0]);
+        else ao::umma_commit(&bar[0]);
+      }
+      __syncwarp();
+      ao::mbar_wait(&bar[0], 0);
+      const long long t1 = clock64();
+      *s_stop = 1;
+      if (lane == 0 && blockIdx.x == 0) {
+        out[0] = (unsigned long long)(t1 - t0);
+        out[1] = (unsigned long long)iters * 8ull;
+      }
+    }
+  } else if (warp < 8 && pressure && leader) {
+    uint32_t k = 0;
+    while (!*s_stop) {
+      *reinterpret_cast<uint4*>(s_scr + ((k * 256u + (uint32_t)tid) * 16u) % kRateScratch) = make_uint4(k, k, k, k);
+      ++k;
+    }
+  }
+  ao::tc_fence_before_sync();
+  __syncthreads();
+  if (PAIR) ao::cluster_sync_all();
+  if (warp == 9) {
+    if (PAIR) ao::tmem_dealloc_pair<512>(tmem);
+    else ao::tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace
+
+// flavour: see above; out3[0] = cycles of CTA 0's issue loop incl. drain, out3[1] = MMAs issued, out3[2] = kernel us
+extern "C" int ao_umma_rate(int flavour, int iters, unsigned long long* out2) {
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, 16) != cudaSuccess) return -2;
+  cudaMemset(d, 0, 16);
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, 0);
+  const int smem = kRateAct + kRateW + kRateScratch + 64;
+  cudaError_t e;
+  if (flavour & 2) {
+    e = cudaFuncSetAttribute(umma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, umma_rate_kernel<true>, flavour, iters, d);
+  } else {
+    e = cudaFuncSetAttribute(umma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) umma_rate_kernel<false><<<148, 320, smem>>>(flavour, iters, d);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  cudaEventRecord(ev1, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  out2[2] = (unsigned long long)(ms * 1000.f);  // kernel time in microseconds (CUDA events)
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : -100 - (int)e;
+}

@@ -22,9 +22,11 @@ typedef struct ao_engine ao_engine;
 
 enum { AO_EVAL_PVNET = 0, AO_EVAL_SYNTH = 1 };    /* synthetic hash "network": exact floats, used by parity tests */
 enum { AO_NOISE_DEVICE = 0, AO_NOISE_TAPE = 1 };  /* Dirichlet gammas: on-device Philox generator, or host tape    */
-enum { AO_NN_FP16 = 0,       /* fp16 operands, one MMA per k-step, issued by CTA pairs (tcgen05 cta_group::2) */
+enum { AO_NN_FP16 = 0,       /* fp16 operands, one MMA per k-step, issued by CTA pairs (tcgen05 cta_group::2), the
+                                two tiles of a CTA staggered so that epilogues hide behind MMAs (tower_stag.cu)    */
        AO_NN_FP16X3 = 1,     /* hi/lo split operands, 3 MMAs per k-step (1e-4 on trained nets), CTA pairs       */
-       AO_NN_FP16_1CTA = 2 };/* as AO_NN_FP16 but one CTA per MMA (cta_group::1); kept for comparison          */
+       AO_NN_FP16_1CTA = 2,  /* one CTA per MMA (cta_group::1), MMA and epilogue in lock-step; kept for comparison */
+       AO_NN_FP16_LOCKSTEP = 3 };/* CTA pairs with MMA and epilogue in lock-step (the round-1 v5 kernel); comparison */
 
 /* Mirrors the module-level constants of main.py:26-45 / eval_main.py:22-51 and ZeroAgent.__init__ (agents.py:39-53). */
 typedef struct ao_config {
@@ -147,6 +149,9 @@ int ao_umma_probe(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16
 /* same with per-tap disable-output-lane masks [ntaps][4] (bit r set: output row r is not updated by that tap) */
 int ao_umma_probe_masked(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init, float* out,
                          int row0, int ntaps, const int* shifts, const uint32_t* masks);
+
+/* raw tcgen05.mma throughput probe (csrc/umma_probe.cu): cycles of `iters`*8 back-to-back MMAs of one flavour */
+int ao_umma_rate(int flavour, int iters, unsigned long long* out2);
 
 #ifdef __cplusplus
 }

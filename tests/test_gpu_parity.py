@@ -295,7 +295,7 @@ def test_tower_single_cta_mode_vs_reference_model(cabi, name):
     sd = pvnet_ref.make_state_dict(int(fx["seed"]), nb, 5, 128, B, bn_jitter=bool(fx["jitter"]))
     ids = [unpad_id(r) for r in fx["ids"]]
     states = np.stack([O.get_state_pt(i, B, 5) for i in ids]).astype(np.float32)
-    for mode in (cabi.AO_NN_FP16_1CTA, cabi.AO_NN_FP16):
+    for mode in (cabi.AO_NN_FP16_1CTA, cabi.AO_NN_FP16, cabi.AO_NN_FP16_LOCKSTEP):
         eng = cabi.Engine(board_size=B, num_mcts=8, max_games=700, n_blocks=nb, nn_precision=mode)
         eng.load_state_dict(sd)
         for n in (len(ids), 1, 2, 5):

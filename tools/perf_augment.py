@@ -24,7 +24,6 @@ for rep in range(3):
 
 # device replay ring (deque(maxlen) semantics) + random.sample gather
 import random
-M = states_n = None
 buf = replay.DeviceReplayBuffer(9, maxlen=2_000_000)
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,7 +32,7 @@ for rep in range(3):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print(f"ring extend rep {rep}: {n} samples, len {len(buf)}: {ms:.2f} ms -> {(n*1948+slab.numel())/ms/1e6:.0f} GB/s")
-k = 32 * buf.cur_len
+k = len(buf) // 2
 idx = buf.sample_indices(k)
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

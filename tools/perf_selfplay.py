@@ -17,9 +17,10 @@ ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--node-cap", type=int, default=0)
 ap.add_argument("--x3", action="store_true")
 ap.add_argument("--single-cta", action="store_true")
+ap.add_argument("--mode", type=int, default=-1, help="AO_NN_* (overrides --x3 / --single-cta)")
 a = ap.parse_args()
 
-eng = _cabi.Engine(board_size=a.board, num_mcts=a.sims, max_games=a.games, seed=1, node_cap=a.node_cap, nn_precision=1 if a.x3 else (2 if a.single_cta else 0))
+eng = _cabi.Engine(board_size=a.board, num_mcts=a.sims, max_games=a.games, seed=1, node_cap=a.node_cap, nn_precision=a.mode if a.mode >= 0 else (1 if a.x3 else (2 if a.single_cta else 0)))
 eng.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, a.board))
 eng.selfplay_begin(a.games)
 prev = eng.selfplay_rounds(20)
