@@ -1,12 +1,42 @@
 """Batched arena: many concurrent matches between two agents, the B200 twin of eval_main.main's match loop
 (eval_main.py:204-333; `Evaluator.get_action` :153-170).  Each side owns its own search trees (one engine slot per
 match), ZeroAgents search with noise=False and tau=0 and pick `utils.argmax_onehot(pi)`, colours alternate by match
-parity (eval_main.py:233,316).  ELO bookkeeping and the web dashboard feed stay out of scope."""
+parity (eval_main.py:233,316).  `elo` / `elo_sequence` restate the reference's rating update (eval_main.py:191-198,
+285-312); the web dashboard feed stays out of scope."""
 from __future__ import annotations
 
 import numpy as np
 
 from . import _cabi, agents, utils
+
+
+def elo(player_elo, enemy_elo, p_winscore, e_winscore):
+    """eval_main.py:191-198 (K = 32, logistic expectation on a 400-point scale)."""
+    elo_diff = enemy_elo - player_elo
+    ex_pw = 1 / (1 + 10 ** (elo_diff / 400))
+    ex_ew = 1 / (1 + 10 ** (-elo_diff / 400))
+    player_elo += 32 * (p_winscore - ex_pw)
+    enemy_elo += 32 * (e_winscore - ex_ew)
+    return player_elo, enemy_elo
+
+
+def elo_sequence(outcomes, player_elo=1500, enemy_elo=1500):
+    """Ratings after a sequence of match outcomes in match order ('player' | 'enemy' | 'draw'), starting from the
+    reference's 1500 / 1500 (eval_main.py:216-217, 285-312).  Returns (player_elo, enemy_elo, result, winrate %)."""
+    result = {"Player": 0, "Enemy": 0, "Draw": 0}
+    for o in outcomes:
+        if o == "draw":
+            result["Draw"] += 1
+            player_elo, enemy_elo = elo(player_elo, enemy_elo, 0.5, 0.5)
+        elif o == "player":
+            result["Player"] += 1
+            player_elo, enemy_elo = elo(player_elo, enemy_elo, 1, 0)
+        else:
+            result["Enemy"] += 1
+            player_elo, enemy_elo = elo(player_elo, enemy_elo, 0, 1)
+    n = sum(result.values())
+    winrate = (result["Player"] + 0.5 * result["Draw"]) / n * 100 if n else 0.0
+    return player_elo, enemy_elo, result, winrate
 
 
 def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, num_mcts=800, inplanes=5, seed=0,
@@ -48,10 +78,16 @@ def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, n
         ply += 1
     res = dict(player_win=0, enemy_win=0, draw=0, black_win=int((winner == 1).sum()), white_win=int((winner == 2).sum()),
                plies=[len(r) - 1 for r in roots], unfinished=int((winner == 0).sum()))
+    outcomes = []
     for m in range(n_matches):
         if winner[m] == 3:
             res["draw"] += 1
+            outcomes.append("draw")
         elif winner[m] in (1, 2):
             black_won = winner[m] == 1
-            res["player_win" if black_won == bool(player_is_black[m]) else "enemy_win"] += 1
+            mine = black_won == bool(player_is_black[m])
+            res["player_win" if mine else "enemy_win"] += 1
+            outcomes.append("player" if mine else "enemy")
+    # the reference plays the matches one after the other and updates the ratings after each (eval_main.py:285-312)
+    res["player_elo"], res["enemy_elo"], _, res["winrate"] = elo_sequence(outcomes)
     return res

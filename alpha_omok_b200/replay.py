@@ -145,7 +145,10 @@ class DeviceReplayBuffer:
         """logical deque indices -> (states [k,5,B,B], pi [k,A], z [k]) CUDA float32, in that order."""
         k = len(indices)
         dev = self.states.device
-        idx = torch.as_tensor(np.asarray(indices, np.int64)).to(dev, non_blocking=False)
+        if isinstance(indices, torch.Tensor):
+            idx = indices.to(device=dev, dtype=torch.int64).contiguous()
+        else:
+            idx = torch.as_tensor(np.asarray(indices, np.int64)).to(dev, non_blocking=False)
         if k and (int(idx.min()) < 0 or int(idx.max()) >= self.len):
             raise IndexError("replay index out of range")
         s = torch.empty((k, 5, self.B, self.B), dtype=torch.float32, device=dev)

@@ -1,0 +1,227 @@
+"""Drop-in for the training half of 2_AlphaOmok/main.py: `train` (main.py:253-336),
+`save_model / save_dataset / load_data` (main.py:339-365) and the iteration loop (main.py:377-407), wired to the
+device-resident self-play engine and replay ring.
+
+What runs where:
+* self-play           -> csrc/tree.cu + csrc/tower_stag.cu (`ao_selfplay_*`), all games of an iteration concurrently;
+* replay buffer       -> csrc/augment.cu (`DeviceReplayBuffer`: deque(maxlen) + augment_dataset + random.sample on the GPU);
+* training step       -> PyTorch autograd on the same `model.PVNet` module, exactly the reference's arithmetic
+                         (train-mode BatchNorm, loss = MSE(v, z) - sum(pi * log p), Adam lr 2e-4 eps 1e-6).  This is the
+                         part of the reference that already is library code (torch.nn / torch.optim) and stays so;
+* multi-GPU           -> one process per GPU: games and replay records shard by rank (`replay.allgather_records`),
+                         gradients are averaged with one flat all-reduce per step over NCCL (gloo on CPU).
+The per-batch arithmetic is pinned against the unmodified reference (tests/golden/train_9_small.npz,
+tests/test_trainer_host.py::test_train_step_matches_reference_golden).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+import random
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import optim
+
+from . import model as model_mod, replay
+
+
+def make_optimizer(net, lr=2e-4, l2=0.0):
+    """main.py:85: optim.Adam(Agent.model.parameters(), lr=LR, weight_decay=L2, eps=1e-6)"""
+    return optim.Adam(net.parameters(), lr=lr, weight_decay=l2, eps=1e-6)
+
+
+def _allreduce_mean_grads(params, group=None):
+    """Average the gradients over all ranks with ONE collective (flat bucket)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+def train_step(net, optimizer, s_batch, pi_batch, z_batch, group=None):
+    """One optimizer step of main.py:286-305 on float32 tensors already on the model's device.
+    Returns (loss, v_loss, p_loss) as Python floats."""
+    p_batch, v_batch = net(s_batch)
+    v_loss = (v_batch - z_batch).pow(2).mean()
+    p_loss = -(pi_batch * p_batch.log()).sum(dim=-1).mean()
+    loss = v_loss + p_loss
+    optimizer.zero_grad()
+    loss.backward()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        _allreduce_mean_grads([p for g in optimizer.param_groups for p in g["params"]], group)
+    optimizer.step()
+    return loss.item(), v_loss.item(), p_loss.item()
+
+
+def train_batches(net, optimizer, states, pis, zs, batch_size=32, n_epochs=1, group=None):
+    """main.py:253-336 for an already sampled train_memory given as tensors [N,5,B,B], [N,A], [N]:
+    `DataLoader(train_memory, batch_size=BATCH_SIZE, shuffle=False)` = consecutive slices, a short last batch kept."""
+    net.train()
+    dev = next(net.parameters()).device
+    states, pis, zs = states.to(dev).float(), pis.to(dev).float(), zs.to(dev).float()
+    log = []
+    for _ in range(n_epochs):
+        for i in range(0, states.shape[0], batch_size):
+            log.append(train_step(net, optimizer, states[i:i + batch_size], pis[i:i + batch_size],
+                                  zs[i:i + batch_size], group))
+    return log
+
+
+def model_file(datetime_now, n_iter, step, data_dir="data"):
+    return os.path.join(data_dir, "{}_{}_{}_step_model.pickle".format(datetime_now, n_iter, step))
+
+
+def dataset_file(datetime_now, n_iter, step, data_dir="data"):
+    return os.path.join(data_dir, "{}_{}_{}_step_dataset.pickle".format(datetime_now, n_iter, step))
+
+
+def save_model(net, n_iter, step, datetime_now=None, data_dir="data"):
+    """main.py:339-342: torch.save(state_dict) as data/{yymmdd}_{iter}_{step}_step_model.pickle"""
+    path = model_file(datetime_now or datetime.now().strftime("%y%m%d"), n_iter, step, data_dir)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    torch.save(net.state_dict(), path)
+    return path
+
+
+def save_dataset(memory, n_iter, step, datetime_now=None, data_dir="data"):
+    """main.py:345-348: pickle of the replay memory (a DeviceReplayBuffer is written as the reference's deque of
+    (state, pi, z) tuples, so the file loads in the reference and vice versa)."""
+    path = dataset_file(datetime_now or datetime.now().strftime("%y%m%d"), n_iter, step, data_dir)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    from collections import deque
+    if isinstance(memory, replay.DeviceReplayBuffer):
+        memory = deque(memory.to_list(), maxlen=memory.maxlen)
+    with open(path, "wb") as f:
+        pickle.dump(memory, f, pickle.HIGHEST_PROTOCOL)
+    return path
+
+
+def parse_model_path(model_path):
+    """main.py:359-360: step and start_iter come from the file NAME ({date}_{iter}_{step}_step_model.pickle)."""
+    name = os.path.basename(model_path)
+    return int(name.split("_")[2]), int(name.split("_")[1]) + 1
+
+
+def load_model(net, model_path):
+    """main.py:356-358 / eval_main.py:95-101: partial update, so 2018 checkpoints without `num_batches_tracked` load."""
+    state = net.state_dict()
+    state.update(torch.load(model_path, map_location="cpu"))
+    net.load_state_dict(state)
+    return net
+
+
+class Trainer:
+    """The module-level state and functions of main.py as an object (names follow main.py:26-85)."""
+
+    def __init__(self, board_size=9, n_mcts=400, tau_thres=6, seed=0, n_blocks=10, in_planes=5, out_planes=128,
+                 n_selfplay=100, memory_size=30000, n_epochs=1, batch_size=32, lr=2e-4, l2=0.0, device=None,
+                 data_dir="data", group=None):
+        self.BOARD_SIZE, self.N_MCTS, self.TAU_THRES, self.SEED = board_size, n_mcts, tau_thres, seed
+        self.N_BLOCKS, self.IN_PLANES, self.OUT_PLANES = n_blocks, in_planes, out_planes
+        self.N_SELFPLAY, self.MEMORY_SIZE, self.N_EPOCHS, self.BATCH_SIZE = n_selfplay, memory_size, n_epochs, batch_size
+        self.data_dir, self.group = data_dir, group
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        random.seed(seed)           # main.py:59-63
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.model = model_mod.PVNet(n_blocks, in_planes, out_planes, board_size).to(self.device)
+        self.optimizer = make_optimizer(self.model, lr, l2)
+        self.rep_memory = replay.DeviceReplayBuffer(board_size, maxlen=memory_size, tau_thres=tau_thres, device=self.device)
+        self.step, self.start_iter, self.total_epoch = 0, 0, 0
+        self.result = {"Black": 0, "White": 0, "Draw": 0}
+        self._engine = None
+        self._episodes = 0
+
+    # ---------------------------------------------------------------- self-play (main.py:122-250)
+    def self_play(self, n_selfplay=None):
+        """All `n_selfplay` episodes of this rank concurrently on the device; records of every rank are all-gathered
+        and appended (8-fold augmented) to every rank's replay ring. Returns len(cur_memory) over all ranks."""
+        from . import _cabi
+        n = n_selfplay or self.N_SELFPLAY
+        self.model.eval()
+        if self._engine is None or self._engine.G < n:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = _cabi.Engine(board_size=self.BOARD_SIZE, num_mcts=self.N_MCTS, max_games=n, noise=True,
+                                        tau_thres=self.TAU_THRES, n_blocks=self.N_BLOCKS, inplanes=self.IN_PLANES,
+                                        seed=self.SEED, device=self.device.index or 0)
+        eng = self._engine
+        eng.load_state_dict(self.model.state_dict())
+        eng.choose_nn_precision()
+        # per-game decision-stream keys are global episode numbers: independent of how games are sharded over ranks
+        eng.selfplay_begin(n, first_key=self._episodes + self.rank * n)
+        self._episodes += n * self.world
+        st = eng.selfplay_rounds(256)
+        while st["running"]:
+            st = eng.selfplay_rounds(256)
+        if st["errors"]:
+            raise _cabi.AoError("%d game tree(s) overflowed their arena; raise node_cap" % st["errors"])
+        slab = replay.allgather_records(replay.device_records(eng, n), self.group)
+        winners = slab[:, 2]
+        for name, code in (("Black", 1), ("White", 2), ("Draw", 3)):
+            self.result[name] += int((winners == code).sum())
+        self.rep_memory.extend_records(slab)
+        return self.rep_memory.cur_len
+
+    # ---------------------------------------------------------------- training (main.py:253-336)
+    def train(self, n_epochs=None):
+        k = self.BATCH_SIZE * self.rep_memory.cur_len          # BATCH_SIZE * len(cur_memory), main.py:263-264
+        idx = self.rep_memory.sample_indices(k)                # every rank draws the same indices (same seed) ...
+        idx = idx[self.rank::self.world]                       # ... and trains on its slice of the batches' rows
+        s, pi, z = self.rep_memory.gather(idx)
+        log = train_batches(self.model, self.optimizer, s, pi, z, max(1, self.BATCH_SIZE // self.world),
+                            n_epochs or self.N_EPOCHS, self.group)
+        self.step += len(log)
+        self.total_epoch += n_epochs or self.N_EPOCHS
+        if log:
+            logging.warning("{:2} Epoch Loss: {:.4f}   Loss_V: {:.4f}   Loss_P: {:.4f}".format(
+                self.total_epoch, *np.mean(np.asarray(log), axis=0)))
+        return log
+
+    # ---------------------------------------------------------------- checkpoints (main.py:339-365)
+    def save(self, n_iter, datetime_now=None):
+        if self.rank != 0:
+            return None, None
+        return (save_model(self.model, n_iter, self.step, datetime_now, self.data_dir),
+                save_dataset(self.rep_memory, n_iter, self.step, datetime_now, self.data_dir))
+
+    def load_data(self, model_path=None, dataset_path=None):
+        if model_path:
+            load_model(self.model, model_path)
+            self.step, self.start_iter = parse_model_path(model_path)
+        if dataset_path:
+            with open(dataset_path, "rb") as f:
+                memory = pickle.load(f)
+            self.rep_memory = replay.DeviceReplayBuffer(self.BOARD_SIZE, maxlen=self.MEMORY_SIZE,
+                                                        tau_thres=self.TAU_THRES, device=self.device)
+            self.rep_memory.extend_list(memory)
+
+    def reset_iter(self):
+        self.result = {"Black": 0, "White": 0, "Draw": 0}
+        self.total_epoch = 0
+        self.rep_memory.cur_len = 0
+
+    # ---------------------------------------------------------------- iteration loop (main.py:377-407)
+    def run(self, total_iter, save_every=100, n_selfplay_later=1):
+        """main.py:386-407. The reference fills the buffer with N_SELFPLAY episodes in iteration 0 and plays
+        N_SELFPLAY = 1 episode per iteration afterwards (main.py:397-400); `n_selfplay_later` is that second number -
+        on a B200 thousands of concurrent episodes per iteration cost about the same wall time as one."""
+        for n_iter in range(self.start_iter, total_iter):
+            if n_iter > 0:
+                self.self_play(n_selfplay_later)
+                self.train()
+            else:
+                self.self_play(self.N_SELFPLAY)
+            if n_iter % save_every == 0:
+                self.save(n_iter + save_every)
+            self.reset_iter()

@@ -240,12 +240,60 @@ def gen_nn(R):
         print(name, "OK  max|p-p_ref|", float((p - p2).abs().max()))
 
 
+def gen_train(R):
+    """main.py:253-305 on a fixed train_memory: the reference's PVNet (train-mode BN), loss and Adam, restated from
+    main.py:286-305 because main.py itself cannot be imported (import-time side effects)."""
+    from torch import optim
+    from torch.utils.data import DataLoader
+    B, n_block, A = 9, 2, 81
+    rs = np.random.RandomState(21)
+    sd = pvnet_ref.make_state_dict(3, n_block, 5, 128, B, bn_jitter=True)
+    net = R.model.PVNet(n_block, 5, 128, B)
+    net.load_state_dict(sd, strict=False)
+    optimizer = optim.Adam(net.parameters(), lr=2e-4, weight_decay=0, eps=1e-6)   # main.py:85
+    train_memory = []
+    for _ in range(80):  # 2 full batches of 32 + a short one of 16
+        k = rs.randint(0, 60)
+        rid = (0,) + tuple(int(x) for x in rs.permutation(A)[:k])
+        pi = rs.dirichlet(np.full(A, 0.3))
+        train_memory.append((R.utils.get_state_pt(rid, B, 5), pi, float(rs.randint(-1, 2))))
+    dataloader = DataLoader(train_memory, batch_size=32, shuffle=False, pin_memory=False)   # main.py:266-269
+    net.train()
+    losses = []
+    for epoch in range(2):
+        for i, (s, pi, z) in enumerate(dataloader):
+            s_batch, pi_batch, z_batch = s.float(), pi.float(), z.float()
+            p_batch, v_batch = net(s_batch)
+            v_loss = (v_batch - z_batch).pow(2).mean()
+            p_loss = -(pi_batch * p_batch.log()).sum(dim=-1).mean()
+            loss = v_loss + p_loss
+            losses.append((loss.item(), v_loss.item(), p_loss.item()))
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+    out_sd = net.state_dict()
+    np.savez_compressed(os.path.join(HERE, "train_9_small.npz"), B=B, n_block=n_block, sd_seed=3,
+                        states=np.stack([m[0] for m in train_memory]).astype(np.float32),
+                        pis=np.stack([m[1] for m in train_memory]), zs=np.asarray([m[2] for m in train_memory]),
+                        losses=np.asarray(losses, np.float64),
+                        conv1_weight=out_sd["conv1.weight"].numpy(), bn1_running_mean=out_sd["bn1.running_mean"].numpy(),
+                        policy_fc_bias=out_sd["policy_head.policy_fc.bias"].numpy(),
+                        value_fc2_weight=out_sd["value_head.value_fc2.weight"].numpy(),
+                        abs_sums=np.asarray([float(v.double().abs().sum()) for k, v in out_sd.items()
+                                             if not k.endswith("num_batches_tracked")]))
+    print("train_9_small OK  losses", losses[0], "->", losses[-1])
+
+
 def main():
     R = import_reference()
     np.random.choice = PATCH.choice
     np.random.dirichlet = PATCH.dirichlet
+    if "--only-train" in sys.argv:
+        gen_train(R)
+        return
     gen_rules(R)
     gen_nn(R)
+    gen_train(R)
     gen_mcts_game(R, "mcts_9_synth_s40", 9, 40, seed=11, game=0, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
     gen_mcts_game(R, "mcts_9_synth_s400", 9, 400, seed=12, game=3, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
     gen_mcts_game(R, "mcts_9_synth_nonoise", 9, 60, seed=13, game=1, noise=False, tau_thres=0, max_moves=None, nn_kind="synth")

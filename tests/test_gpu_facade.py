@@ -182,3 +182,41 @@ def test_device_replay_ring_matches_deque_and_random_sample():
         assert len(buf2) == len(buf)
         a, b = buf.gather(list(range(len(buf)))), buf2.gather(list(range(len(buf2))))
         assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_trainer_iteration_loop_on_device(tmp_path):
+    """main.py's iteration loop with every stage on the GPU - device self-play -> replay ring -> sampled
+    batches -> PyTorch train step (the reference's arithmetic, pinned on CPU by tests/test_trainer_host.py) -> weights
+    re-folded into the tower for the next round -> checkpoint / dataset files in the reference's formats."""
+    from alpha_omok_b200 import trainer
+    tr = trainer.Trainer(board_size=9, n_mcts=16, n_blocks=2, n_selfplay=8, memory_size=3000, batch_size=32, seed=0,
+                         data_dir=str(tmp_path))
+    w0 = {k: v.clone() for k, v in tr.model.state_dict().items()}
+    n0 = tr.self_play(8)                                  # iteration 0: fill the buffer (main.py:401-402)
+    assert n0 > 8 * 9 and len(tr.rep_memory) == min(3000, 8 * n0) and sum(tr.result.values()) == 8
+    tr.reset_iter()
+    n1 = tr.self_play(2)                                  # iteration 1: self-play + train (main.py:397-400)
+    log = tr.train()
+    assert len(log) == n1 and tr.step == n1               # BATCH_SIZE * len(cur_memory) samples in batches of BATCH_SIZE
+    assert all(np.isfinite(l).all() for l in log)
+    assert log[0][0] > 4.0 and np.mean([l[0] for l in log[-5:]]) < np.mean([l[0] for l in log[:5]])  # it learns
+    changed = [k for k, v in tr.model.state_dict().items() if not torch.equal(v, w0[k])]
+    assert "conv1.weight" in changed and "layers.1.bn2.running_var" in changed
+    # the updated weights reach the tower: the device forward equals the torch eval forward of the trained module
+    x = tr.rep_memory.gather(list(range(16)))[0]
+    tr.model.eval()
+    with torch.no_grad():
+        p_dev, v_dev = tr.model(x)                        # facade: eval + no_grad -> ao_nn_forward
+    p_ref, v_ref = pvnet_ref.pvnet_forward({k: v.cpu() for k, v in tr.model.state_dict().items()}, x.cpu())
+    assert (p_dev.cpu() - p_ref).abs().max() < 1e-4 and (v_dev.cpu() - v_ref).abs().max() < 1e-4
+    n2 = tr.self_play(2)                                  # next round plays with the new weights
+    assert n2 > 0
+    # checkpoints
+    mpath, dpath = tr.save(100, datetime_now="181001")
+    tr2 = trainer.Trainer(board_size=9, n_mcts=16, n_blocks=2, n_selfplay=8, memory_size=3000, data_dir=str(tmp_path))
+    tr2.load_data(mpath, dpath)
+    assert tr2.step == tr.step and tr2.start_iter == 101 and len(tr2.rep_memory) == len(tr.rep_memory)
+    for k, v in tr.model.state_dict().items():
+        assert torch.equal(v, tr2.model.state_dict()[k])
+    a, b = tr.rep_memory.gather(list(range(len(tr.rep_memory)))), tr2.rep_memory.gather(list(range(len(tr2.rep_memory))))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
