@@ -288,13 +288,16 @@ def run_ours(a):
         full = {"ms": f0.elapsed_time(f1), "games": G, "moves": fs["moves"], "sims": fs["sims"], "errors": fs["errors"]}
         # the one exchange step of the path: all-gather of this round's replay records into every rank
         from alpha_omok_b200 import replay
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        local = replay.device_records(eng, G)          # pack kernel on the engine stream (synchronised inside)
-        gathered = replay.allgather_records(local)     # NCCL all_gather_into_tensor of the fixed-size slabs
-        g1.record()
-        torch.cuda.synchronize()
+        for timed in (False, True):                        # one untimed pass: allocator / communicator warm-up
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            local = replay.device_records(eng, G)          # pack kernel on the engine stream (synchronised inside)
+            gathered = replay.allgather_records(local)     # NCCL all_gather_into_tensor of the fixed-size slabs
+            g1.record()
+            torch.cuda.synchronize()
+            if not timed:
+                del gathered
         full.update(allgather_ms=g0.elapsed_time(g1), allgather_bytes=int(gathered.numel()),
                     allgather_ok=bool(torch.equal(gathered[rank * G:(rank + 1) * G], local)))
         del gathered

@@ -1,0 +1,44 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / synccheck / racecheck): tower forward in every operand mode
+(9x9 and 15x15), a few self-play rounds with the real tower, the replay ring kernels."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from alpha_omok_b200 import _cabi
+from oracle import pvnet_ref  # weight generator only
+
+modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 1, 2, 3]
+for B in (9, 15):
+    A = B * B
+    sd = pvnet_ref.make_state_dict(0, 2, 5, 128, B)
+    rs = np.random.RandomState(1)
+    x = np.zeros((7, 5, B, B), np.float32)
+    x[:, 2:4] = (rs.rand(7, 2, B, B) < 0.2)
+    x[:, 0:2] = x[:, 2:4]
+    ref = None
+    for mode in modes:
+        eng = _cabi.Engine(board_size=B, num_mcts=8, max_games=8, n_blocks=2, nn_precision=mode)
+        eng.load_state_dict(sd)
+        p, v = eng.nn_forward(x)
+        assert np.isfinite(p).all() and abs(p.sum(1) - 1).max() < 1e-4
+        if ref is not None:
+            assert abs(p - ref).max() < 1e-4
+        ref = p
+        eng.selfplay_begin(8)
+        st = eng.selfplay_rounds(30)
+        assert st["errors"] == 0 and st["sims"] > 0
+        eng.close()
+        print("board", B, "mode", mode, "ok", flush=True)
+import torch
+from alpha_omok_b200 import replay
+eng = _cabi.Engine(board_size=9, num_mcts=8, max_games=4, seed=6, eval_mode=_cabi.AO_EVAL_SYNTH)
+eng.selfplay_begin(4)
+st = eng.selfplay_rounds(1)
+while st["running"]:
+    st = eng.selfplay_rounds(1)
+slab = replay.device_records(eng, 4).clone()
+buf = replay.DeviceReplayBuffer(9, maxlen=500)
+for _ in range(3):
+    buf.extend_records(slab)
+s, p, z = buf.sample(64)
+torch.cuda.synchronize()
+print("replay ring ok", len(buf), flush=True)
