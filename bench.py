@@ -191,8 +191,13 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 meanwhile (e.g. NCCL's version banner,
+    # which ignores NCCL_DEBUG_FILE on some builds) is sent to stderr; the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL banner)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, G, S = a.board, a.games, a.sims
     A = B * B
@@ -360,7 +365,8 @@ def run_ours(a):
             line["cpu_baseline"] = {"value": v, "unit": "expansions/s", "cores": workers, "kind": "port",
                                     "sample": f"{workers} single-thread workers x {a.cpu_seconds:.0f} s of the oracle port's simulation loop "
                                               f"(first move, {B}x{B}, {S} sims budget, torch CPU fp32 PVNet); host has {cores} cpus"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         dist.barrier()
