@@ -16,9 +16,11 @@
 // thread).  Both tiles use every tap, so the weight ring holds exactly one layer of this CTA's half of B (9 slots x
 // 16 KB): T0 reads a slot, T1 reads it again and releases it, and the next layer's tap streams in behind it.
 //
-// Warp roles (448 threads): 0-7 epilogue, 8 weight/bias producer, 9 MMA issuer (leader CTA) or weights-landed
-// forwarder (peer CTA), 10-13 heads (1x1 conv outputs -> FC/softmax/tanh of the PREVIOUS pass while the tower of the
-// next pass is already running).
+// Warp roles (480 threads): 0-7 epilogue, 8 and 9 the MMA issuers of tile 1 / tile 0 (leader CTA; in the peer CTA warp 9
+// forwards weights-landed), 10-13 heads (1x1 conv outputs -> FC/softmax/tanh of the PREVIOUS pass while the tower of the
+// next pass is already running), 14 weight/bias producer.
+// Two issuing warps on two different scheduler ports: a single thread gets one M256 N128 K16 MMA per ~109 cycles out of
+// the tensor pipe, two threads with their own accumulators one per ~87 (tools/probe_mma_rate.py).
 #include <cuda_fp16.h>
 #include <stdio.h>
 
@@ -27,7 +29,7 @@
 namespace ao {
 namespace {
 
-constexpr int kStagThreads = 448;
+constexpr int kStagThreads = 480;
 constexpr int kHeadThreads = 128;
 
 template <int B>
@@ -111,12 +113,12 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_empty[s], 2);  // both MMA streams are done with the tap
       mbar_init(&bar_peer_full[s], 1);
     }
     for (int t = 0; t < 4; ++t) mbar_init(&bar_act[t], 16);  // lane 0 of the 8 epilogue warps of each CTA of the pair
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&bar_acc[t], 1);
+      mbar_init(&bar_acc[t], 2);  // own tile accumulated + the other stream no longer reads this tile's boundary rows
       mbar_init(&bar_bias[t], 1);
     }
     mbar_init(bar_feat_full, 8);
@@ -131,7 +133,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
   tc_fence_after_sync();
   const uint32_t tmem = *s_tmem;
 
-  if (warp == 8) {
+  if (warp == 14) {
     // =========================================================== weight + bias producer: slot = tap, one layer in flight
     if (lane == 0) {
       uint32_t lc = 0;
@@ -157,10 +159,11 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 9 || warp == 8) {
+    const int stream = 9 - warp;  // MMA stream 0 (warp 9) owns tile 0, stream 1 (warp 8) tile 1: two scheduler ports
     if (!leader) {
       // ---- peer CTA: forward "my half of slot s has landed" to the leader (the operand-ready arrivals go there directly)
-      if (lane == 0) {
+      if (stream == 0 && lane == 0) {
         int g0, ng, ntiles, n_k = 0;
         while (get_pass<G::GPC, G::A, PAIR>(n_k, n, g0, ng, ntiles)) ++n_k;
         const uint32_t n_stage = (uint32_t)(n_k * n_layers) * 9u;
@@ -171,7 +174,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
         }
       }
     } else {
-      // =========================================================== MMA issuer (leader CTA)
+      // =========================================================== MMA issuers (leader CTA), one per tile
       const uint32_t idesc = umma_idesc_f16_f32(256, 128);
       const uint32_t lbo_a = (uint32_t)G::Rows * 16u;
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_act), lbo_a);
@@ -183,6 +186,10 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       const long long dbg_t0 = W.dbg ? clock64() : 0;
       int g0, ng, ntiles;
       for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+        if (stream == 1 && ntiles < kTiles) {  // one-game tail pass: tile 1 holds no board
+          lc += (uint32_t)n_layers;
+          continue;
+        }
         for (int l = 0; l < n_layers; ++l, ++lc) {
           const bool to_b = (l & 1) == 0;      // stem and conv2 accumulate in accB (holds the block input x)
           const bool residual = to_b && l > 0;
@@ -192,8 +199,8 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
           // columns every epilogue thread converts first, 1: {2,3,6,7}, 2: all); first_use: wait for the slot's
           // weights; release: hand the slot back
           auto issue = [&](const int tile, const int st_lo, const int st_hi, const int grp, const bool first_use,
-                           const bool release) {
-            if (nk == 1 && grp == 1) return;  // stem: a single k-step
+                           const int release) {  // release: number of arrivals on the slot's empty barrier (0, 1, 2)
+            const bool no_mma = nk == 1 && grp == 1;  // stem: a single k-step (group 0); only the releases remain
             for (int st = st_lo; st < st_hi; ++st) {
               if (first_use) {
                 const long long t_f0 = W.dbg ? clock64() : 0;
@@ -214,13 +221,13 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
                 uint32_t acc = (residual || st > 0 || grp == 1) ? 1u : 0u;
 #pragma unroll
                 for (int j = 0; j < kC / 16; ++j) {
-                  if (j >= nk) break;
+                  if (j >= nk || no_mma) break;
                   if (grp != 2 && ((j >> 1) & 1) != grp) continue;
                   umma_f16_ss_pair_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc,
                                           acc, m0, m1, m2, m3);
                   acc = 1u;
                 }
-                if (release) umma_commit_pair(&bar_empty[st]);
+                for (int r = 0; r < release; ++r) umma_commit_pair(&bar_empty[st]);
               }
               __syncwarp();
             }
@@ -236,28 +243,36 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
             if (elect_one()) umma_commit_pair(&bar_acc[tile]);
             __syncwarp();
           };
-          if (ntiles == kTiles) {
+          if (ntiles < kTiles) {          // one-game tail pass: stream 0 alone, arriving for both streams
             wait_act(0);
-            issue(0, 0, 5, 0, true, false);
             wait_act(1);
-            issue(0, 0, 5, 1, false, false);
+            issue(0, 0, 9, 2, true, 2);
+            commit_acc(0);
+            commit_acc(0);
+          } else if (stream == 0) {       // T0: centre/negative taps need T0's epilogue only, positive taps also T1's
+            wait_act(0);
+            issue(0, 0, 5, 0, true, 0);
+            wait_act(1);
+            issue(0, 0, 5, 1, false, 1);
             wait_act(2);
-            issue(0, 5, 9, 0, true, false);
+            issue(0, 5, 9, 0, true, 0);
             wait_act(3);
-            issue(0, 5, 9, 1, false, false);
-            issue(1, 0, 5, 2, false, true);
-            commit_acc(0);
-            issue(1, 5, 9, 2, false, true);
-            commit_acc(1);
-          } else {  // one-game tail pass: tile 0 only
+            issue(0, 5, 9, 1, false, 1);
+            commit_acc(0);                // T0 accumulated
+            commit_acc(1);                // T0 no longer reads T1's first rows
+          } else {                        // T1: every tap reads T1's own rows, the negative ones also T0's last rows
             wait_act(0);
             wait_act(1);
-            issue(0, 0, 9, 2, true, true);
-            commit_acc(0);
+            wait_act(2);
+            wait_act(3);
+            issue(1, 0, 5, 2, true, 1);
+            commit_acc(0);                // T1 no longer reads T0's last rows: T0's epilogue may overwrite them
+            issue(1, 5, 9, 2, true, 1);
+            commit_acc(1);                // T1 accumulated
           }
         }
       }
-      if (W.dbg && blockIdx.x == 0 && lane == 0) {
+      if (W.dbg && blockIdx.x == 0 && lane == 0 && stream == 0) {
         atomicAdd(&W.dbg[0], (unsigned long long)(clock64() - dbg_t0));
         atomicAdd(&W.dbg[1], (unsigned long long)dbg_act_wait);
         atomicAdd(&W.dbg[2], (unsigned long long)dbg_full_wait);

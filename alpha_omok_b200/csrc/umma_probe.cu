@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(int flavour, int iter
   uint8_t* s_w = smem + kRateAct;
   uint8_t* s_scr = s_w + kRateW;
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_scr + kRateScratch);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 4);
   volatile int* s_stop = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < (kRateAct + kRateW + kRateScratch) / 16; i += 320) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    ao::mbar_init(&bar[0], 1);
+    for (int i = 0; i < 4; ++i) ao::mbar_init(&bar[i], 1);
     *s_stop = 0;
     ao::fence_mbar_init();
   }
@@ -233,8 +233,12 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(int flavour, int iter
   const uint32_t tmem = *s_tmem;
   const bool leader = !PAIR || ao::cluster_ctarank() == 0u;
   const bool masked = flavour & 1, shifted = flavour & 4, pressure = flavour & 8;
-  if (warp == 9) {
+  // several issuing warps (9, 8, 7, 6), each with its own accumulator and its share of the MMAs
+  const int n_issuers = (flavour & 512) ? 4 : ((flavour & 256) ? 2 : 1);
+  const bool two_issuers = n_issuers > 1;
+  if (warp <= 9 && warp > 9 - n_issuers) {
     if (leader) {
+      iters /= n_issuers;
       const int N = (flavour & 16) ? 64 : ((flavour & 64) ? 256 : 128);
       const uint32_t idesc = ao::umma_idesc_f16_f32(PAIR ? 256 : 128, N);
       const uint32_t brows = (uint32_t)(PAIR ? N / 2 : N);
@@ -245,11 +249,24 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(int flavour, int iter
       const uint32_t kAStep = (2u * kRateRows * 16u) >> 4, kBStep = (2u * brows * 16u) >> 4;
       const long long t0 = clock64();
       if (ao::elect_one()) {
+        uint32_t wph = 0;
         for (int it = 0; it < iters; ++it) {
+          // 1024: commit every 8 MMAs (no wait); 2048: commit AND wait for completion every 16 MMAs (shallow queue);
+          // 4096: the same every 32 MMAs
+          if ((flavour & 1024) && it > 0) {
+            if (PAIR) ao::umma_commit_pair(&bar[3]); else ao::umma_commit(&bar[3]);
+          }
+          if (((flavour & 2048) && it > 0 && (it & 1) == 0) || ((flavour & 4096) && it > 0 && (it & 3) == 0)) {
+            if (PAIR) ao::umma_commit_pair(&bar[2]); else ao::umma_commit(&bar[2]);
+            ao::mbar_wait(&bar[2], wph);
+            wph ^= 1u;
+          }
           const int tap = it % 9;
           const int shift = shifted ? (tap / 3 - 1) * 9 + (tap % 3 - 1) : 0;
           const uint32_t a = a_lo0 + (uint32_t)(16 + ((it / 9) & 1) * 128 + shift);
-          const uint32_t d0 = tmem + (uint32_t)((flavour & 64) ? ((it / 9) & 1) * 256 : ((it / 9) & 3) * 128);
+          const uint32_t d0 = n_issuers == 4 ? tmem + (uint32_t)((9 - warp) * 128)
+                              : two_issuers ? tmem + (uint32_t)(((warp & 1) * 2 + ((it / 9) & 1)) * 128)
+                                          : tmem + (uint32_t)((flavour & 64) ? ((it / 9) & 1) * 256 : ((it / 9) & 3) * 128);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t d = (flavour & 32) ? tmem + (uint32_t)((j & 3) * 128) : d0;
@@ -277,22 +294,22 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(int flavour, int iter
             }
           }
         }
-        if (PAIR) ao::umma_commit_pair(&bar[0]);
-        else ao::umma_commit(&bar[0]);
+        if (PAIR) ao::umma_commit_pair(&bar[9 - warp]);
+        else ao::umma_commit(&bar[9 - warp]);
       }
       __syncwarp();
-      ao::mbar_wait(&bar[0], 0);
+      ao::mbar_wait(&bar[9 - warp], 0);
       const long long t1 = clock64();
       *s_stop = 1;
-      if (lane == 0 && blockIdx.x == 0) {
+      if (lane == 0 && blockIdx.x == 0 && warp == 9) {
         out[0] = (unsigned long long)(t1 - t0);
-        out[1] = (unsigned long long)iters * 8ull;
+        out[1] = (unsigned long long)iters * 8ull * (unsigned long long)n_issuers;
       }
     }
-  } else if (warp < 8 && pressure && leader) {
+  } else if (warp < 6 && pressure && leader) {
     uint32_t k = 0;
     while (!*s_stop) {
-      *reinterpret_cast<uint4*>(s_scr + ((k * 256u + (uint32_t)tid) * 16u) % kRateScratch) = make_uint4(k, k, k, k);
+      *reinterpret_cast<uint4*>(s_scr + ((k * 192u + (uint32_t)tid) * 16u) % kRateScratch) = make_uint4(k, k, k, k);
       ++k;
     }
   }
