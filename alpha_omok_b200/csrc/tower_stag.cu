@@ -377,9 +377,9 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
                 pk.z = *reinterpret_cast<uint32_t*>(&h);
                 h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
                 pk.w = *reinterpret_cast<uint32_t*>(&h);
-                *reinterpret_cast<uint4*>(s_act + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pk;
+                if (!(W.xflags & 32)) *reinterpret_cast<uint4*>(s_act + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pk;
               }
-              if (to_b) tmem_st32(stash_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
+              if (to_b && !(W.xflags & 16)) tmem_st32(stash_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -392,9 +392,14 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
           };
           if (!(W.xflags & 4) || last) {
             uint32_t va[32], vb[32];
-            tmem_ld32(acc_addr + (uint32_t)(half * 64), va);
-            tmem_ld32(acc_addr + (uint32_t)(half * 64 + 32), vb);
-            tmem_ld_wait();
+            if (!(W.xflags & 64) || last) {
+              tmem_ld32(acc_addr + (uint32_t)(half * 64), va);
+              tmem_ld32(acc_addr + (uint32_t)(half * 64 + 32), vb);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) va[j] = vb[j] = (uint32_t)(j + lane) << 20;
+            }
             process(va, half * 2);
             if (!last) arrive_act(t * 2);  // k-steps {0,1} / {4,5} of the next layer can start
             process(vb, half * 2 + 1);

@@ -16,6 +16,46 @@ from torch import nn
 from . import _cabi
 
 
+def seeded_state_dict(seed, n_block=10, inplanes=5, planes=128, board_size=9, bn_jitter=False, gain=1.0):
+    """Reproducible "random-init PVNet" (BASELINE configs 1-4) without torch's RNG: numpy MT19937 draws with torch's
+    default distributions (uniform +-1/sqrt(fan_in) for conv / linear weights and linear biases; BN gamma=1, beta=0,
+    mean=0, var=1 as model.py:86-89), optionally with jittered BN statistics to exercise the BN folding.  Returns an
+    ordered dict of float32 tensors with the reference's parameter names (load with strict=False: no
+    num_batches_tracked keys, like the reference's 2018 checkpoints)."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    a = board_size * board_size
+    sd = {}
+
+    def uni(shape, fan_in, g=1.0):
+        b = g / np.sqrt(fan_in)
+        return torch.from_numpy(rs.uniform(-b, b, size=shape).astype(np.float32))
+
+    def bn(prefix, c):
+        lo_hi = ((0.5, 1.5), (-0.2, 0.2), (-0.1, 0.1), (0.5, 1.5)) if bn_jitter else None
+        for i, (name, const) in enumerate((("weight", 1.0), ("bias", 0.0), ("running_mean", 0.0), ("running_var", 1.0))):
+            sd[prefix + "." + name] = (torch.from_numpy(rs.uniform(*lo_hi[i], c).astype(np.float32)) if bn_jitter
+                                       else torch.full((c,), const))
+
+    sd["conv1.weight"] = uni((planes, inplanes, 3, 3), inplanes * 9, gain)
+    bn("bn1", planes)
+    for i in range(n_block):
+        for c in (1, 2):
+            sd[f"layers.{i}.conv{c}.weight"] = uni((planes, planes, 3, 3), planes * 9, gain)
+            bn(f"layers.{i}.bn{c}", planes)
+    sd["policy_head.policy_head.weight"] = uni((2, planes, 1, 1), planes, gain)
+    bn("policy_head.policy_bn", 2)
+    sd["policy_head.policy_fc.weight"] = uni((a, 2 * a), 2 * a, gain)
+    sd["policy_head.policy_fc.bias"] = uni((a,), 2 * a)
+    sd["value_head.value_head.weight"] = uni((1, planes, 1, 1), planes, gain)
+    bn("value_head.value_bn", 1)
+    sd["value_head.value_fc1.weight"] = uni((planes, a), a, gain)
+    sd["value_head.value_fc1.bias"] = uni((planes,), a)
+    sd["value_head.value_fc2.weight"] = uni((1, planes), planes, gain)
+    sd["value_head.value_fc2.bias"] = uni((1,), planes)
+    return sd
+
+
 def _conv(cin, cout, k):
     return nn.Conv2d(cin, cout, kernel_size=k, padding=k // 2, bias=False)
 

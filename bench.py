@@ -183,7 +183,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
     from alpha_omok_b200 import _cabi
-    from oracle import pvnet_ref  # deterministic numpy weight generator only (no oracle compute on this path)
+    from alpha_omok_b200.model import seeded_state_dict
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,7 +203,7 @@ def run_ours(a):
     A = B * B
     stream = torch.cuda.Stream()
     eng = _cabi.Engine(board_size=B, num_mcts=S, max_games=G, seed=1000 + rank, device=local, stream=stream.cuda_stream)
-    eng.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, B))
+    eng.load_state_dict(seeded_state_dict(0, 10, 5, 128, B))
 
     def barrier():
         torch.cuda.synchronize()

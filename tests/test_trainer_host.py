@@ -150,3 +150,15 @@ def test_gradient_allreduce_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "rank0ok" in res.stdout and "rank1ok" in res.stdout, res.stdout
+
+
+def test_seeded_weight_generator_matches_the_oracles():
+    """bench.py / tools use the product package's generator for "random-init PVNet (numpy seed s)"; the tests use the
+    oracle's: both must be the same function so that fixtures and bench weights agree"""
+    from alpha_omok_b200 import model
+    for kw in (dict(seed=0), dict(seed=3, n_block=2, bn_jitter=True), dict(seed=1, board_size=15, n_block=1, gain=2.0)):
+        a = model.seeded_state_dict(**kw)
+        b = pvnet_ref.make_state_dict(**kw)
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert a[k].dtype == torch.float32 and torch.equal(a[k], b[k]), k

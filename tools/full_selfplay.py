@@ -3,7 +3,7 @@ import argparse, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _cabi
-from oracle import pvnet_ref  # weight generator only
+from alpha_omok_b200.model import seeded_state_dict
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--board", type=int, default=9)
@@ -11,7 +11,7 @@ ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--sims", type=int, default=400)
 a = ap.parse_args()
 eng = _cabi.Engine(board_size=a.board, num_mcts=a.sims, max_games=a.games, seed=7)
-eng.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, a.board))
+eng.load_state_dict(seeded_state_dict(0, 10, 5, 128, a.board))
 eng.selfplay_begin(a.games)
 t0 = time.time()
 st = eng.selfplay_rounds(a.sims)

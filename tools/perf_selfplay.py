@@ -6,7 +6,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _cabi  # noqa: E402
-from oracle import pvnet_ref  # noqa: E402  (weight generator only)
+from alpha_omok_b200.model import seeded_state_dict
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--board", type=int, default=9)
@@ -21,7 +21,7 @@ ap.add_argument("--mode", type=int, default=-1, help="AO_NN_* (overrides --x3 / 
 a = ap.parse_args()
 
 eng = _cabi.Engine(board_size=a.board, num_mcts=a.sims, max_games=a.games, seed=1, node_cap=a.node_cap, nn_precision=a.mode if a.mode >= 0 else (1 if a.x3 else (2 if a.single_cta else 0)))
-eng.load_state_dict(pvnet_ref.make_state_dict(0, 10, 5, 128, a.board))
+eng.load_state_dict(seeded_state_dict(0, 10, 5, 128, a.board))
 eng.selfplay_begin(a.games)
 prev = eng.selfplay_rounds(20)
 eng.tower_debug(True)

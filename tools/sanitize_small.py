@@ -4,12 +4,12 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _cabi
-from oracle import pvnet_ref  # weight generator only
+from alpha_omok_b200.model import seeded_state_dict
 
 modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 1, 2, 3]
 for B in (9, 15):
     A = B * B
-    sd = pvnet_ref.make_state_dict(0, 2, 5, 128, B)
+    sd = seeded_state_dict(0, 2, 5, 128, B)
     rs = np.random.RandomState(1)
     x = np.zeros((7, 5, B, B), np.float32)
     x[:, 2:4] = (rs.rand(7, 2, B, B) < 0.2)
