@@ -461,3 +461,51 @@ def test_tower_split_precision_15x15(cabi):
         eng.close()
     assert max(err[cabi.AO_NN_FP16X3]) < TOL, err
     assert max(err[cabi.AO_NN_FP16]) > max(err[cabi.AO_NN_FP16X3]), err
+
+
+def test_config1_end_to_end_without_replay_vs_reference_game(cabi):
+    """BASELINE config 1 (one 9x9 game, 40 sims/move, random-init PVNet) end to end WITHOUT NN replay (third
+    bullet): the device plays with its own tcgen05 floats, the golden game was played by the unmodified reference with
+    torch fp32 floats, both consume the same decision stream.  Floats within 1e-4 can still flip an arg-max, so the
+    contract is: every NN evaluation of the device has its counterpart within 1e-4 in the reference's log, and for this
+    game (asserted) every ply's visit-count vector, every move and the winner coincide."""
+    fx = load("mcts_9_pvnet_s40")
+    B, game, sims = int(fx["B"]), int(fx["game"]), int(fx["sims"])
+    sd = pvnet_ref.make_state_dict(0, 10, 5, 128, B)
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=game + 1, noise=bool(fx["noise"]),
+                      tau_thres=int(fx["tau_thres"]), seed=int(fx["seed"]), noise_mode=cabi.AO_NOISE_TAPE,
+                      nn_log_cap=(sims + 1) * 82)
+    eng.load_state_dict(sd)
+    eng.set_gamma_tape(game, fx["gamma_tape"])
+    eng.selfplay_begin(game + 1, first_key=0)
+    st = eng.selfplay_rounds(64)
+    while st["running"]:
+        st = eng.selfplay_rounds(64)
+    assert st["errors"] == 0
+    moves, n_moves, winners, visits = eng.selfplay_fetch(game + 1)
+    gm, gv = fx["moves"], fx["visits"].astype(np.uint32)
+    k = min(len(gm), int(n_moves[game]))
+    same = [bool(moves[game, t] == gm[t] and np.array_equal(visits[game, t], gv[t])) for t in range(k)]
+    prefix = same.index(False) if False in same else k
+    pol, val = eng.nn_log(game, (sims + 1) * 82)
+    print("identical plies: %d of %d (reference game %d plies, device %d); winner ref %d dev %d"
+          % (prefix, k, len(gm), int(n_moves[game]), int(fx["winner"]), int(winners[game])))
+    # the reference's own NN outputs of this game (torch fp32, non-terminal expansions in call order, logged while the
+    # fixture was generated).  The device must produce the same evaluations within 1e-4; two nearly tied PUCT scores
+    # may be ordered differently by the device's floats (observed: simulations 789/790 of this game run in the other
+    # order and converge again), so the match is searched within +-2 positions.
+    rp, rv = fx["nn_policy"], fx["nn_value"]
+    assert len(val) == len(rv) == st["nn_evals"]
+    used, reordered = set(), 0
+    for i in range(len(val)):
+        for j in sorted(range(max(0, i - 2), min(len(rv), i + 3)), key=lambda j: abs(j - i)):
+            if j not in used and np.abs(pol[i] - rp[j]).max() < TOL and abs(val[i] - rv[j]) < TOL:
+                used.add(j)
+                reordered += j != i
+                break
+        else:
+            raise AssertionError("device evaluation %d has no counterpart within 1e-4 in the reference's log" % i)
+    print("NN evaluations matched within 1e-4: %d, of which out of order: %d" % (len(used), reordered))
+    assert reordered <= 8
+    assert prefix == len(gm) == int(n_moves[game]) and int(winners[game]) == int(fx["winner"])
+    eng.close()
