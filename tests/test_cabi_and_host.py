@@ -147,3 +147,23 @@ def test_allgather_records_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "rank0ok" in res.stdout and "rank1ok" in res.stdout, res.stdout
+
+
+def test_replay_entry_points_reject_bad_arguments_without_touching_the_gpu():
+    """argument validation of the replay-ring C ABI happens before any CUDA call (null / out-of-range -> -1)"""
+    import ctypes as C
+    from alpha_omok_b200 import _cabi
+    L = _cabi.lib()
+    n = C.c_longlong(0)
+    assert L.ao_augment_records_dev(None, 1, 9, 6, None, None, None, 0, C.byref(n), None) == -1
+    assert L.ao_augment_records_dev(1, 0, 9, 6, None, None, None, 0, C.byref(n), None) == -1
+    assert L.ao_augment_records_dev(1, 1, 16, 6, None, None, None, 0, C.byref(n), None) == -1
+    head, ln = C.c_longlong(0), C.c_longlong(0)
+    assert L.ao_replay_extend_dev(None, 1, 9, 6, 1, 1, 1, 10, C.byref(head), C.byref(ln), C.byref(n), None) == -1
+    head.value = 10                                   # head must be < cap
+    assert L.ao_replay_extend_dev(1, 1, 9, 6, 1, 1, 1, 10, C.byref(head), C.byref(ln), C.byref(n), None) == -1
+    head.value, ln.value = 0, 11                      # len must be <= cap
+    assert L.ao_replay_extend_dev(1, 1, 9, 6, 1, 1, 1, 10, C.byref(head), C.byref(ln), C.byref(n), None) == -1
+    assert L.ao_replay_gather_dev(None, 1, 1, 10, 0, 1, 1, 9, 1, 1, 1, None) == -1
+    assert L.ao_replay_gather_dev(1, 1, 1, 10, 10, 1, 1, 9, 1, 1, 1, None) == -1
+    assert L.ao_replay_gather_dev(1, 1, 1, 10, 0, 1, 0, 9, 1, 1, 1, None) == 0    # k = 0: nothing to do
