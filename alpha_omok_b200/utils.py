@@ -74,3 +74,65 @@ def augment_dataset(memory, board_size):
             out.append((s_k.copy(), p_k.flatten().copy(), z))
             out.append((s_k[:, :, ::-1].copy(), p_k[:, ::-1].flatten().copy(), z))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Host-side helpers of the reference's utils module that are NOT on the hot path (printing, the rollout agents' helpers,
+# a TensorFlow-era encoder) - provided so that `import utils` keeps working for main.py / eval_main.py unchanged.
+ALPHABET = ' A B C D E F G H I J K L M N O P Q R S'
+
+
+def valid_actions(board):
+    """utils.py:8-19 - [[(row, col), flat index], ...] of the empty cells, row-major"""
+    b = np.asarray(board)
+    n = len(b)
+    return [[(int(i), int(j)), int(i * n + j)] for i, j in zip(*np.nonzero(b == 0))]
+
+
+def get_reward(win_index, leaf_id):
+    """utils.py:208-223 - +1 / -1 from the point of view of the side to move at the leaf, 0 for draw / running"""
+    if win_index not in (1, 2):
+        return 0.
+    mover_lost = (win_index == 1) == (get_turn(leaf_id) == 1)
+    return 1. if mover_lost else -1.
+
+
+def render_str(board, board_size, action_index):
+    """utils.py:62-102 - text board: ' .', ' O' (black), ' X' (white); the last move is bracketed '(O)' and the cell to
+    its right drops its leading blank so that the columns stay aligned; footer with the move count."""
+    b = np.asarray(board)
+    count = int(np.count_nonzero(b))
+    last = None if action_index is None else (int(action_index) // board_size, int(action_index) % board_size)
+    if count > 0 and last is None:
+        raise NameError("render_str needs the last action once stones are on the board")  # as the reference does
+    lines = ['', '  ' + ALPHABET[:board_size * 2]]
+    glyph = {0: '.', 1: 'O', -1: 'X'}
+    for i in range(board_size):
+        row = '{:2}'.format(i + 1)
+        for j in range(board_size):
+            g = glyph[int(b[i][j])]
+            if last is not None and (i, j) == last and g != '.':
+                row += '(' + g + ')'
+            elif last is not None and (i, j) == (last[0], last[1] + 1) and (g != '.' or count > 0):
+                row += g
+            else:
+                row += ' ' + g
+        lines.append(row + ' ')
+    footer = '  ' + '-' * (board_size - 6) + '  MOVE: {:2}  '.format(count) + '-' * (board_size - 6)
+    print('\n'.join(lines) + '\n' + footer)
+
+
+def get_state_tf(id, turn, board_size, channel_size):
+    """utils.py:105-136 - channels-last encoder kept from the reference's TensorFlow days (unused by the PyTorch path):
+    channel c < channel_size-1 holds the cumulative stones of the colour that moved c plies before the end of `id`,
+    the last channel is the colour-to-move flag."""
+    state = np.zeros([board_size, board_size, channel_size])
+    planes = [np.zeros([board_size, board_size]), np.zeros([board_size, board_size])]  # even / odd positions of id
+    n = len(id)
+    for i in range(n):
+        if i != 0:
+            planes[i % 2][int(id[i] / board_size), int(id[i] % board_size)] = 1
+        if n - i < channel_size:
+            state[:, :, n - i - 1] = planes[i % 2]
+    state[:, :, channel_size - 1] = 1 if turn == 0 else 0
+    return state

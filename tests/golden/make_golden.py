@@ -284,6 +284,35 @@ def gen_train(R):
     print("train_9_small OK  losses", losses[0], "->", losses[-1])
 
 
+def gen_utils_aux(R):
+    """the reference's non-hot-path utils (render_str, valid_actions, get_reward, get_state_tf) on random boards"""
+    import contextlib, io, json
+    rs = np.random.RandomState(5)
+    cases = []
+    for B in (9, 15):
+        for trial in range(12):
+            k = int(rs.randint(0, B * B)) if trial else 0
+            cells = [int(c) for c in rs.permutation(B * B)[:k]]
+            board = np.zeros((B, B))
+            for t, c in enumerate(cells):
+                board[c // B, c % B] = 1 if t % 2 == 0 else -1
+            last = cells[-1] if k else None
+            if trial % 5 == 4:
+                last = int(rs.randint(0, B * B))
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                R.utils.render_str(board, B, last)
+            rid = (0,) + tuple(cells)
+            cases.append(dict(B=B, cells=cells, last=last, render=buf.getvalue(),
+                              valid=[[list(a[0]), a[1]] for a in R.utils.valid_actions(board)],
+                              reward=[R.utils.get_reward(w, rid) for w in (0, 1, 2, 3)],
+                              state_tf_sum=[float((R.utils.get_state_tf(rid, t, B, 5) * np.arange(1, 6)).sum()) for t in (0, 1)],
+                              state_tf=R.utils.get_state_tf(rid, 0, B, 5).astype(int).tolist() if trial < 3 else None))
+    with open(os.path.join(HERE, "utils_aux.json"), "w") as f:
+        json.dump(cases, f)
+    print("utils_aux.json OK", len(cases))
+
+
 def main():
     R = import_reference()
     np.random.choice = PATCH.choice
@@ -291,9 +320,13 @@ def main():
     if "--only-train" in sys.argv:
         gen_train(R)
         return
+    if "--only-utils-aux" in sys.argv:
+        gen_utils_aux(R)
+        return
     gen_rules(R)
     gen_nn(R)
     gen_train(R)
+    gen_utils_aux(R)
     gen_mcts_game(R, "mcts_9_synth_s40", 9, 40, seed=11, game=0, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
     gen_mcts_game(R, "mcts_9_synth_s400", 9, 400, seed=12, game=3, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
     gen_mcts_game(R, "mcts_9_synth_nonoise", 9, 60, seed=13, game=1, noise=False, tau_thres=0, max_moves=None, nn_kind="synth")

@@ -167,3 +167,29 @@ def test_replay_entry_points_reject_bad_arguments_without_touching_the_gpu():
     assert L.ao_replay_gather_dev(None, 1, 1, 10, 0, 1, 1, 9, 1, 1, 1, None) == -1
     assert L.ao_replay_gather_dev(1, 1, 1, 10, 10, 1, 1, 9, 1, 1, 1, None) == -1
     assert L.ao_replay_gather_dev(1, 1, 1, 10, 0, 1, 0, 9, 1, 1, 1, None) == 0    # k = 0: nothing to do
+
+
+def test_aux_utils_match_reference_golden(capsys):
+    """render_str / valid_actions / get_reward / get_state_tf (host helpers off the hot path) vs outputs of the
+    unmodified reference (tests/golden/utils_aux.json)"""
+    import json
+    from alpha_omok_b200 import utils
+    with open(os.path.join(ROOT, "tests", "golden", "utils_aux.json")) as f:
+        cases = json.load(f)
+    assert len(cases) == 24
+    for c in cases:
+        B = c["B"]
+        board = np.zeros((B, B))
+        for t, cell in enumerate(c["cells"]):
+            board[cell // B, cell % B] = 1 if t % 2 == 0 else -1
+        capsys.readouterr()
+        utils.render_str(board, B, c["last"])
+        assert capsys.readouterr().out == c["render"]
+        assert [[list(a[0]), a[1]] for a in utils.valid_actions(board)] == c["valid"]
+        rid = (0,) + tuple(c["cells"])
+        assert [utils.get_reward(w, rid) for w in (0, 1, 2, 3)] == c["reward"]
+        for t in (0, 1):
+            st = utils.get_state_tf(rid, t, B, 5)
+            assert float((st * np.arange(1, 6)).sum()) == c["state_tf_sum"][t]
+        if c["state_tf"] is not None:
+            assert np.array_equal(utils.get_state_tf(rid, 0, B, 5), np.asarray(c["state_tf"]))
