@@ -91,3 +91,99 @@ def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, n
     # the reference plays the matches one after the other and updates the ratings after each (eval_main.py:285-312)
     res["player_elo"], res["enemy_elo"], _, res["winrate"] = elo_sequence(outcomes)
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Drop-in for eval_main.Evaluator / eval_main.main (eval_main.py:54-188, 204-333) without the Flask / pygame wiring:
+# one match at a time through the reference-shaped single-game agents (each ZeroAgent = a batch of 1 on the device).
+class Evaluator(object):
+    """eval_main.py:54-188.  `set_agents(player, enemy, monitor)`: each argument is 'random' or a checkpoint path
+    (-> ZeroAgent(noise=False) + PVNet with the reference's tolerant key-by-key load); 'puct' / 'uct' / 'human' / 'web'
+    name agents that are out of this repository's scope and raise NotImplementedError."""
+
+    def __init__(self, board_size=9, n_mcts_player=800, n_mcts_enemy=800, n_mcts_monitor=800, n_blocks=10,
+                 in_planes=5, out_planes=128):
+        self.board_size = board_size
+        self.n_mcts = {"player": n_mcts_player, "enemy": n_mcts_enemy, "monitor": n_mcts_monitor}
+        self.n_blocks, self.in_planes, self.out_planes = n_blocks, in_planes, out_planes
+        self.player = self.enemy = self.monitor = None
+        self.env = None
+
+    def _make(self, role, path):
+        import torch
+        from . import model
+        if path == "random":
+            return agents.RandomAgent(self.board_size)
+        if path in ("puct", "uct", "human", "web"):
+            raise NotImplementedError("agent '%s' (rollout / interactive) is outside the accelerated path" % path)
+        agent = agents.ZeroAgent(self.board_size, self.n_mcts[role], self.in_planes, noise=False)
+        agent.model = model.PVNet(self.n_blocks, self.in_planes, self.out_planes, self.board_size)
+        state = agent.model.state_dict()
+        loaded = path if isinstance(path, dict) else torch.load(path, map_location="cpu")
+        for k, v in loaded.items():          # eval_main.py:95-101: keys the module does not know are ignored,
+            if k in state:                   # keys the file lacks (num_batches_tracked) keep their defaults
+                state[k] = v
+        agent.model.load_state_dict(state)
+        return agent
+
+    def set_agents(self, model_path_a, model_path_b, model_path_m):
+        from .env import env_regular, env_small
+        game = env_small if self.board_size == 9 else env_regular
+        self.env = game.GameState("text")
+        self.player = self._make("player", model_path_a)
+        self.enemy = self._make("enemy", model_path_b)
+        self.monitor = self._make("monitor", model_path_m)
+
+    def get_action(self, root_id, board, turn, enemy_turn):
+        """eval_main.py:153-170"""
+        mover = self.player if turn != enemy_turn else self.enemy
+        if isinstance(mover, agents.ZeroAgent):
+            pi = mover.get_pi(root_id, tau=0)
+        else:
+            pi = mover.get_pi(root_id, board, turn, tau=0)
+            if mover is self.player:
+                self.monitor.get_pi(root_id, tau=0)      # "for monitor" (eval_main.py:160-161)
+        return utils.argmax_onehot(pi)
+
+    def return_env(self):
+        return self.env
+
+    def reset(self):
+        self.player.reset()
+        self.enemy.reset()
+
+
+def run_matches(evaluator, n_match=12, verbose=False):
+    """eval_main.main (eval_main.py:204-333) minus the dashboard objects: alternating colours, the opponent's tree
+    pruned after every move (`del_parents`), ELO and win-rate bookkeeping.  Returns (result, player_elo, enemy_elo)."""
+    B = evaluator.board_size
+    env = evaluator.return_env()
+    result = {"Player": 0, "Enemy": 0, "Draw": 0}
+    turn, enemy_turn = 0, 1
+    player_elo, enemy_elo = 1500, 1500
+    for i in range(n_match):
+        board = np.zeros([B, B])
+        root_id, win_index, action_index = (0,), 0, None
+        while win_index == 0:
+            if verbose:
+                utils.render_str(board, B, action_index)
+            evaluator.monitor.get_pv(root_id)
+            action, action_index = evaluator.get_action(root_id, board, turn, enemy_turn)
+            mover = evaluator.player if turn != enemy_turn else evaluator.enemy
+            root_id = (mover.root_id if mover.root_id is not None else root_id) + (int(action_index),)
+            board, _, win_index, turn, _ = env.step(action)
+            (evaluator.enemy if turn == enemy_turn else evaluator.player).del_parents(root_id)
+            if win_index != 0:
+                if win_index == 3:
+                    result["Draw"] += 1
+                    player_elo, enemy_elo = elo(player_elo, enemy_elo, 0.5, 0.5)
+                elif turn == enemy_turn:      # the side that just moved (and won) was the player
+                    result["Player"] += 1
+                    player_elo, enemy_elo = elo(player_elo, enemy_elo, 1, 0)
+                else:
+                    result["Enemy"] += 1
+                    player_elo, enemy_elo = elo(player_elo, enemy_elo, 0, 1)
+                enemy_turn = abs(enemy_turn - 1)      # swap colours (eval_main.py:316)
+                turn = 0
+                evaluator.reset()
+    return result, player_elo, enemy_elo

@@ -220,3 +220,23 @@ def test_trainer_iteration_loop_on_device(tmp_path):
         assert torch.equal(v, tr2.model.state_dict()[k])
     a, b = tr.rep_memory.gather(list(range(len(tr.rep_memory)))), tr2.rep_memory.gather(list(range(len(tr2.rep_memory))))
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_evaluator_dropin_trained_vs_random(golden_dir):
+    """eval_main.Evaluator / main (eval_main.py:54-188, 204-333) through the single-game facades: the reference's shipped
+    checkpoint (50 sims, noise off, tau 0) against RandomAgent, colours alternating, ELO bookkeeping; the survey's probe
+    of the reference itself gave 2-0 for the same setting"""
+    import os
+    from alpha_omok_b200 import agents, arena
+    z = np.load(os.path.join(golden_dir, "trained_9x9_180927.npz"))
+    ckpt = {k: torch.from_numpy(z[k]) for k in z.files}
+    np.random.seed(0)
+    ev = arena.Evaluator(board_size=9, n_mcts_player=50, n_mcts_enemy=50, n_mcts_monitor=50)
+    ev.set_agents(ckpt, "random", ckpt)
+    assert isinstance(ev.player, agents.ZeroAgent) and isinstance(ev.enemy, agents.RandomAgent) and not ev.player.noise
+    result, p_elo, e_elo = arena.run_matches(ev, n_match=2)
+    assert result == {"Player": 2, "Enemy": 0, "Draw": 0}
+    exp_p, exp_e = arena.elo(*arena.elo(1500, 1500, 1, 0), 1, 0)
+    assert (p_elo, e_elo) == (exp_p, exp_e)
+    with pytest.raises(NotImplementedError):
+        ev.set_agents(ckpt, "puct", ckpt)
