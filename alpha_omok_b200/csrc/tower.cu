@@ -117,10 +117,10 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_empty[s], PAIR ? 2 : 1);  // PAIR: one commit per MMA stream (tile)
     }
     mbar_init(bar_act, (PAIR && leader) ? kEpiThreads + 1 : kEpiThreads);  // + the peer's forwarded arrival
-    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc, PAIR ? 2 : 1);
     for (int s = 0; s < NSLOT; ++s) mbar_init(&bar_peer_full[s], 1);
     fence_mbar_init();
   }
@@ -197,15 +197,18 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         }
       }
     }
-  } else if (warp == 9) {
-    // =========================================================== MMA issuer
+  } else if (warp == 9 || (PAIR && warp == 10)) {
+    // =========================================================== MMA issuer(s)
     // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; one elected
-    // lane issues tcgen05.mma / commit.
+    // lane issues tcgen05.mma / commit.  CTA pairs use two issuing warps on two scheduler ports, one per tile (a
+    // single thread gets one M256 N128 K16 MMA per ~109 cycles out of the tensor pipe, two threads one per ~87:
+    // tools/probe_mma_rate.py); both run the same control flow and commit to the same barriers (count 2).
+    const int stream = warp == 9 ? 0 : 1;
     if (PAIR && !leader) {
       // ---- peer CTA of a pair: no MMA issue; one lane forwards this CTA's readiness to the leader's barriers.
       // Two independent event streams (operand-ready per layer, weights-landed per stage) are polled without
       // blocking so that neither delays the other.
-      if (lane == 0) {
+      if (stream == 0 && lane == 0) {
         int g0, ng, ntiles, n_k = 0;
         while (get_pass<G::GPC, G::A, PAIR>(n_k, n, g0, ng, ntiles)) ++n_k;
         const uint32_t n_act = (uint32_t)(n_k * n_layers);
@@ -275,6 +278,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
 #pragma unroll
               for (int tile = 0; tile < kTiles; ++tile) {
                 if (tile >= ntiles) break;  // one-game tail pass: tile 1 holds no board
+                if (PAIR && tile != stream) continue;
                 const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
                 const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
                 const uint32_t d_tmem = tmem + (uint32_t)(tile * 256 + (to_b ? 128 : 0));
@@ -326,14 +330,14 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
           }
         }
       }
-      if (W.dbg && blockIdx.x == 0 && lane == 0) {  // profiling counters (ao_tower_debug): MMA-issuer view of CTA 0
+      if (W.dbg && blockIdx.x == 0 && lane == 0 && stream == 0) {  // profiling counters (ao_tower_debug): MMA-issuer view of CTA 0
         atomicAdd(&W.dbg[0], (unsigned long long)(clock64() - dbg_t0));
         atomicAdd(&W.dbg[1], (unsigned long long)dbg_act_wait);
         atomicAdd(&W.dbg[2], (unsigned long long)dbg_full_wait);
         atomicAdd(&W.dbg[3], 1ull);
       }
     }
-  } else {
+  } else if (warp < 8) {
     // =========================================================== epilogue warps (256 threads)
     const int tile = tid >> 7, r = tid & 127;
     const int R = tile * kTileRows + r;          // logical row in the CTA's padded position stream

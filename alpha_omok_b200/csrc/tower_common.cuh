@@ -13,7 +13,7 @@ constexpr int kC = 128;
 constexpr int kTileRows = 128;
 constexpr int kTiles = 2;
 constexpr int kEpiThreads = 256;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;  // 8 epilogue warps, producer, MMA issuer(s): warp 9 and, for CTA pairs, warp 10
 constexpr int kStageBytes = kC * kC * 2;  // one tap, 128 in-channels: 32 KB
 constexpr int kStemStageBytes = 16 * kC * 2;
 constexpr int kMaxLayers = 21;            // 1 + 2*10 blocks (bias table lives in shared memory)
