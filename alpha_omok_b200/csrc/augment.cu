@@ -67,10 +67,14 @@ augment_kernel(const uint8_t* __restrict__ slab, size_t rec_bytes, int n, int B,
                long long ring_skip) {
   __shared__ float s_pi[kWarps][kMaxA + 3];
   __shared__ uint16_t s_rows[kWarps][4][32];
+  __shared__ uint8_t s_cell[kWarps][kMaxA + 3];   // per ply: bit k = plane k of the cell
+  __shared__ uint8_t s_src[8][kMaxA + 3];          // per block: source cell of output cell c under augmentation a
   const int g = blockIdx.x;
   if (g >= n) return;
   const int A = B * B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * A; i += kWarps * 32) s_src[i / A][i % A] = (uint8_t)aug_source(i / A, (i % A) / B, (i % A) % B, B);
+  __syncthreads();
   const uint8_t* rec = slab + (size_t)g * rec_bytes;
   const int n_moves = *reinterpret_cast<const int16_t*>(rec);
   const int winner = rec[2];
@@ -116,6 +120,12 @@ augment_kernel(const uint8_t* __restrict__ slab, size_t rec_bytes, int n, int B,
       for (int a = lane; a < A; a += 32) s_pi[warp][a] = a == played ? 1.f : 0.f;
     }
     __syncwarp();
+    for (int c = lane; c < A; c += 32) {
+      const int y = c / B, x = c % B;
+      s_cell[warp][c] = (uint8_t)(((s_rows[warp][0][y] >> x) & 1u) | (((s_rows[warp][1][y] >> x) & 1u) << 1) |
+                                  (((s_rows[warp][2][y] >> x) & 1u) << 2) | (((s_rows[warp][3][y] >> x) & 1u) << 3));
+    }
+    __syncwarp();
     const float colour = black_to_move ? 1.f : 0.f;
     const float z = black_to_move ? z_black : -z_black;
     // ---- the 8 dihedral copies
@@ -128,12 +138,12 @@ augment_kernel(const uint8_t* __restrict__ slab, size_t rec_bytes, int n, int B,
       float* so = states + (size_t)s_idx * 5 * A;
       float* po = pis + (size_t)s_idx * A;
       for (int c = lane; c < A; c += 32) {
-        const int src = aug_source(a8, c / B, c % B, B);
-        const int sy = src / B, sx = src % B;
-        so[0 * A + c] = (float)((s_rows[warp][0][sy] >> sx) & 1u);
-        so[1 * A + c] = (float)((s_rows[warp][1][sy] >> sx) & 1u);
-        so[2 * A + c] = (float)((s_rows[warp][2][sy] >> sx) & 1u);
-        so[3 * A + c] = (float)((s_rows[warp][3][sy] >> sx) & 1u);
+        const int src = s_src[a8][c];
+        const uint32_t bits = s_cell[warp][src];
+        so[0 * A + c] = (float)(bits & 1u);
+        so[1 * A + c] = (float)((bits >> 1) & 1u);
+        so[2 * A + c] = (float)((bits >> 2) & 1u);
+        so[3 * A + c] = (float)((bits >> 3) & 1u);
         so[4 * A + c] = colour;
         po[c] = s_pi[warp][src];
       }
