@@ -174,8 +174,14 @@ class Trainer:
         return self.rep_memory.cur_len
 
     # ---------------------------------------------------------------- training (main.py:253-336)
-    def train(self, n_epochs=None):
+    def train(self, n_epochs=None, max_samples=None, strict_reference=False):
+        """main.py:253-336.  The reference trains on BATCH_SIZE * len(cur_memory) samples (main.py:263-264) and
+        `random.sample` raises when that exceeds the replay memory - which it does as soon as an iteration plays
+        thousands of concurrent episodes instead of one.  `strict_reference=True` keeps that behaviour; by default the
+        count is clamped to the memory size (and to `max_samples` if given)."""
         k = self.BATCH_SIZE * self.rep_memory.cur_len          # BATCH_SIZE * len(cur_memory), main.py:263-264
+        if not strict_reference:
+            k = min(k, len(self.rep_memory), max_samples if max_samples is not None else k)
         idx = self.rep_memory.sample_indices(k)                # every rank draws the same indices (same seed) ...
         idx = idx[self.rank::self.world]                       # ... and trains on its slice of the batches' rows
         s, pi, z = self.rep_memory.gather(idx)
@@ -212,14 +218,14 @@ class Trainer:
         self.rep_memory.cur_len = 0
 
     # ---------------------------------------------------------------- iteration loop (main.py:377-407)
-    def run(self, total_iter, save_every=100, n_selfplay_later=1):
+    def run(self, total_iter, save_every=100, n_selfplay_later=1, max_samples=None):
         """main.py:386-407. The reference fills the buffer with N_SELFPLAY episodes in iteration 0 and plays
         N_SELFPLAY = 1 episode per iteration afterwards (main.py:397-400); `n_selfplay_later` is that second number -
         on a B200 thousands of concurrent episodes per iteration cost about the same wall time as one."""
         for n_iter in range(self.start_iter, total_iter):
             if n_iter > 0:
                 self.self_play(n_selfplay_later)
-                self.train()
+                self.train(max_samples=max_samples)
             else:
                 self.self_play(self.N_SELFPLAY)
             if n_iter % save_every == 0:
