@@ -27,7 +27,7 @@ class AoConfig(C.Structure):
 
 EXPORTS = [
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
-    "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_rounds",
+    "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_stream_begin", "ao_selfplay_stream_records_dev", "ao_selfplay_rounds",
     "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_augment_records_dev", "ao_replay_extend_dev", "ao_replay_gather_dev", "ao_synchronize", "ao_check_win",
     "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked", "ao_umma_rate",
 ]
@@ -60,6 +60,8 @@ def lib():
     L.ao_selfplay_begin.argtypes = [vp, i32, u32]
     L.ao_selfplay_begin_mode.argtypes = [vp, i32, u32, i32]
     L.ao_selfplay_rounds.argtypes = [vp, i32, vp]
+    L.ao_selfplay_stream_begin.argtypes = [vp, i32, u32, i32]
+    L.ao_selfplay_stream_records_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(i32)]
     L.ao_selfplay_rounds_timed.argtypes = [vp, i32, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.ao_tower_debug.argtypes = [vp, i32, vp]
     L.ao_set_nn_precision.argtypes = [vp, i32]
@@ -209,6 +211,15 @@ class Engine:
 
     def selfplay_begin(self, n_games, first_key=0, recycle=False):
         check(lib().ao_selfplay_begin_mode(self._h, n_games, first_key, int(recycle)))
+
+    def selfplay_stream_begin(self, n_episodes, n_slots=None, first_key=0):
+        """continuous self-play: `n_slots` (default: all) concurrent games work through `n_episodes` episodes"""
+        check(lib().ao_selfplay_stream_begin(self._h, self.G if n_slots is None else n_slots, first_key, n_episodes))
+
+    def stream_records_dev(self):
+        p, b, n = C.c_void_p(), C.c_size_t(), C.c_int32()
+        check(lib().ao_selfplay_stream_records_dev(self._h, C.byref(p), C.byref(b), C.byref(n)))
+        return p.value, b.value, n.value
 
     @staticmethod
     def _counters(out, **extra):

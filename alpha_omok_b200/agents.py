@@ -202,7 +202,7 @@ class BatchedZeroAgent(_EngineOwner):
 
 
 def self_play(model, n_selfplay, board_size=9, num_mcts=400, inplanes=5, tau_thres=6, noise=True, seed=0,
-              first_key=0, rounds_per_call=256, engine=None, augment=False):
+              first_key=0, rounds_per_call=256, engine=None, augment=False, max_slots=None):
     """Batched twin of main.self_play (main.py:122-250): `n_selfplay` episodes played concurrently on the device.
 
     Returns (cur_memory, result): cur_memory is the reference's list of (state [5,B,B] float64, pi [A] float64, z)
@@ -210,18 +210,31 @@ def self_play(model, n_selfplay, board_size=9, num_mcts=400, inplanes=5, tau_thr
     """
     A = board_size * board_size
     own = engine is None
+    slots = n_selfplay if max_slots is None else min(n_selfplay, max_slots)
     if own:
         n_blocks = getattr(model, "n_block", None) or len(
             {k.split(".")[1] for k in model.state_dict() if k.startswith("layers.")})
-        engine = _cabi.Engine(board_size=board_size, num_mcts=num_mcts, max_games=n_selfplay, noise=noise,
+        engine = _cabi.Engine(board_size=board_size, num_mcts=num_mcts, max_games=slots, noise=noise,
                               tau_thres=tau_thres, n_blocks=n_blocks, inplanes=inplanes, seed=seed)
         engine.load_state_dict(model.state_dict())
-    engine.selfplay_begin(n_selfplay, first_key=first_key)
+    else:
+        slots = min(slots, engine.G)
+    stream = n_selfplay > slots   # more episodes than resident games: continuous mode (ao_selfplay_stream_begin)
+    if stream:
+        engine.selfplay_stream_begin(n_selfplay, n_slots=slots, first_key=first_key)
+    else:
+        engine.selfplay_begin(n_selfplay, first_key=first_key)
     st = engine.selfplay_rounds(rounds_per_call)
     while st["running"]:
         st = engine.selfplay_rounds(rounds_per_call)
     if st["errors"]:
         raise _cabi.AoError("%d game tree(s) overflowed their arena; raise node_cap" % st["errors"])
+    if stream:
+        from . import replay
+        cur_memory, result = replay.decode_records(replay.device_stream_records(engine), board_size, tau_thres)
+        if own:
+            engine.close()
+        return (utils.augment_dataset(cur_memory, board_size) if augment else cur_memory), result
     moves, n_moves, winners, visits = engine.selfplay_fetch(n_selfplay)
     cur_memory, result = [], {"Black": 0, "White": 0, "Draw": 0}
     for g in range(n_selfplay):

@@ -63,6 +63,11 @@ struct ao_engine {
   size_t rec_bytes;
   int32_t* h_pinned;  // [0] n_active
   int selfplay_games;
+  // continuous self-play: record slab of the episodes of one stream run (resized on demand), next-key counter
+  uint8_t* d_stream;
+  size_t stream_capacity;      // episodes the slab can hold
+  uint32_t* d_stream_next;
+  int stream_episodes;         // episodes of the current stream run (0 = none)
   // optional per-kernel timing (bench roofline): event pairs recorded around every launch of a timed call
   bool timing;
   std::vector<cudaEvent_t> ev;  // [tree_begin, tree_end(=tower_begin), tower_end] per round
@@ -145,6 +150,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->num_sms = prop.multiProcessorCount;
   h->weights_loaded = false;
   h->selfplay_games = 0;
+  h->d_stream = nullptr; h->stream_capacity = 0; h->d_stream_next = nullptr; h->stream_episodes = 0;
   h->timing = false;
   h->launches = 0;
   h->h_pinned = nullptr;
@@ -217,6 +223,7 @@ extern "C" int ao_engine_destroy(ao_engine* h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->d_stream) cudaFree(h->d_stream);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -462,6 +469,59 @@ extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_
   AO_CUDA(ao::launch_reset_games(h->tp, nullptr, n_games, h->d_keys, recycle ? 2 : 1, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->selfplay_games = n_games;
+  return 0;
+}
+
+// Continuous self-play (the caller side of main.self_play for more episodes than game slots): `n_slots`
+// games run concurrently; a slot whose episode ends packs its record on the device and starts the episode with the
+// next unplayed decision-stream key until `n_episodes` keys [first_key, first_key + n_episodes) are handed out.  Every
+// episode is a function of its key alone, so the records equal those of ao_selfplay_begin runs with the same keys, and
+// short games no longer leave their slot idle while the longest game of the batch finishes.
+extern "C" int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t first_key, int n_episodes) {
+  if (!h) return fail(-1, "null engine");
+  if (n_episodes < 1) return fail(-1, "n_episodes = %d must be positive", n_episodes);
+  if (n_slots > n_episodes) n_slots = n_episodes;
+  if (n_slots < 1 || n_slots > h->G) return fail(-1, "n_slots = %d out of range 1..%d", n_slots, h->G);
+  if (h->cfg.noise && h->cfg.noise_mode == AO_NOISE_TAPE)
+    return fail(-1, "continuous self-play needs the device noise generator (gamma tapes are per slot, not per key)");
+  int rc = require_weights(h);
+  if (rc) return rc;
+  if ((size_t)n_episodes > h->stream_capacity) {
+    if (h->d_stream) cudaFree(h->d_stream);
+    h->d_stream = nullptr;
+    h->stream_capacity = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_stream), (size_t)n_episodes * h->rec_bytes);
+    if (e != cudaSuccess) return fail(-2, "cudaMalloc of the stream record slab (%zu bytes) failed: %s", (size_t)n_episodes * h->rec_bytes, cudaGetErrorString(e));
+    h->stream_capacity = (size_t)n_episodes;
+  }
+  if (!h->d_stream_next && (rc = ealloc(h, &h->d_stream_next, 1)) != 0) return rc;
+  AO_CUDA(cudaMemsetAsync(h->d_stream, 0, (size_t)n_episodes * h->rec_bytes, h->stream));
+  const uint32_t next = first_key + (uint32_t)n_slots;
+  AO_CUDA(cudaMemcpyAsync(h->d_stream_next, &next, 4, cudaMemcpyHostToDevice, h->stream));
+  h->tp.stream_out = h->d_stream;
+  h->tp.stream_rec_bytes = h->rec_bytes;
+  h->tp.stream_next_key = h->d_stream_next;
+  h->tp.stream_first_key = first_key;
+  h->tp.stream_key_end = first_key + (uint32_t)n_episodes;
+  std::vector<uint32_t> keys(n_slots);
+  for (int i = 0; i < n_slots; ++i) keys[i] = first_key + (uint32_t)i;
+  AO_CUDA(cudaMemcpyAsync(h->d_keys, keys.data(), (size_t)n_slots * 4, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(ao::launch_reset_games(h->tp, nullptr, n_slots, h->d_keys, 3, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  h->selfplay_games = n_slots;
+  h->stream_episodes = n_episodes;
+  return 0;
+}
+
+// Record slab of the current / last stream run: n_episodes records of ao_records_dev's layout, index = key - first_key
+// (complete once ao_selfplay_rounds reports 0 running games).  The pointer stays valid until the next stream_begin.
+extern "C" int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_game, int* n_episodes) {
+  if (!h) return fail(-1, "null engine");
+  if (h->stream_episodes <= 0) return fail(-1, "call ao_selfplay_stream_begin first");
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  if (dev_ptr) *dev_ptr = h->d_stream;
+  if (bytes_per_game) *bytes_per_game = h->rec_bytes;
+  if (n_episodes) *n_episodes = h->stream_episodes;
   return 0;
 }
 

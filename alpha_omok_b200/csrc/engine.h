@@ -84,6 +84,12 @@ struct TreeParams {
   int32_t* n_active;     // device counter
   float* nnlog_policy;   // [G][cap][A]
   float* nnlog_value;    // [G][cap]
+  // continuous self-play (auto_play == 3): a slot whose episode ends packs its record at index (key - first_key) of
+  // stream_out and takes the next unplayed key from the device counter until key_end is reached
+  uint8_t* stream_out;         // [key_end - first_key][stream_rec_bytes]
+  size_t stream_rec_bytes;
+  uint32_t* stream_next_key;   // device counter
+  uint32_t stream_first_key, stream_key_end;
 };
 
 // folded network parameters on the device (one weight set)

@@ -449,19 +449,46 @@ __device__ void play_move(Ctx& c, Regs& g) {
       c.gm->winner = win;
       c.gm->games_finished += 1ull;
     }
-    if (c.gm->auto_play != 2) {
+    const int mode = c.gm->auto_play;
+    if (mode != 2 && mode != 3) {
       g.status = ST_FINISHED;
       return;
     }
-    // bench mode (auto_play == 2): recycle the slot - a fresh episode with the next decision-stream key
+    uint32_t next_key = c.gm->game_key + (uint32_t)P.G;  // bench mode (2): the slot's next decision-stream key
+    if (mode == 3) {
+      // continuous self-play: the finished episode's record goes to index (key - first_key) of the stream slab (same
+      // layout as pack_records_kernel), then the slot takes the next unplayed key - or retires when none is left
+      const uint32_t key = c.gm->game_key;
+      uint8_t* out = P.stream_out + (size_t)(key - P.stream_first_key) * P.stream_rec_bytes;
+      if (c.lane == 0) {
+        reinterpret_cast<int16_t*>(out)[0] = (int16_t)g.n_moves;
+        out[2] = (uint8_t)win;
+        out[3] = 0;
+      }
+      int16_t* mv = reinterpret_cast<int16_t*>(out) + 2;
+      for (int i = c.lane; i < A; i += 32) mv[i] = i < g.n_moves ? (int16_t)c.gm->moves[i] : (int16_t)-1;
+      uint32_t* vis = reinterpret_cast<uint32_t*>(out + ((4 + (size_t)A * 2 + 3) & ~(size_t)3));
+      const uint32_t* src = P.rec_visits + (size_t)c.game * A * A;
+      const int n_words = g.n_moves * A;
+      for (int i = c.lane; i < A * A; i += 32) vis[i] = i < n_words ? src[i] : 0u;
+      uint32_t nk = 0u;
+      if (c.lane == 0) nk = atomicAdd(P.stream_next_key, 1u);
+      next_key = __shfl_sync(kFull, nk, 0);
+      if (next_key >= P.stream_key_end) {
+        g.status = ST_FINISHED;
+        return;
+      }
+    }
+    // recycle the slot: a fresh episode
     g.rb = 0u; g.rw = 0u;
     g.n_moves = 0; g.last1 = -1; g.last2 = -1;
     g.root_node = CH_UNVISITED; g.root_n = 0u; g.root_w = 0.f; g.slot_count = 0u;
     g.sims_done = 0; g.sims_target = P.num_mcts + 1;
     g.rng_ctr = 0u; g.noise_draws = 0u;
     if (c.lane == 0) {
-      c.gm->game_key += (uint32_t)P.G;
+      c.gm->game_key = next_key;
       c.gm->is_real_root = 1;
+      c.gm->winner = 0;
     }
     __syncwarp();
     return;

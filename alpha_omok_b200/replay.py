@@ -36,6 +36,14 @@ def device_records(engine, n_games) -> torch.Tensor:
     return t.view(n_games, bpg)
 
 
+def device_stream_records(engine) -> torch.Tensor:
+    """uint8 CUDA tensor [n_episodes, record_bytes] aliasing the record slab of a finished continuous self-play run
+    (`Engine.selfplay_stream_begin`), episode i = decision-stream key first_key + i."""
+    ptr, bpg, n = engine.stream_records_dev()
+    t = torch.as_tensor(_DevSlab(ptr, n * bpg), device=torch.device("cuda", torch.cuda.current_device()))
+    return t.view(n, bpg)
+
+
 def allgather_records(local: torch.Tensor, group=None) -> torch.Tensor:
     """[n_local, bytes] uint8 on every rank -> [world * n_local, bytes], rank-major (rank r's games at r*n_local...)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

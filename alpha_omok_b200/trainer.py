@@ -123,11 +123,12 @@ class Trainer:
 
     def __init__(self, board_size=9, n_mcts=400, tau_thres=6, seed=0, n_blocks=10, in_planes=5, out_planes=128,
                  n_selfplay=100, memory_size=30000, n_epochs=1, batch_size=32, lr=2e-4, l2=0.0, device=None,
-                 data_dir="data", group=None):
+                 data_dir="data", group=None, max_slots=4096):
         self.BOARD_SIZE, self.N_MCTS, self.TAU_THRES, self.SEED = board_size, n_mcts, tau_thres, seed
         self.N_BLOCKS, self.IN_PLANES, self.OUT_PLANES = n_blocks, in_planes, out_planes
         self.N_SELFPLAY, self.MEMORY_SIZE, self.N_EPOCHS, self.BATCH_SIZE = n_selfplay, memory_size, n_epochs, batch_size
         self.data_dir, self.group = data_dir, group
+        self.max_slots = max_slots  # concurrent games resident in HBM; more episodes than that run in continuous mode
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         random.seed(seed)           # main.py:59-63
         np.random.seed(seed)
@@ -149,24 +150,30 @@ class Trainer:
         from . import _cabi
         n = n_selfplay or self.N_SELFPLAY
         self.model.eval()
-        if self._engine is None or self._engine.G < n:
+        slots = min(n, self.max_slots)
+        if self._engine is None or self._engine.G < slots:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = _cabi.Engine(board_size=self.BOARD_SIZE, num_mcts=self.N_MCTS, max_games=n, noise=True,
+            self._engine = _cabi.Engine(board_size=self.BOARD_SIZE, num_mcts=self.N_MCTS, max_games=slots, noise=True,
                                         tau_thres=self.TAU_THRES, n_blocks=self.N_BLOCKS, inplanes=self.IN_PLANES,
                                         seed=self.SEED, device=self.device.index or 0)
         eng = self._engine
         eng.load_state_dict(self.model.state_dict())
         eng.choose_nn_precision()
         # per-game decision-stream keys are global episode numbers: independent of how games are sharded over ranks
-        eng.selfplay_begin(n, first_key=self._episodes + self.rank * n)
+        first_key = self._episodes + self.rank * n
+        if n > slots:   # a slot that finishes its episode takes the next unplayed key (ao_selfplay_stream_begin)
+            eng.selfplay_stream_begin(n, n_slots=slots, first_key=first_key)
+        else:
+            eng.selfplay_begin(n, first_key=first_key)
         self._episodes += n * self.world
         st = eng.selfplay_rounds(256)
         while st["running"]:
             st = eng.selfplay_rounds(256)
         if st["errors"]:
             raise _cabi.AoError("%d game tree(s) overflowed their arena; raise node_cap" % st["errors"])
-        slab = replay.allgather_records(replay.device_records(eng, n), self.group)
+        local = replay.device_stream_records(eng) if n > slots else replay.device_records(eng, n)
+        slab = replay.allgather_records(local, self.group)
         winners = slab[:, 2]
         for name, code in (("Black", 1), ("White", 2), ("Draw", 3)):
             self.result[name] += int((winners == code).sum())

@@ -94,6 +94,14 @@ int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_key, int re
 int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out8);
 int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_moves, int8_t* winners,
                       uint32_t* visits);
+/* Continuous self-play: n_slots concurrent games play the episodes with decision-stream keys [first_key, first_key +
+ * n_episodes); a slot whose episode ends packs its record on the device and takes the next unplayed key (main.py:132
+ * `for episode in range(n_selfplay)` with more episodes than game slots).  Drive it with ao_selfplay_rounds until no
+ * game is running; ao_selfplay_stream_records_dev then returns the DEVICE slab of n_episodes records in ao_records_dev's
+ * layout, index = key - first_key.  Episodes are functions of their key alone: the records equal those of
+ * ao_selfplay_begin runs with the same keys.  Needs noise_mode == AO_NOISE_DEVICE (or noise off). */
+int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t first_key, int n_episodes);
+int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_game, int* n_episodes);
 /* ao_selfplay_rounds with CUDA events around every launch: summed device milliseconds of the tree-step kernels and of
  * the tower kernels over the `rounds` rounds (bench.py's roofline numbers). rounds <= 4096. */
 int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out8, float* tree_ms, float* tower_ms);

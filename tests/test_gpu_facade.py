@@ -240,3 +240,16 @@ def test_evaluator_dropin_trained_vs_random(golden_dir):
     assert (p_elo, e_elo) == (exp_p, exp_e)
     with pytest.raises(NotImplementedError):
         ev.set_agents(ckpt, "puct", ckpt)
+
+
+def test_self_play_facade_continuous_mode_equals_batch_mode():
+    """agents.self_play with more episodes than resident game slots (continuous mode) returns the same cur_memory as the
+    all-at-once run: the episodes are functions of their decision-stream keys"""
+    from alpha_omok_b200 import agents, model
+    net = model.PVNet(2, 5, 128, 9)
+    net.load_state_dict(pvnet_ref.make_state_dict(4, 2, 5, 128, 9), strict=False)
+    a, ra = agents.self_play(net, 14, board_size=9, num_mcts=20, seed=3)
+    b, rb = agents.self_play(net, 14, board_size=9, num_mcts=20, seed=3, max_slots=4)
+    assert ra == rb and len(a) == len(b) > 14 * 9
+    for (s1, p1, z1), (s2, p2, z2) in zip(a, b):
+        assert np.array_equal(s1, s2) and np.array_equal(p1, p2) and z1 == z2

@@ -509,3 +509,40 @@ def test_config1_end_to_end_without_replay_vs_reference_game(cabi):
     assert reordered <= 8
     assert prefix == len(gm) == int(n_moves[game]) and int(winners[game]) == int(fx["winner"])
     eng.close()
+
+
+@pytest.mark.parametrize("eval_mode", ["synth", "pvnet"])
+def test_continuous_selfplay_records_equal_batch_runs(cabi, eval_mode):
+    """continuous self-play (a slot that finishes its episode packs the record and takes the next unplayed key) must give,
+    key for key, the records of plain runs with the same keys: 40 episodes on 6 slots vs one 40-slot batch"""
+    from alpha_omok_b200 import replay
+    B, N, SLOTS, sims = 9, 40, 6, 24
+    kw = dict(board_size=B, num_mcts=sims, seed=77, n_blocks=2)
+    if eval_mode == "synth":
+        kw["eval_mode"] = cabi.AO_EVAL_SYNTH
+    sd = pvnet_ref.make_state_dict(5, 2, 5, 128, B)
+
+    def run(eng, begin):
+        if eval_mode == "pvnet":
+            eng.load_state_dict(sd)
+        begin(eng)
+        st = eng.selfplay_rounds(64)
+        while st["running"]:
+            st = eng.selfplay_rounds(64)
+        assert st["errors"] == 0
+        return st
+
+    ref = cabi.Engine(max_games=N, **kw)
+    run(ref, lambda e: e.selfplay_begin(N, first_key=100))
+    want = replay.device_records(ref, N).clone()
+    ref.close()
+    eng = cabi.Engine(max_games=SLOTS, **kw)
+    st = run(eng, lambda e: e.selfplay_stream_begin(N, first_key=100))
+    got = replay.device_stream_records(eng).clone()
+    assert st["games_finished"] == N and got.shape == want.shape
+    assert torch.equal(got, want)
+    # a second run on the same engine with fewer episodes than slots, other keys
+    run(eng, lambda e: e.selfplay_stream_begin(4, first_key=120))
+    got2 = replay.device_stream_records(eng)
+    assert got2.shape[0] == 4 and torch.equal(got2, want[20:24])
+    eng.close()
