@@ -238,3 +238,39 @@ class Trainer:
             if n_iter % save_every == 0:
                 self.save(n_iter + save_every)
             self.reset_iter()
+
+
+def main(argv=None):
+    """`python -m alpha_omok_b200.trainer` = main.py's `__main__` block (main.py:377-407) with its module constants as flags."""
+    import argparse
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("--board-size", type=int, default=9, choices=(9, 15))          # env_small / env_regular
+    ap.add_argument("--n-mcts", type=int, default=400)
+    ap.add_argument("--n-selfplay", type=int, default=100, help="episodes of iteration 0 (N_SELFPLAY)")
+    ap.add_argument("--n-selfplay-later", type=int, default=1, help="episodes per later iteration (main.py:398)")
+    ap.add_argument("--memory-size", type=int, default=30000)
+    ap.add_argument("--batch-size", type=int, default=32)
+    ap.add_argument("--total-iter", type=int, default=10000000)
+    ap.add_argument("--save-every", type=int, default=100)
+    ap.add_argument("--max-slots", type=int, default=4096)
+    ap.add_argument("--max-train-samples", type=int, default=None)
+    ap.add_argument("--model-path", default=None)
+    ap.add_argument("--dataset-path", default=None)
+    ap.add_argument("--data-dir", default="data")
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args(argv)
+    os.makedirs("logs", exist_ok=True)
+    logging.basicConfig(filename="logs/log_{}.txt".format(datetime.now().strftime("%y%m%d")), level=logging.WARNING)
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    tr = Trainer(board_size=a.board_size, n_mcts=a.n_mcts, n_selfplay=a.n_selfplay, memory_size=a.memory_size,
+                 batch_size=a.batch_size, seed=a.seed, data_dir=a.data_dir, max_slots=a.max_slots)
+    tr.load_data(a.model_path, a.dataset_path)
+    tr.run(a.total_iter, save_every=a.save_every, n_selfplay_later=a.n_selfplay_later, max_samples=a.max_train_samples)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
