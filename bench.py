@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_EXPANSION = {9: 478_800_004, 15: 1_330_129_156}  # one PVNet forward, 2*MAC, padded taps
-TOWER_DRAM_BYTES_PER_LAUNCH = {(9, 4096): 6_712_064}  # ncu capture, round 1 v6 (profiles/r01_tower_stag_kernel_ncu_full_summary.txt)
+TOWER_DRAM_BYTES_PER_LAUNCH = {(9, 4096): 6_716_160}  # ncu capture of bench.py itself, round 1 v7 (profiles/r01_tower_stag_kernel_v7_ncu_full_summary.txt)
 METRIC = "MCTS node-expansions/sec, 9x9 Omok self-play @400 sims/move"
 
 
@@ -340,7 +340,7 @@ def run_ours(a):
                          "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": peak_src + ", bf16 sustained",
                          "frac_of_burst": achieved / burst,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (4096 leaves), from the committed
-                         # ncu --set full capture profiles/r01_tower_stag_kernel_ncu_full_summary.txt
+                         # ncu --set full capture profiles/r01_tower_stag_kernel_v7_ncu_full_summary.txt
                          "traffic": TOWER_DRAM_BYTES_PER_LAUNCH.get((B, G)),
                          "kernel_share_of_step": tot[5] / (tot[5] + tot[6]) if tot[5] + tot[6] > 0 else None,
                          "tower_ms_per_launch": tower_ms_rank / (a.steps * S), "tree_ms_per_launch": tot[6] / world / (a.steps * S),
