@@ -60,7 +60,10 @@ class _EngineOwner:
         if self.model is None:
             raise RuntimeError("ZeroAgent.model is not set (assign a PVNet before searching, main.py:81)")
         sd = self.model.state_dict()
-        fp = (id(self.model),) + tuple((id(t), getattr(t, "_version", 0)) for t in sd.values())
+        # state_dict() hands out fresh detached aliases on every call: identify the weights by storage address and
+        # version counter (shared with the parameter; bumped by optimizer steps and load_state_dict), not by id()
+        fp = (id(self.model),) + tuple((t.data_ptr(), t._version) if hasattr(t, "data_ptr") else (id(t), 0)
+                                       for t in sd.values())
         if fp != self._fingerprint:
             self._engine.load_state_dict(sd)
             self._fingerprint = fp

@@ -120,7 +120,7 @@ class PVNet(nn.Module):
 
     # ---- weights -> device engine (shared with ZeroAgent)
     def weights_fingerprint(self):
-        return tuple((id(t), t._version) for t in self.state_dict().values())
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict().values())
 
     def _inference_engine(self, batch):
         fp = self.weights_fingerprint()

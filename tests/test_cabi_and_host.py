@@ -193,3 +193,41 @@ def test_aux_utils_match_reference_golden(capsys):
             assert float((st * np.arange(1, 6)).sum()) == c["state_tf_sum"][t]
         if c["state_tf"] is not None:
             assert np.array_equal(utils.get_state_tf(rid, 0, B, 5), np.asarray(c["state_tf"]))
+
+
+def test_weights_are_uploaded_once_per_change_not_once_per_search():
+    """the facades re-fold / re-upload the network only when its parameters changed: state_dict() returns fresh alias
+    tensors on every call, so the fingerprint must not depend on their id()"""
+    from alpha_omok_b200 import agents, model
+
+    class FakeEngine:
+        uploads = probes = 0
+
+        def load_state_dict(self, sd):
+            self.uploads += 1
+
+        def choose_nn_precision(self):
+            self.probes += 1
+
+    agent = agents.ZeroAgent(9, 8, 5)
+    agent.model = model.PVNet(2, 5, 128, 9)
+    agent._engine = FakeEngine()
+    for _ in range(3):
+        agent._sync_weights()
+    assert agent._engine.uploads == 1 and agent._engine.probes == 1
+    opt = torch.optim.SGD(agent.model.parameters(), lr=0.1)
+    agent.model.train()
+    p, v = agent.model(torch.zeros(2, 5, 9, 9))
+    (p.sum() + v.sum()).backward()
+    opt.step()
+    agent._sync_weights()
+    agent._sync_weights()
+    assert agent._engine.uploads == 2
+    agent.model.load_state_dict(model.seeded_state_dict(1, 2, 5, 128, 9), strict=False)
+    agent._sync_weights()
+    assert agent._engine.uploads == 3
+    other = model.PVNet(2, 5, 128, 9)       # main.py:81 style re-assignment of Agent.model
+    agent.model = other
+    agent._sync_weights()
+    assert agent._engine.uploads == 4
+    agent._engine = None                     # do not let __del__ paths touch the fake
