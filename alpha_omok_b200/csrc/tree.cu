@@ -458,6 +458,7 @@ __device__ void play_move(Ctx& c, Regs& g) {
     if (mode == 3) {
       // continuous self-play: the finished episode's record goes to index (key - first_key) of the stream slab (same
       // layout as pack_records_kernel), then the slot takes the next unplayed key - or retires when none is left
+      __syncwarp();  // lane 0's store of the last move (advance_root) must be visible to the lanes that copy the moves
       const uint32_t key = c.gm->game_key;
       uint8_t* out = P.stream_out + (size_t)(key - P.stream_first_key) * P.stream_rec_bytes;
       if (c.lane == 0) {
@@ -872,6 +873,8 @@ __global__ void pack_records_kernel(TreeParams P, int n, uint8_t* out, size_t by
   int16_t* mv = hdr + 2;
   for (int i = threadIdx.x; i < P.A; i += blockDim.x) mv[i] = i < gm->n_moves ? (int16_t)gm->moves[i] : (int16_t)-1;
   const size_t voff = (4 + (size_t)P.A * 2 + 3) & ~(size_t)3;
+  if (threadIdx.x == 0)
+    for (size_t i = 4 + (size_t)P.A * 2; i < voff; ++i) rec[i] = 0;  // alignment padding: records compare byte for byte
   uint32_t* vis = reinterpret_cast<uint32_t*>(rec + voff);
   const uint32_t* src = P.rec_visits + (size_t)game * P.A * P.A;
   for (int i = threadIdx.x; i < P.A * P.A; i += blockDim.x) vis[i] = (i / P.A) < gm->n_moves ? src[i] : 0u;
