@@ -6,15 +6,21 @@
 // one tile (TMEM -> bias/ReLU -> fp16 operand rows in smem) runs while the tensor core works on the other tile,
 // instead of MMA and epilogue taking turns:
 //
-//   MMA issue order of a layer:  T0[c, neg taps]  T0[pos taps]  T1[c, neg taps]  commit(acc T0)  T1[pos taps]  commit(acc T1)
-//   needs (previous layer):        epi T0           epi T1        (both)                            -
+//   stream 0 (warp 9), tile T0:  T0[centre, negative-shift taps]  T0[positive-shift taps]   commit -> acc T0, acc T1
+//   needs (previous layer):         epilogue of T0                   epilogue of T1
+//   stream 1 (warp 8), tile T1:  T1[centre, negative-shift taps]  commit -> acc T0   T1[positive-shift taps]  commit -> acc T1
+//   needs (previous layer):         epilogues of T0 and T1
 //
 // With dense packing the tiles depend on each other only through the +-(B+1) boundary rows: taps with a negative row
 // shift read rows below, so T0's centre/negative taps need T0's own epilogue only and its positive taps also T1's first
-// rows; T1's negative taps read T0's last rows, which is why acc T0 is committed (and T0's rows are overwritten in
-// place by its epilogue) only after them.  All 8 epilogue warps work on ONE tile at a time (64 accumulator columns per
-// thread).  Both tiles use every tap, so the weight ring holds exactly one layer of this CTA's half of B (9 slots x
-// 16 KB): T0 reads a slot, T1 reads it again and releases it, and the next layer's tap streams in behind it.
+// rows; T1's negative taps read T0's last rows.  A tile's epilogue overwrites its rows in place, so it may start only
+// when the tile is accumulated AND the other stream no longer reads its boundary rows: every acc barrier collects one
+// commit from each stream.  All 8 epilogue warps work on ONE tile at a time (64 accumulator columns per thread) and
+// signal their two 32-column groups separately, so stream 0 can start the matching k-steps of the next layer early.
+// The epilogues stagger the two streams by themselves: while one tile is in its epilogue the other stream has the
+// tensor pipe alone.  Both tiles use every tap, so the weight ring holds exactly one layer of this CTA's half of B
+// (9 slots x 16 KB, slot = tap); a slot is released by one commit from each stream and the next layer's tap streams
+// in behind it.
 //
 // Warp roles (480 threads): 0-7 epilogue, 8 and 9 the MMA issuers of tile 1 / tile 0 (leader CTA; in the peer CTA warp 9
 // forwards weights-landed), 10-13 heads (1x1 conv outputs -> FC/softmax/tanh of the PREVIOUS pass while the tower of the
