@@ -123,12 +123,16 @@ class Trainer:
 
     def __init__(self, board_size=9, n_mcts=400, tau_thres=6, seed=0, n_blocks=10, in_planes=5, out_planes=128,
                  n_selfplay=100, memory_size=30000, n_epochs=1, batch_size=32, lr=2e-4, l2=0.0, device=None,
-                 data_dir="data", group=None, max_slots=4096):
+                 data_dir="data", group=None, max_slots=4096, nn_precision="auto"):
         self.BOARD_SIZE, self.N_MCTS, self.TAU_THRES, self.SEED = board_size, n_mcts, tau_thres, seed
         self.N_BLOCKS, self.IN_PLANES, self.OUT_PLANES = n_blocks, in_planes, out_planes
         self.N_SELFPLAY, self.MEMORY_SIZE, self.N_EPOCHS, self.BATCH_SIZE = n_selfplay, memory_size, n_epochs, batch_size
         self.data_dir, self.group = data_dir, group
         self.max_slots = max_slots  # concurrent games resident in HBM; more episodes than that run in continuous mode
+        # "auto": keep policy / value within 1e-4 of fp32 for whatever the weights are (trained nets then run the 3-MMA
+        # split mode, ~2.7x slower); 0 (AO_NN_FP16): always single-pass fp16, ~2e-3 on trained nets - the usual
+        # AlphaZero trade-off for self-play data, but outside this repository's parity contract
+        self.nn_precision = nn_precision
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         random.seed(seed)           # main.py:59-63
         np.random.seed(seed)
@@ -159,7 +163,10 @@ class Trainer:
                                         seed=self.SEED, device=self.device.index or 0)
         eng = self._engine
         eng.load_state_dict(self.model.state_dict())
-        eng.choose_nn_precision()
+        if self.nn_precision == "auto":
+            eng.choose_nn_precision()
+        else:
+            eng.set_nn_precision(int(self.nn_precision))
         # per-game decision-stream keys are global episode numbers: independent of how games are sharded over ranks
         first_key = self._episodes + self.rank * n
         if n > slots:   # a slot that finishes its episode takes the next unplayed key (ao_selfplay_stream_begin)
@@ -253,6 +260,7 @@ def main(argv=None):
     ap.add_argument("--total-iter", type=int, default=10000000)
     ap.add_argument("--save-every", type=int, default=100)
     ap.add_argument("--max-slots", type=int, default=4096)
+    ap.add_argument("--nn-precision", default="auto", help="auto | 0 (fp16 single pass) | 1 (hi/lo split)")
     ap.add_argument("--max-train-samples", type=int, default=None)
     ap.add_argument("--model-path", default=None)
     ap.add_argument("--dataset-path", default=None)
@@ -265,7 +273,8 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
     tr = Trainer(board_size=a.board_size, n_mcts=a.n_mcts, n_selfplay=a.n_selfplay, memory_size=a.memory_size,
-                 batch_size=a.batch_size, seed=a.seed, data_dir=a.data_dir, max_slots=a.max_slots)
+                 batch_size=a.batch_size, seed=a.seed, data_dir=a.data_dir, max_slots=a.max_slots,
+                 nn_precision=a.nn_precision if a.nn_precision == "auto" else int(a.nn_precision))
     tr.load_data(a.model_path, a.dataset_path)
     tr.run(a.total_iter, save_every=a.save_every, n_selfplay_later=a.n_selfplay_later, max_samples=a.max_train_samples)
     if dist.is_initialized():
