@@ -68,6 +68,13 @@ struct ao_engine {
   size_t stream_capacity;      // episodes the slab can hold
   uint32_t* d_stream_next;
   int stream_episodes;         // episodes of the current stream run (0 = none)
+  // CUDA graph of kGraphRounds lock-step rounds (memsets + tree step + tower), re-captured whenever a kernel argument
+  // changes; ao_selfplay_rounds replays it instead of issuing 4 stream operations per round
+  cudaGraphExec_t round_graph;
+  ao::TreeParams graph_tp;
+  ao::TowerWeights graph_tw;
+  int graph_n, graph_max_iters, graph_precision;
+  bool graph_disabled;
   // optional per-kernel timing (bench roofline): event pairs recorded around every launch of a timed call
   bool timing;
   std::vector<cudaEvent_t> ev;  // [tree_begin, tree_end(=tower_begin), tower_end] per round
@@ -100,6 +107,57 @@ int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int ti
     h->launches += 1;
   }
   if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 2], h->stream));
+  return 0;
+}
+
+constexpr int kGraphRounds = 16;
+
+// `rounds` lock-step rounds over the first n game slots; whole multiples of kGraphRounds are replayed from a CUDA graph
+// (captured from run_round itself, so both paths launch exactly the same work), the rest is issued directly.
+int run_rounds(ao_engine* h, int n, int max_iters, int rounds) {
+  int rc;
+  int done = 0;
+  const bool graphable = !h->graph_disabled && rounds >= 2 * kGraphRounds;
+  if (graphable) {
+    const bool stale = h->round_graph == nullptr || h->graph_n != n || h->graph_max_iters != max_iters ||
+                       h->graph_precision != h->cfg.nn_precision || memcmp(&h->graph_tp, &h->tp, sizeof h->tp) != 0 ||
+                       memcmp(&h->graph_tw, &h->tw, sizeof h->tw) != 0;
+    if (stale) {
+      if (h->round_graph) cudaGraphExecDestroy(h->round_graph);
+      h->round_graph = nullptr;
+      // one direct round first: per-kernel attributes (dynamic smem opt-in) are set outside the capture
+      if ((rc = run_round(h, nullptr, n, max_iters)) != 0) return rc;
+      ++done;
+      cudaGraph_t graph = nullptr;
+      const unsigned long long launches0 = h->launches;
+      cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        for (int r = 0; r < kGraphRounds && rc == 0; ++r) rc = run_round(h, nullptr, n, max_iters);
+        e = cudaStreamEndCapture(h->stream, &graph);
+      }
+      h->launches = launches0;  // nothing ran during the capture
+      if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&h->round_graph, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e != cudaSuccess || rc != 0 || !h->round_graph) {  // fall back to direct launches for good
+        cudaGetLastError();
+        h->round_graph = nullptr;
+        h->graph_disabled = true;
+      } else {
+        memcpy(&h->graph_tp, &h->tp, sizeof h->tp);
+        memcpy(&h->graph_tw, &h->tw, sizeof h->tw);
+        h->graph_n = n;
+        h->graph_max_iters = max_iters;
+        h->graph_precision = h->cfg.nn_precision;
+      }
+    }
+    while (h->round_graph && rounds - done >= kGraphRounds) {
+      AO_CUDA(cudaGraphLaunch(h->round_graph, h->stream));
+      h->launches += (h->cfg.eval_mode == AO_EVAL_PVNET ? 2ull : 1ull) * kGraphRounds;
+      done += kGraphRounds;
+    }
+  }
+  for (; done < rounds; ++done)
+    if ((rc = run_round(h, nullptr, n, max_iters)) != 0) return rc;
   return 0;
 }
 
@@ -151,6 +209,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->weights_loaded = false;
   h->selfplay_games = 0;
   h->d_stream = nullptr; h->stream_capacity = 0; h->d_stream_next = nullptr; h->stream_episodes = 0;
+  h->round_graph = nullptr; h->graph_n = -1; h->graph_disabled = getenv("AO_NO_GRAPH") != nullptr;
   h->timing = false;
   h->launches = 0;
   h->h_pinned = nullptr;
@@ -224,6 +283,7 @@ extern "C" int ao_engine_destroy(ao_engine* h) {
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_stream) cudaFree(h->d_stream);
+  if (h->round_graph) cudaGraphExecDestroy(h->round_graph);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -531,8 +591,7 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   const bool synth = h->cfg.eval_mode == AO_EVAL_SYNTH;
   const int max_iters = synth ? (1 << 30) : 64;
   int rc;
-  for (int r = 0; r < rounds; ++r)
-    if ((rc = run_round(h, nullptr, h->selfplay_games, max_iters)) != 0) return rc;
+  if ((rc = run_rounds(h, h->selfplay_games, max_iters, rounds)) != 0) return rc;
   AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
   h->launches += 1;
   unsigned long long c[8];
