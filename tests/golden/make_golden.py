@@ -284,6 +284,16 @@ def gen_train(R):
     print("train_9_small OK  losses", losses[0], "->", losses[-1])
 
 
+def gen_trained_checkpoint():
+    """the reference's shipped trained network (data/180927_9400_297233_step_model.pickle, 121 fp32 tensors of
+    PVNet(10,5,128,9) without num_batches_tracked keys) re-saved as .npz: the 'trained' side of BASELINE config 5 and the
+    realistic-weights numerics fixture.  Weights are data, not code; nothing else is taken over."""
+    src = os.path.join(REF, "data", "180927_9400_297233_step_model.pickle")
+    sd = torch.load(src, map_location="cpu")
+    np.savez_compressed(os.path.join(HERE, "trained_9x9_180927.npz"), **{k: v.numpy() for k, v in sd.items()})
+    print("trained_9x9_180927.npz OK", len(sd), "tensors")
+
+
 def gen_utils_aux(R):
     """the reference's non-hot-path utils (render_str, valid_actions, get_reward, get_state_tf) on random boards"""
     import contextlib, io, json
@@ -323,10 +333,14 @@ def main():
     if "--only-utils-aux" in sys.argv:
         gen_utils_aux(R)
         return
+    if "--only-trained" in sys.argv:
+        gen_trained_checkpoint()
+        return
     gen_rules(R)
     gen_nn(R)
     gen_train(R)
     gen_utils_aux(R)
+    gen_trained_checkpoint()
     gen_mcts_game(R, "mcts_9_synth_s40", 9, 40, seed=11, game=0, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
     gen_mcts_game(R, "mcts_9_synth_s400", 9, 400, seed=12, game=3, noise=True, tau_thres=6, max_moves=None, nn_kind="synth")
     gen_mcts_game(R, "mcts_9_synth_nonoise", 9, 60, seed=13, game=1, noise=False, tau_thres=0, max_moves=None, nn_kind="synth")
