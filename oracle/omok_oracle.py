@@ -25,7 +25,7 @@ from __future__ import annotations
 import numpy as np
 
 # --------------------------------------------------------------------------------------------------------------
-# Decision stream: Philox4x32-10, identical on host (here) and device (csrc/rng.cuh).
+# Decision stream: Philox4x32-10, identical on host (here) and device (philox4x32 in csrc/rules.cuh, used by csrc/tree.cu).
 # counter = (index, 0, game, stream) ; key = (seed_lo, seed_hi)
 # --------------------------------------------------------------------------------------------------------------
 _M0, _M1, _W0, _W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
