@@ -25,12 +25,15 @@ class AoConfig(C.Structure):
     ]
 
 
-EXPORTS = [
+EXPORTS = [  # every symbol include/alpha_omok_b200.h declares (checked by tests/test_cabi_and_host.py)
     "ao_last_error", "ao_engine_create", "ao_engine_destroy", "ao_load_weights", "ao_games_reset",
-    "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode", "ao_selfplay_stream_begin", "ao_selfplay_stream_records_dev", "ao_selfplay_rounds",
-    "ao_selfplay_rounds_timed", "ao_launch_count", "ao_tower_debug", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev", "ao_records_pack", "ao_augment_records_dev", "ao_replay_extend_dev", "ao_replay_gather_dev", "ao_synchronize", "ao_check_win",
-    "ao_encode_state", "ao_legal_actions", "ao_umma_probe", "ao_umma_probe_masked", "ao_umma_rate",
+    "ao_set_gamma_tape", "ao_search", "ao_nn_forward", "ao_selfplay_begin", "ao_selfplay_begin_mode",
+    "ao_selfplay_stream_begin", "ao_selfplay_stream_records_dev", "ao_selfplay_rounds", "ao_selfplay_rounds_timed",
+    "ao_launch_count", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev",
+    "ao_records_pack", "ao_augment_records_dev", "ao_replay_extend_dev", "ao_replay_gather_dev", "ao_synchronize",
+    "ao_check_win", "ao_encode_state", "ao_legal_actions",
 ]
+PROBE_EXPORTS = ["ao_tower_debug", "ao_umma_probe", "ao_umma_probe_masked", "ao_umma_rate"]  # alpha_omok_b200_probe.h
 
 _lib = None
 
@@ -39,15 +42,7 @@ class AoError(RuntimeError):
     pass
 
 
-def lib():
-    """Load (building if necessary) libalpha_omok_b200.so."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build()
-    L = C.CDLL(path)
+def _bind(L):
     L.ao_last_error.restype = C.c_char_p
     vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
     L.ao_engine_create.argtypes = [C.POINTER(AoConfig), C.POINTER(vp)]
@@ -63,7 +58,6 @@ def lib():
     L.ao_selfplay_stream_begin.argtypes = [vp, i32, u32, i32]
     L.ao_selfplay_stream_records_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(i32)]
     L.ao_selfplay_rounds_timed.argtypes = [vp, i32, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
-    L.ao_tower_debug.argtypes = [vp, i32, vp]
     L.ao_set_nn_precision.argtypes = [vp, i32]
     L.ao_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ao_selfplay_fetch.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -78,13 +72,67 @@ def lib():
     L.ao_check_win.argtypes = [vp, i32, i32, vp]
     L.ao_encode_state.argtypes = [vp, vp, i32, i32, vp]
     L.ao_legal_actions.argtypes = [vp, vp, i32, i32, vp]
-    L.ao_umma_probe.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]
-    L.ao_umma_probe_masked.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp]
     for name in EXPORTS:
         if name != "ao_last_error":
             getattr(L, name).restype = C.c_int
-    _lib = L
     return L
+
+
+def lib():
+    """Load (building if necessary) libalpha_omok_b200.so - the product library.
+
+    Profiling tools set AO_USE_PROBE_LIB=1 to run the same Python API on libalpha_omok_b200_probe.so (the sources
+    compiled with -DAO_PROBE: tower cycle counters + AO_TOWER_XFLAGS experiments); tests and bench never do."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("AO_USE_PROBE_LIB") == "1":
+        _lib = probe_lib()
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()
+    _lib = _bind(C.CDLL(path))
+    return _lib
+
+
+_probe = None
+
+
+def probe_lib():
+    """libalpha_omok_b200_probe.so (include/alpha_omok_b200_probe.h): product entry points + instrumentation."""
+    global _probe
+    if _probe is None:
+        path = _build.PROBE_LIB_PATH
+        if not os.path.exists(path):
+            path = _build.build(probe=True)
+        L = _bind(C.CDLL(path))
+        vp, i32 = C.c_void_p, C.c_int32
+        L.ao_tower_debug.argtypes = [vp, i32, vp]
+        L.ao_umma_probe.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]
+        L.ao_umma_probe_masked.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp]
+        for name in PROBE_EXPORTS:
+            getattr(L, name).restype = C.c_int
+        _probe = L
+    return _probe
+
+
+def default_device(model=None):
+    """CUDA ordinal an engine created on behalf of `model` should live on: the device of the model's parameters when
+    they are on a GPU, otherwise torch's current device (so a torchrun rank that called torch.cuda.set_device(local_rank)
+    gets its own GPU), otherwise 0."""
+    try:
+        import torch
+        if model is not None:
+            for p in model.parameters():
+                if p.device.type == "cuda":
+                    return p.device.index if p.device.index is not None else torch.cuda.current_device()
+                break
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
 
 
 def check(rc):
@@ -115,6 +163,7 @@ class Engine:
                  nn_precision=AO_NN_FP16, nn_log_cap=0, c_puct=5.0, alpha=0.0, stream=None):
         self.B, self.A, self.G = board_size, board_size * board_size, max_games
         self.num_mcts = num_mcts
+        self.device = int(device)
         self.nn_precision = nn_precision
         cfg = AoConfig(device, board_size, inplanes, planes, n_blocks, num_mcts, int(bool(noise)), tau_thres,
                        max_games, node_cap, eval_mode, noise_mode, nn_precision, nn_log_cap, float(c_puct),
@@ -240,6 +289,9 @@ class Engine:
         return self._counters(out, tree_ms=a.value, tower_ms=b.value)
 
     def tower_debug(self, enable=True):
+        """probe build only (AO_USE_PROBE_LIB=1): cycle counters of CTA 0 of the tower kernel"""
+        if not hasattr(lib(), "ao_tower_debug"):
+            raise AoError("ao_tower_debug exists only in libalpha_omok_b200_probe.so (set AO_USE_PROBE_LIB=1)")
         out = np.zeros(8, np.uint64)
         check(lib().ao_tower_debug(self._h, int(enable), ptr(out)))
         return [int(x) for x in out]

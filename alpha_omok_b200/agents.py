@@ -52,6 +52,7 @@ class _EngineOwner:
             n_blocks = len({k.split(".")[1] for k in m.state_dict() if k.startswith("layers.")})
         if getattr(self, "nn_precision", "auto") != "auto":
             kw.setdefault("nn_precision", self.nn_precision)
+        kw.setdefault("device", _cabi.default_device(m))
         return _cabi.Engine(board_size=self.board_size, num_mcts=self.num_mcts, max_games=max_games,
                             noise=self.noise, n_blocks=n_blocks, inplanes=self.inplanes, c_puct=self.c_puct,
                             alpha=self.alpha, **kw)
@@ -218,7 +219,8 @@ def self_play(model, n_selfplay, board_size=9, num_mcts=400, inplanes=5, tau_thr
         n_blocks = getattr(model, "n_block", None) or len(
             {k.split(".")[1] for k in model.state_dict() if k.startswith("layers.")})
         engine = _cabi.Engine(board_size=board_size, num_mcts=num_mcts, max_games=slots, noise=noise,
-                              tau_thres=tau_thres, n_blocks=n_blocks, inplanes=inplanes, seed=seed)
+                              tau_thres=tau_thres, n_blocks=n_blocks, inplanes=inplanes, seed=seed,
+                              device=_cabi.default_device(model))
         engine.load_state_dict(model.state_dict())
     else:
         slots = min(slots, engine.G)

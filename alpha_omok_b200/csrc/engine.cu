@@ -33,6 +33,21 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(-100 - (int)e__, "%s: %s", #x, cudaGetErrorString(e__)); \
   } while (0)
 
+// Every entry point runs with the engine's device current and restores the caller's device on the way out (an engine
+// created for GPU k inside a process whose current device is j must neither fail nor silently switch the caller to k).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 template <class T>
 cudaError_t dalloc(T** p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
@@ -79,6 +94,8 @@ struct ao_engine {
   bool timing;
   std::vector<cudaEvent_t> ev;  // [tree_begin, tree_end(=tower_begin), tower_end] per round
   unsigned long long launches;  // kernels launched by this engine (bench's gpu_launches)
+  float* d_fwd_states;          // ao_nn_forward staging (lazily allocated)
+  int* d_fwd_bad;
 };
 
 namespace {
@@ -193,7 +210,8 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   cudaError_t e0 = cudaGetDeviceCount(&ndev);
   if (e0 != cudaSuccess || ndev == 0)
     return fail(-4, "no CUDA device: alpha_omok_b200 has no CPU fallback (%s)", cudaGetErrorString(e0));
-  AO_CUDA(cudaSetDevice(cfg->device));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(-1, "device %d out of range 0..%d", cfg->device, ndev - 1);
+  DeviceGuard guard(cfg->device);
   cudaDeviceProp prop;
   AO_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail(-4, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
@@ -213,6 +231,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->timing = false;
   h->launches = 0;
   h->h_pinned = nullptr;
+  h->d_fwd_states = nullptr; h->d_fwd_bad = nullptr;
   if (cfg->stream) {
     h->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
     h->own_stream = false;
@@ -280,6 +299,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
 
 extern "C" int ao_engine_destroy(ao_engine* h) {
   if (!h) return 0;
+  DeviceGuard guard(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_stream) cudaFree(h->d_stream);
@@ -293,6 +313,7 @@ extern "C" int ao_engine_destroy(ao_engine* h) {
 
 extern "C" int ao_synchronize(ao_engine* h) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   AO_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -301,6 +322,7 @@ extern "C" int ao_synchronize(ao_engine* h) {
 extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* names, const float* const* ptrs,
                                const int64_t* numel) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   std::map<std::string, std::pair<const float*, int64_t>> sd;
   for (int i = 0; i < n_tensors; ++i) sd[names[i]] = {ptrs[i], numel[i]};
   const int A = h->A, C = 128, nb = h->cfg.n_blocks, CI = h->cfg.inplanes;
@@ -413,7 +435,9 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   AO_CUDA(cudaMemcpy(h->d_vfc1_b, v1b, (size_t)C * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(h->d_vfc2_w, v2w, (size_t)C * 4, cudaMemcpyHostToDevice));
   ao::TowerWeights& tw = h->tw;
+#ifdef AO_PROBE
   tw.xflags = getenv("AO_TOWER_XFLAGS") ? atoi(getenv("AO_TOWER_XFLAGS")) : 0;
+#endif
   tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.conv_pair = h->d_conv_pair; tw.conv_pair_lo = h->d_conv_pair_lo; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
   tw.pfc_wT = h->d_pfc_wT; tw.pfc_b = h->d_pfc_b; tw.vfc1_wT = h->d_vfc1_wT; tw.vfc1_b = h->d_vfc1_b; tw.vfc2_w = h->d_vfc2_w;
   tw.vfc2_b = v2b[0];
@@ -425,6 +449,7 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
 // ---------------------------------------------------------------------------------------------------- games
 extern "C" int ao_games_reset(ao_engine* h, const int32_t* game_ids, int n, const uint32_t* game_keys) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (n < 0 || n > h->G) return fail(-1, "n out of range");
   for (int i = 0; i < n; ++i)
     if (game_ids[i] < 0 || game_ids[i] >= h->G) return fail(-1, "game id %d out of range", game_ids[i]);
@@ -437,6 +462,7 @@ extern "C" int ao_games_reset(ao_engine* h, const int32_t* game_ids, int n, cons
 
 extern "C" int ao_set_gamma_tape(ao_engine* h, int game_id, const double* tape, int n_draws) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (!h->tp.gamma_tape) return fail(-1, "engine was not created with noise_mode = AO_NOISE_TAPE");
   if (game_id < 0 || game_id >= h->G) return fail(-1, "game id out of range");
   if (n_draws > h->tp.tape_rows) n_draws = h->tp.tape_rows;
@@ -448,12 +474,16 @@ extern "C" int ao_set_gamma_tape(ao_engine* h, int game_id, const double* tape, 
 extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int16_t* roots, const int32_t* root_lens,
                          uint32_t* visits, double* priors, int32_t* is_real_root) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (n < 1 || n > h->G) return fail(-1, "n = %d out of range 1..%d", n, h->G);
   int rc = require_weights(h);
   if (rc) return rc;
   const int A = h->A;
+  std::vector<uint8_t> seen((size_t)h->G, 0);  // one warp per listed slot: a slot listed twice would race on its tree
   for (int i = 0; i < n; ++i) {
     if (game_ids[i] < 0 || game_ids[i] >= h->G) return fail(-1, "game id %d out of range", game_ids[i]);
+    if (seen[game_ids[i]]) return fail(-1, "game id %d listed twice", game_ids[i]);
+    seen[game_ids[i]] = 1;
     if (root_lens[i] < 1 || root_lens[i] > A) return fail(-1, "root id length %d out of range 1..%d", root_lens[i], A);
   }
   AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
@@ -485,15 +515,19 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
 
 extern "C" int ao_nn_forward(ao_engine* h, const float* states, int n, float* p, float* v) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (!h->weights_loaded) return fail(-3, "no weights loaded");
   if (h->B != 9 && h->B != 15) return fail(-1, "tower kernel supports board_size 9 and 15");
   const int A = h->A, C = h->cfg.inplanes;
-  float* d_states = nullptr;
-  int* d_bad = nullptr;
   const int chunk = h->G;
-  AO_CUDA(dalloc(&d_states, (size_t)chunk * C * A));
-  AO_CUDA(dalloc(&d_bad, 1));
-  cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream);
+  if (!h->d_fwd_states) {  // staging of the dense input planes: allocated once, lives as long as the engine
+    int rc0;
+    if ((rc0 = ealloc(h, &h->d_fwd_states, (size_t)chunk * C * A)) != 0) return rc0;
+    if ((rc0 = ealloc(h, &h->d_fwd_bad, 1)) != 0) return rc0;
+  }
+  float* d_states = h->d_fwd_states;
+  int* d_bad = h->d_fwd_bad;
+  AO_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
   int rc = 0;
   for (int o = 0; o < n && rc == 0; o += chunk) {
     const int m = n - o < chunk ? n - o : chunk;
@@ -507,8 +541,6 @@ extern "C" int ao_nn_forward(ao_engine* h, const float* states, int n, float* p,
   }
   int bad = 0;
   if (rc == 0 && cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(-2, "memcpy failed");
-  cudaFree(d_states);
-  cudaFree(d_bad);
   if (rc == 0 && bad) rc = fail(-8, "states must be {0,1}-valued planes with a constant colour plane (utils.get_state_pt)");
   return rc;
 }
@@ -520,6 +552,7 @@ extern "C" int ao_selfplay_begin(ao_engine* h, int n_games, uint32_t first_key) 
 }
 extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_key, int recycle) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (n_games < 1 || n_games > h->G) return fail(-1, "n_games = %d out of range 1..%d", n_games, h->G);
   int rc = require_weights(h);
   if (rc) return rc;
@@ -539,6 +572,7 @@ extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_
 // short games no longer leave their slot idle while the longest game of the batch finishes.
 extern "C" int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t first_key, int n_episodes) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (n_episodes < 1) return fail(-1, "n_episodes = %d must be positive", n_episodes);
   if (n_slots > n_episodes) n_slots = n_episodes;
   if (n_slots < 1 || n_slots > h->G) return fail(-1, "n_slots = %d out of range 1..%d", n_slots, h->G);
@@ -577,6 +611,7 @@ extern "C" int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t firs
 // (complete once ao_selfplay_rounds reports 0 running games).  The pointer stays valid until the next stream_begin.
 extern "C" int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_game, int* n_episodes) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (h->stream_episodes <= 0) return fail(-1, "call ao_selfplay_stream_begin first");
   AO_CUDA(cudaStreamSynchronize(h->stream));
   if (dev_ptr) *dev_ptr = h->d_stream;
@@ -587,6 +622,7 @@ extern "C" int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size
 
 extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (h->selfplay_games <= 0) return fail(-1, "call ao_selfplay_begin first");
   const bool synth = h->cfg.eval_mode == AO_EVAL_SYNTH;
   const int max_iters = synth ? (1 << 30) : 64;
@@ -605,6 +641,7 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
 // tree-step kernels and of the tower kernels (ms) - the per-kernel numbers behind bench.py's roofline object.
 extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5, float* tree_ms, float* tower_ms) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (h->selfplay_games <= 0) return fail(-1, "call ao_selfplay_begin first");
   if (rounds < 1 || rounds > 4096) return fail(-1, "rounds out of range 1..4096");
   while ((int)h->ev.size() < 3 * rounds) {
@@ -635,11 +672,13 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
   return 0;
 }
 
+#ifdef AO_PROBE
 // Cycle counters of CTA 0 of the tower kernel, accumulated over all launches since enabling:
 // [0] MMA-issuer total, [1] MMA waits for the epilogue (operand ready), [2] MMA waits for weights (TMA ring),
 // [3] launches, [4] epilogue thread 0 total, [5] epilogue waits for the accumulators, [6] heads.
 extern "C" int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   AO_CUDA(cudaStreamSynchronize(h->stream));
   if (out8 && h->tw.dbg) AO_CUDA(cudaMemcpy(out8, h->tw.dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (enable && !h->tw.dbg) {
@@ -652,11 +691,13 @@ extern "C" int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8) {
   if (!enable) h->tw.dbg = nullptr;
   return 0;
 }
+#endif  // AO_PROBE
 
 // Switch the tower's operand mode at run time (AO_NN_*); the facades use it to pick the cheapest mode that meets the
 // 1e-4 contract for the loaded weights.
 extern "C" int ao_set_nn_precision(ao_engine* h, int mode) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (mode != AO_NN_FP16 && mode != AO_NN_FP16X3 && mode != AO_NN_FP16_1CTA && mode != AO_NN_FP16_LOCKSTEP) return fail(-1, "unknown nn_precision %d", mode);
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->cfg.nn_precision = mode;
@@ -672,6 +713,7 @@ extern "C" int ao_launch_count(ao_engine* h, uint64_t* out) {
 extern "C" int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int32_t* n_moves, int8_t* winners,
                                  uint32_t* visits) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (n_games < 1 || n_games > h->G) return fail(-1, "n_games out of range");
   const int A = h->A;
   AO_CUDA(ao::launch_pack_records(h->tp, n_games, h->d_records, h->rec_bytes, h->stream));
@@ -692,6 +734,7 @@ extern "C" int ao_selfplay_fetch(ao_engine* h, int n_games, int16_t* moves, int3
 
 extern "C" int ao_get_nn_log(ao_engine* h, int game_id, float* policy, float* value, int32_t capacity, int32_t* count) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (h->tp.nn_log_cap <= 0) return fail(-1, "engine was created with nn_log_cap = 0");
   if (game_id < 0 || game_id >= h->G) return fail(-1, "game id out of range");
   ao::Game g;
@@ -708,6 +751,7 @@ extern "C" int ao_get_nn_log(ao_engine* h, int game_id, float* policy, float* va
 
 extern "C" int ao_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_game) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (dev_ptr) *dev_ptr = h->d_records;
   if (bytes_per_game) *bytes_per_game = h->rec_bytes;
   return 0;
@@ -715,6 +759,7 @@ extern "C" int ao_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_per_ga
 
 extern "C" int ao_records_pack(ao_engine* h, int n_games) {
   if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
   if (n_games < 1 || n_games > h->G) return fail(-1, "n_games out of range");
   AO_CUDA(ao::launch_pack_records(h->tp, n_games, h->d_records, h->rec_bytes, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));

@@ -108,9 +108,20 @@ struct TowerWeights {
   const float* vfc2_w;     // [128]
   float vfc2_b;
   int n_layers;            // 1 + 2*n_blocks
+#ifdef AO_PROBE           // probe build only (libalpha_omok_b200_probe.so): never part of the product library
   unsigned long long* dbg; // optional profiling counters of CTA 0 (null = off), see ao_tower_debug
-  int xflags;              // timing experiments only (env AO_TOWER_XFLAGS, results become wrong): see tower_stag_kernel
+  int xflags;              // timing experiments (env AO_TOWER_XFLAGS, results become wrong): see tower_stag_kernel
+#endif
 };
+
+// Instrumentation hooks of the tower kernels: compiled in only with -DAO_PROBE.
+#ifdef AO_PROBE
+#define AO_DBG(...) __VA_ARGS__
+#define AO_XFLAG(W, bit) (((W).xflags & (bit)) != 0)
+#else
+#define AO_DBG(...)
+#define AO_XFLAG(W, bit) false
+#endif
 
 // host-side launchers implemented in the .cu files
 cudaError_t launch_tree_step(const TreeParams& p, const int32_t* game_ids, int n, int max_iters, cudaStream_t s);

@@ -242,8 +242,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;  // two k-chunks further along K
       constexpr uint32_t kBStep = (2u * kBRows * 16u) >> 4;
       uint32_t it = 0, act_phase = 0;
-      long long dbg_act_wait = 0, dbg_full_wait = 0;
-      const long long dbg_t0 = W.dbg ? clock64() : 0;
+      AO_DBG(long long dbg_act_wait = 0, dbg_full_wait = 0; const long long dbg_t0 = W.dbg ? clock64() : 0;)
       int g0, ng, ntiles;
       for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         for (int l = 0; l < n_layers; ++l) {
@@ -251,21 +250,21 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
           // X3 mode: every layer accumulates in a fresh accA and accB is only the epilogue's fp32 stash of x
           const bool to_b = !X3 && (l & 1) == 0;
           const bool residual = to_b && l > 0;
-          const long long t_a0 = W.dbg ? clock64() : 0;
+          AO_DBG(const long long t_a0 = W.dbg ? clock64() : 0;)
           if (PAIR) mbar_wait_cluster(bar_act, act_phase);  // 256 local arrivals + the peer's forwarded one
           else mbar_wait(bar_act, act_phase);
           act_phase ^= 1u;
           tc_fence_after_sync();
-          if (W.dbg) dbg_act_wait += clock64() - t_a0;
+          AO_DBG(if (W.dbg) dbg_act_wait += clock64() - t_a0;)
           const int n_st = !X3 ? 9 : (l == 0 ? 9 : 27);
           for (int st = 0; st < n_st; ++st, ++it) {
             const int s = it % NSLOT;
             const uint32_t ph = (it / NSLOT) & 1u;
-            const long long t_f0 = W.dbg ? clock64() : 0;
+            AO_DBG(const long long t_f0 = W.dbg ? clock64() : 0;)
             mbar_wait(&bar_full[s], ph);
             if (PAIR) mbar_wait_cluster(&bar_peer_full[s], ph);
             tc_fence_after_sync();
-            if (W.dbg) dbg_full_wait += clock64() - t_f0;
+            AO_DBG(if (W.dbg) dbg_full_wait += clock64() - t_f0;)
             const bool lo_phase = X3 && l > 0 && st < 18;
             // the weights are packed with the centre tap first: it has no disabled rows, so the first MMA of a fresh
             // accumulation (accumulate = 0) writes every accumulator row
@@ -330,12 +329,14 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
           }
         }
       }
+#ifdef AO_PROBE
       if (W.dbg && blockIdx.x == 0 && lane == 0 && stream == 0) {  // profiling counters (ao_tower_debug): MMA-issuer view of CTA 0
         atomicAdd(&W.dbg[0], (unsigned long long)(clock64() - dbg_t0));
         atomicAdd(&W.dbg[1], (unsigned long long)dbg_act_wait);
         atomicAdd(&W.dbg[2], (unsigned long long)dbg_full_wait);
         atomicAdd(&W.dbg[3], 1ull);
       }
+#endif
     }
   } else if (warp < 8) {
     // =========================================================== epilogue warps (256 threads)
@@ -349,9 +350,8 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     const uint32_t chunk_stride = (uint32_t)G::Rows * 16u;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * 256);
     uint32_t acc_phase = 0;
-    long long dbg_acc_wait = 0, dbg_heads = 0;
-    const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    const long long dbg_e0 = dbg_on ? clock64() : 0;
+    AO_DBG(long long dbg_acc_wait = 0, dbg_heads = 0; const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+           const long long dbg_e0 = dbg_on ? clock64() : 0;)
 
     int g0, ng, ntiles;
     for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
@@ -384,11 +384,11 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         const bool to_b = (l & 1) == 0;
         const bool last = l == n_layers - 1;
         const float* bias = s_bias + l * kC;
-        const long long t_w0 = dbg_on ? clock64() : 0;
+        AO_DBG(const long long t_w0 = dbg_on ? clock64() : 0;)
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1u;
         tc_fence_after_sync();
-        if (dbg_on) dbg_acc_wait += clock64() - t_w0;
+        AO_DBG(if (dbg_on) dbg_acc_wait += clock64() - t_w0;)
         const uint32_t stash_addr = lane_addr + 128u;                          // accB: fp32 block input x
         const uint32_t acc_addr = (!X3 && to_b) ? stash_addr : lane_addr;      // X3 accumulates in accA only
         // 4 chunks of 32 accumulator columns, TMEM loads double-buffered against the per-chunk math
@@ -475,7 +475,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         }
       }
       // ---- heads (model.py:43-50, 63-73)
-      const long long t_h0 = dbg_on ? clock64() : 0;
+      AO_DBG(const long long t_h0 = dbg_on ? clock64() : 0;)
       if (valid) {
         float* f = s_feat + g_local * 3 * G::A;
         f[0 * G::A + pos] = fmaxf(hd0 + W.head_b[0], 0.f);
@@ -529,13 +529,15 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       epi_bar_sync();
       if (p_thread) policy[(size_t)(g0 + pg) * G::A + po] = expf(logit - s_red[pg * 2]) / s_red[pg * 2 + 1];
       // s_feat / s_logits are rewritten only after the next pass's 21 layers: no extra barrier needed
-      if (dbg_on) dbg_heads += clock64() - t_h0;
+      AO_DBG(if (dbg_on) dbg_heads += clock64() - t_h0;)
     }
+#ifdef AO_PROBE
     if (dbg_on) {
       atomicAdd(&W.dbg[4], (unsigned long long)(clock64() - dbg_e0));
       atomicAdd(&W.dbg[5], (unsigned long long)dbg_acc_wait);
       atomicAdd(&W.dbg[6], (unsigned long long)dbg_heads);
     }
+#endif
   }
   tc_fence_before_sync();
   __syncthreads();

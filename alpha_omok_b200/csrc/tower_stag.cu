@@ -147,7 +147,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         size_t off = 0;
         for (int l = 0; l < n_layers; ++l, ++lc) {
-          const uint32_t part = (W.xflags & 8) ? 64u : (l == 0 ? kStemTapBytes : kTapBytes);
+          const uint32_t part = AO_XFLAG(W, 8) ? 64u : (l == 0 ? kStemTapBytes : kTapBytes);
           for (int st = 0; st < 9; ++st) {
             mbar_wait(&bar_empty[st], (lc & 1u) ^ 1u);
             if (st == 0) {
@@ -188,8 +188,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;
       constexpr uint32_t kBStep = (2u * kBRows * 16u) >> 4;
       uint32_t lc = 0, act_ph = 0;
-      long long dbg_act_wait = 0, dbg_full_wait = 0;
-      const long long dbg_t0 = W.dbg ? clock64() : 0;
+      AO_DBG(long long dbg_act_wait = 0, dbg_full_wait = 0; const long long dbg_t0 = W.dbg ? clock64() : 0;)
       int g0, ng, ntiles;
       for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         if (stream == 1 && ntiles < kTiles) {  // one-game tail pass: tile 1 holds no board
@@ -209,14 +208,14 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
             const bool no_mma = nk == 1 && grp == 1;  // stem: a single k-step (group 0); only the releases remain
             for (int st = st_lo; st < st_hi; ++st) {
               if (first_use) {
-                const long long t_f0 = W.dbg ? clock64() : 0;
+                AO_DBG(const long long t_f0 = W.dbg ? clock64() : 0;)
                 mbar_wait(&bar_full[st], full_ph);
                 mbar_wait_cluster(&bar_peer_full[st], full_ph);
                 tc_fence_after_sync();
-                if (W.dbg) dbg_full_wait += clock64() - t_f0;
+                AO_DBG(if (W.dbg) dbg_full_wait += clock64() - t_f0;)
               }
               const int t = st == 0 ? 4 : (st <= 4 ? st - 1 : st);  // packed order: centre, 4 negative, 4 positive shifts
-              const int shift = (W.xflags & 1) ? 0 : (t / 3 - 1) * G::S + (t % 3 - 1);
+              const int shift = AO_XFLAG(W, 1) ? 0 : (t / 3 - 1) * G::S + (t % 3 - 1);
               const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + st * kSlotBytes), kBRows * 16u);
               if (elect_one()) {
                 const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
@@ -239,11 +238,11 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
             }
           };
           auto wait_act = [&](const int idx) {  // idx = tile * 2 + column group
-            const long long t_a0 = W.dbg ? clock64() : 0;
+            AO_DBG(const long long t_a0 = W.dbg ? clock64() : 0;)
             mbar_wait_cluster(&bar_act[idx], (act_ph >> idx) & 1u);
             act_ph ^= 1u << idx;
             tc_fence_after_sync();
-            if (W.dbg) dbg_act_wait += clock64() - t_a0;
+            AO_DBG(if (W.dbg) dbg_act_wait += clock64() - t_a0;)
           };
           auto commit_acc = [&](const int tile) {
             if (elect_one()) umma_commit_pair(&bar_acc[tile]);
@@ -278,12 +277,14 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
           }
         }
       }
+#ifdef AO_PROBE
       if (W.dbg && blockIdx.x == 0 && lane == 0 && stream == 0) {
         atomicAdd(&W.dbg[0], (unsigned long long)(clock64() - dbg_t0));
         atomicAdd(&W.dbg[1], (unsigned long long)dbg_act_wait);
         atomicAdd(&W.dbg[2], (unsigned long long)dbg_full_wait);
         atomicAdd(&W.dbg[3], 1ull);
       }
+#endif
     }
   } else if (warp < 8) {
     // =========================================================== epilogue: all 8 warps on one tile at a time
@@ -295,9 +296,8 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
     const int R_in = half * kTileRows + r;
     const int gl_in = R_in / G::A, pos_in = R_in % G::A;
     uint32_t acc_ph0 = 0, acc_ph1 = 0, lc = 0, pass_ph = 0;
-    long long dbg_acc_wait = 0, dbg_heads = 0;
-    const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    const long long dbg_e0 = dbg_on ? clock64() : 0;
+    AO_DBG(long long dbg_acc_wait = 0, dbg_heads = 0; const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+           const long long dbg_e0 = dbg_on ? clock64() : 0;)
     // "this warp's rows of tile t are written": all lanes fence, lane 0 arrives on the LEADER's barrier
     auto arrive_act = [&](const int idx) {  // idx = tile * 2 + column group
       fence_proxy_async_smem();
@@ -345,12 +345,12 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
           const int g_local = R / G::A, pos = R % G::A;
           const bool valid = g_local < G::GPC && g_local < ng;
           const uint32_t row_off = (uint32_t)(G::Halo + R) * 16u;
-          const long long t_w0 = dbg_on ? clock64() : 0;
+          AO_DBG(const long long t_w0 = dbg_on ? clock64() : 0;)
           mbar_wait(&bar_acc[t], t ? acc_ph1 : acc_ph0);
           if (t) acc_ph1 ^= 1u;
           else acc_ph0 ^= 1u;
           tc_fence_after_sync();
-          if (dbg_on) dbg_acc_wait += clock64() - t_w0;
+          AO_DBG(if (dbg_on) dbg_acc_wait += clock64() - t_w0;)
           const uint32_t lane_addr = lane_base + (uint32_t)(t * 256);
           const uint32_t stash_addr = lane_addr + 128u;
           const uint32_t acc_addr = to_b ? stash_addr : lane_addr;
@@ -383,9 +383,9 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
                 pk.z = *reinterpret_cast<uint32_t*>(&h);
                 h = __floats2half2_rn(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
                 pk.w = *reinterpret_cast<uint32_t*>(&h);
-                if (!(W.xflags & 32)) *reinterpret_cast<uint4*>(s_act + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pk;
+                if (!AO_XFLAG(W, 32)) *reinterpret_cast<uint4*>(s_act + (uint32_t)(qd * 4 + cc) * chunk_stride + row_off) = pk;
               }
-              if (to_b && !(W.xflags & 16)) tmem_st32(stash_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
+              if (to_b && !AO_XFLAG(W, 16)) tmem_st32(stash_addr + (uint32_t)(qd * 32), v);  // fp32 block input for the next residual add
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -396,9 +396,9 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
               }
             }
           };
-          if (!(W.xflags & 4) || last) {
+          if (!AO_XFLAG(W, 4) || last) {
             uint32_t va[32], vb[32];
-            if (!(W.xflags & 64) || last) {
+            if (!AO_XFLAG(W, 64) || last) {
               tmem_ld32(acc_addr + (uint32_t)(half * 64), va);
               tmem_ld32(acc_addr + (uint32_t)(half * 64 + 32), vb);
               tmem_ld_wait();
@@ -432,11 +432,13 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       if (lane == 0) mbar_arrive(bar_feat_full);
       pass_ph ^= 1u;
     }
+#ifdef AO_PROBE
     if (dbg_on) {
       atomicAdd(&W.dbg[4], (unsigned long long)(clock64() - dbg_e0));
       atomicAdd(&W.dbg[5], (unsigned long long)dbg_acc_wait);
       atomicAdd(&W.dbg[6], (unsigned long long)dbg_heads);
     }
+#endif
   } else {
     // =========================================================== heads (model.py:43-50, 63-73), one pass behind the tower
     const int ht = tid - 10 * 32, hw = warp - 10;

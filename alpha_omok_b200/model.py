@@ -129,7 +129,7 @@ class PVNet(nn.Module):
                 self._ao_engine.close()
             self._ao_engine = _cabi.Engine(board_size=self.board_size, num_mcts=1, max_games=max(batch, 64),
                                            n_blocks=self.n_block, inplanes=self.inplanes, planes=self.planes,
-                                           node_cap=4)
+                                           node_cap=4, device=_cabi.default_device(self))
             self._ao_fingerprint = None
         if self._ao_fingerprint != fp:
             self._ao_engine.load_state_dict(self.state_dict())

@@ -32,7 +32,7 @@ def device_records(engine, n_games) -> torch.Tensor:
     """Pack the finished games of `engine` and return a uint8 CUDA tensor [n_games, record_bytes] aliasing the slab."""
     engine.records_pack(n_games)
     ptr, bpg = engine.records_dev()
-    t = torch.as_tensor(_DevSlab(ptr, n_games * bpg), device=torch.device("cuda", torch.cuda.current_device()))
+    t = torch.as_tensor(_DevSlab(ptr, n_games * bpg), device=torch.device("cuda", engine.device))
     return t.view(n_games, bpg)
 
 
@@ -40,7 +40,7 @@ def device_stream_records(engine) -> torch.Tensor:
     """uint8 CUDA tensor [n_episodes, record_bytes] aliasing the record slab of a finished continuous self-play run
     (`Engine.selfplay_stream_begin`), episode i = decision-stream key first_key + i."""
     ptr, bpg, n = engine.stream_records_dev()
-    t = torch.as_tensor(_DevSlab(ptr, n * bpg), device=torch.device("cuda", torch.cuda.current_device()))
+    t = torch.as_tensor(_DevSlab(ptr, n * bpg), device=torch.device("cuda", engine.device))
     return t.view(n, bpg)
 
 

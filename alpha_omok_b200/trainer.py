@@ -61,18 +61,42 @@ def train_step(net, optimizer, s_batch, pi_batch, z_batch, group=None):
     return loss.item(), v_loss.item(), p_loss.item()
 
 
-def train_batches(net, optimizer, states, pis, zs, batch_size=32, n_epochs=1, group=None):
+def train_batches(net, optimizer, states, pis, zs, batch_size=32, n_epochs=1, group=None, batch_sizes=None):
     """main.py:253-336 for an already sampled train_memory given as tensors [N,5,B,B], [N,A], [N]:
-    `DataLoader(train_memory, batch_size=BATCH_SIZE, shuffle=False)` = consecutive slices, a short last batch kept."""
+    `DataLoader(train_memory, batch_size=BATCH_SIZE, shuffle=False)` = consecutive slices, a short last batch kept.
+    `batch_sizes` (optional) gives the row count of every consecutive batch explicitly (multi-rank shards)."""
     net.train()
     dev = next(net.parameters()).device
     states, pis, zs = states.to(dev).float(), pis.to(dev).float(), zs.to(dev).float()
+    if batch_sizes is None:
+        n = states.shape[0]
+        batch_sizes = [min(batch_size, n - i) for i in range(0, n, batch_size)]
+    assert sum(batch_sizes) == states.shape[0]
     log = []
     for _ in range(n_epochs):
-        for i in range(0, states.shape[0], batch_size):
-            log.append(train_step(net, optimizer, states[i:i + batch_size], pis[i:i + batch_size],
-                                  zs[i:i + batch_size], group))
+        i = 0
+        for b in batch_sizes:
+            log.append(train_step(net, optimizer, states[i:i + b], pis[i:i + b], zs[i:i + b], group))
+            i += b
     return log
+
+
+def shard_global_batches(n_rows, batch_size, rank, world):
+    """Rows of the sampled train_memory this rank trains on, batch by batch: global batch i = rows
+    [i*BS, (i+1)*BS) exactly as the reference's DataLoader cuts them (main.py:266-269), of which rank r takes every
+    world-th row.  Every rank gets the SAME number of batches (one gradient all-reduce per batch on every rank) and the
+    same number of rows in each of them, which needs BATCH_SIZE % world == 0 and n_rows % world == 0 (callers trim).
+    Returns (row index list, per-batch row counts)."""
+    if batch_size % world != 0:
+        raise ValueError("BATCH_SIZE = %d must be a multiple of the world size %d" % (batch_size, world))
+    if n_rows % world != 0:
+        raise ValueError("sample count %d must be a multiple of the world size %d" % (n_rows, world))
+    rows, sizes = [], []
+    for i in range(0, n_rows, batch_size):
+        mine = list(range(i, min(i + batch_size, n_rows)))[rank::world]
+        rows += mine
+        sizes.append(len(mine))
+    return rows, sizes
 
 
 def model_file(datetime_now, n_iter, step, data_dir="data"):
@@ -196,11 +220,21 @@ class Trainer:
         k = self.BATCH_SIZE * self.rep_memory.cur_len          # BATCH_SIZE * len(cur_memory), main.py:263-264
         if not strict_reference:
             k = min(k, len(self.rep_memory), max_samples if max_samples is not None else k)
+        if self.world > 1:
+            k -= k % self.world                                # every global batch then splits evenly over the ranks
         idx = self.rep_memory.sample_indices(k)                # every rank draws the same indices (same seed) ...
-        idx = idx[self.rank::self.world]                       # ... and trains on its slice of the batches' rows
+        rows, sizes = shard_global_batches(len(idx), self.BATCH_SIZE, self.rank, self.world)
+        idx = [idx[r] for r in rows]                           # ... and trains on its rows of every global batch
+        if self.world > 1:
+            # belt and braces: a rank with a different batch count would dead-lock in the gradient all-reduce
+            cnt = torch.tensor([len(sizes), -len(sizes)],
+                               device=self.device if dist.get_backend(self.group) == "nccl" else "cpu")
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX, group=self.group)
+            if cnt[0].item() != -cnt[1].item():
+                raise RuntimeError("ranks disagree on the number of training batches")
         s, pi, z = self.rep_memory.gather(idx)
-        log = train_batches(self.model, self.optimizer, s, pi, z, max(1, self.BATCH_SIZE // self.world),
-                            n_epochs or self.N_EPOCHS, self.group)
+        log = train_batches(self.model, self.optimizer, s, pi, z, self.BATCH_SIZE // self.world,
+                            n_epochs or self.N_EPOCHS, self.group, batch_sizes=sizes)
         self.step += len(log)
         self.total_epoch += n_epochs or self.N_EPOCHS
         if log:

@@ -105,8 +105,6 @@ int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_p
 /* ao_selfplay_rounds with CUDA events around every launch: summed device milliseconds of the tree-step kernels and of
  * the tower kernels over the `rounds` rounds (bench.py's roofline numbers). rounds <= 4096. */
 int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out8, float* tree_ms, float* tower_ms);
-/* Profiling aid: cycle counters of CTA 0 of the tower kernel (see csrc/engine.cu); enable=1 starts / resets them. */
-int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8);
 /* Switch the tower's operand mode (AO_NN_*) at run time. */
 int ao_set_nn_precision(ao_engine* h, int mode);
 /* Number of kernels this engine has launched so far (bench.py's gpu_launches). */
@@ -151,16 +149,6 @@ int ao_check_win(const int8_t* boards, int n, int board_size, uint8_t* out);
 int ao_encode_state(const int16_t* ids, const int32_t* lens, int n, int board_size, float* out);
 /* utils.legal_actions (utils.py:22-27) incl. the CPython set-order regime: -> int16 [n][A] (-1 padded). */
 int ao_legal_actions(const int16_t* ids, const int32_t* lens, int n, int board_size, int16_t* out);
-/* tcgen05 building-block probe (csrc/umma_probe.cu). */
-int ao_umma_probe(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init, float* out,
-                  int row0, int ntaps, const int* shifts);
-/* same with per-tap disable-output-lane masks [ntaps][4] (bit r set: output row r is not updated by that tap) */
-int ao_umma_probe_masked(const uint16_t* act_f16, int rows, const uint16_t* wpacked_f16, const float* init, float* out,
-                         int row0, int ntaps, const int* shifts, const uint32_t* masks);
-
-/* raw tcgen05.mma throughput probe (csrc/umma_probe.cu): cycles of `iters`*8 back-to-back MMAs of one flavour */
-int ao_umma_rate(int flavour, int iters, unsigned long long* out2);
-
 #ifdef __cplusplus
 }
 #endif

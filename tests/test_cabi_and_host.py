@@ -32,6 +32,22 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
 
 
+def test_product_library_carries_no_probe_code():
+    """experiment switches and probes live in libalpha_omok_b200_probe.so only (include/alpha_omok_b200_probe.h): the
+    product library exports none of the probe entry points and does not even contain the AO_TOWER_XFLAGS string"""
+    from alpha_omok_b200 import _build, _cabi
+    lib = _cabi.lib()
+    for name in _cabi.PROBE_EXPORTS:
+        assert not hasattr(lib, name), name
+    blob = open(_build.LIB_PATH, "rb").read()
+    assert b"AO_TOWER_XFLAGS" not in blob and b"ao_umma" not in blob
+    hdr = open(os.path.join(ROOT, "include", "alpha_omok_b200_probe.h")).read()
+    assert set(re.findall(r"\b(ao_[a-z0-9_]+)\s*\(", hdr)) == set(_cabi.PROBE_EXPORTS)
+    probe = _cabi.probe_lib()      # builds it on demand; exports product + probe symbols
+    for name in _cabi.EXPORTS + _cabi.PROBE_EXPORTS:
+        assert getattr(probe, name) is not None, name
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_gpu():
     from alpha_omok_b200 import _cabi, utils

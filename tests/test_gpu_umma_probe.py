@@ -1,4 +1,4 @@
-"""Hardware facts the tower kernel is built on, checked through the C ABI probe (csrc/umma_probe.cu):
+"""Hardware facts the tower kernel is built on, checked through the C ABI probe (csrc/probe/umma_probe.cu):
 shifted start addresses of the K-major no-swizzle UMMA operand, TMEM-preloaded accumulation, and per-MMA
 disable-output-lane masks (board edges without padding)."""
 import numpy as np
@@ -26,7 +26,7 @@ def _run(lib, act, W, init, row0, shifts, masks=None):
 @pytest.mark.parametrize("stride,use_init", [(10, False), (10, True), (16, True), (9, True)])
 def test_shifted_operand_conv(stride, use_init):
     from alpha_omok_b200 import _cabi
-    lib = _cabi.lib()
+    lib = _cabi.probe_lib()
     rng = np.random.default_rng(stride)
     rows, row0 = 300, 24
     shifts = [dy * stride + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
@@ -42,7 +42,7 @@ def test_shifted_operand_conv(stride, use_init):
 
 def test_disable_output_lane_masks_replace_padding():
     from alpha_omok_b200 import _cabi
-    lib = _cabi.lib()
+    lib = _cabi.probe_lib()
     rng = np.random.default_rng(1)
     B, rows, row0 = 9, 160, 16
     taps = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]

@@ -162,3 +162,24 @@ def test_seeded_weight_generator_matches_the_oracles():
         assert list(a.keys()) == list(b.keys())
         for k in a:
             assert a[k].dtype == torch.float32 and torch.equal(a[k], b[k]), k
+
+
+def test_global_batch_sharding_gives_every_rank_the_same_batches():
+    """rows of every global batch of 32 are dealt round-robin to the ranks, so all ranks run the same number
+    of optimizer steps (one gradient all-reduce each) with equal row counts - also for a short last batch"""
+    from alpha_omok_b200 import trainer
+    for n, world in ((64, 2), (34, 2), (96, 4), (40, 8), (8, 8)):
+        shards = [trainer.shard_global_batches(n, 32, r, world) for r in range(world)]
+        sizes = [tuple(s) for _, s in shards]
+        assert len(set(sizes)) == 1, (n, world, sizes)                       # same batches, same row counts
+        assert sum(sizes[0]) * world == n
+        allrows = sorted(r for rows, _ in shards for r in rows)
+        assert allrows == list(range(n))                                    # every sampled row trained exactly once
+        for b, cnt in enumerate(sizes[0]):                                  # batch b holds rows of global batch b only
+            for rows, s in shards:
+                off = sum(s[:b])
+                assert all(b * 32 <= r < (b + 1) * 32 for r in rows[off:off + cnt])
+    with pytest.raises(ValueError):
+        trainer.shard_global_batches(64, 32, 0, 3)
+    with pytest.raises(ValueError):
+        trainer.shard_global_batches(33, 32, 0, 2)

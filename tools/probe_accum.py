@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _build
 from tools.probe_umma import pack_w
-lib = ctypes.CDLL(_build.build())
+lib = ctypes.CDLL(_build.build(probe=True))
 lib.ao_umma_probe.restype = ctypes.c_int
 lib.ao_umma_probe.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 rng = np.random.default_rng(0)

@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _cabi
 from tools.probe_umma import pack_w
-lib = _cabi.lib()
+lib = _cabi.probe_lib()
 rng = np.random.default_rng(1)
 B = 9
 rows, row0 = 16 + 128 + 16, 16

@@ -3,7 +3,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _cabi
 from tools.probe_umma import pack_w
-lib = _cabi.lib()
+lib = _cabi.probe_lib()
 rng = np.random.default_rng(1)
 rows, row0 = 160, 16
 for name, nt, maskfn in (("zero-masks 1 tap", 1, lambda t, r: 0), ("zero-masks 9 taps", 9, lambda t, r: 0),

@@ -1,8 +1,8 @@
-"""Raw tcgen05.mma issue rate of the tower's MMA flavours (csrc/umma_probe.cu: ao_umma_rate)."""
+"""Raw tcgen05.mma issue rate of the tower's MMA flavours (csrc/probe/umma_probe.cu: ao_umma_rate)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _cabi
-L = _cabi.lib()
+L = _cabi.probe_lib()
 L.ao_umma_rate.argtypes = [C.c_int, C.c_int, C.c_void_p]
 L.ao_umma_rate.restype = C.c_int
 names = {0: "cta_group::1 M128 unmasked", 1: "cta_group::1 M128 masked", 2: "cta_group::2 M256 unmasked", 3: "cta_group::2 M256 masked"}

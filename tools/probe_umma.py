@@ -1,4 +1,4 @@
-"""Hardware probe for the shifted no-swizzle UMMA operand trick (see csrc/umma_probe.cu).
+"""Hardware probe for the shifted no-swizzle UMMA operand trick (see csrc/probe/umma_probe.cu).
 
 Run on the GPU box:  python tools/probe_umma.py   (prints one line per case, exit 1 on mismatch)
 """
@@ -41,7 +41,7 @@ def run_case(lib, name, rows, row0, shifts, use_init, rng):
 
 
 def main():
-    lib = ctypes.CDLL(_build.build())
+    lib = ctypes.CDLL(_build.build(probe=True))
     lib.ao_umma_probe.restype = ctypes.c_int
     lib.ao_umma_probe.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
