@@ -32,6 +32,7 @@ EXPORTS = [  # every symbol include/alpha_omok_b200.h declares (checked by tests
     "ao_launch_count", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev",
     "ao_records_pack", "ao_augment_records_dev", "ao_replay_extend_dev", "ao_replay_gather_dev", "ao_synchronize",
     "ao_check_win", "ao_encode_state", "ao_legal_actions",
+    "ao_load_weights_set", "ao_nn_forward_set", "ao_set_nn_precision_set", "ao_arena_begin",
 ]
 PROBE_EXPORTS = ["ao_tower_debug", "ao_umma_probe", "ao_umma_probe_masked", "ao_umma_rate"]  # alpha_omok_b200_probe.h
 
@@ -48,6 +49,10 @@ def _bind(L):
     L.ao_engine_create.argtypes = [C.POINTER(AoConfig), C.POINTER(vp)]
     L.ao_engine_destroy.argtypes = [vp]
     L.ao_load_weights.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.ao_load_weights_set.argtypes = [vp, i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.ao_nn_forward_set.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.ao_set_nn_precision_set.argtypes = [vp, i32, i32]
+    L.ao_arena_begin.argtypes = [vp, i32, u32, i32, i32, i32, i32, i32]
     L.ao_games_reset.argtypes = [vp, vp, i32, vp]
     L.ao_set_gamma_tape.argtypes = [vp, i32, vp, i32]
     L.ao_search.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
@@ -164,7 +169,7 @@ class Engine:
         self.B, self.A, self.G = board_size, board_size * board_size, max_games
         self.num_mcts = num_mcts
         self.device = int(device)
-        self.nn_precision = nn_precision
+        self.nn_precision = self.nn_precision_enemy = nn_precision
         cfg = AoConfig(device, board_size, inplanes, planes, n_blocks, num_mcts, int(bool(noise)), tau_thres,
                        max_games, node_cap, eval_mode, noise_mode, nn_precision, nn_log_cap, float(c_puct),
                        float(alpha), seed, stream)
@@ -180,8 +185,9 @@ class Engine:
 
     __del__ = close
 
-    def load_state_dict(self, state_dict):
-        """fp32 tensors straight from nn.Module.state_dict() (BN folded inside the library)."""
+    def load_state_dict(self, state_dict, which=0):
+        """fp32 tensors straight from nn.Module.state_dict() (BN folded inside the library).
+        which = 1 fills the second weight set (the arena's enemy, eval_main.py:87-101)."""
         names, arrs = [], []
         for k, v in state_dict.items():
             if k.endswith("num_batches_tracked"):
@@ -193,13 +199,16 @@ class Engine:
         c_names = (C.c_char_p * n)(*names)
         c_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
         c_numel = (C.c_int64 * n)(*[a.size for a in arrs])
-        check(lib().ao_load_weights(self._h, n, c_names, c_ptrs, c_numel))
+        check(lib().ao_load_weights_set(self._h, which, n, c_names, c_ptrs, c_numel))
 
-    def set_nn_precision(self, mode):
-        check(lib().ao_set_nn_precision(self._h, mode))
-        self.nn_precision = mode
+    def set_nn_precision(self, mode, which=0):
+        check(lib().ao_set_nn_precision_set(self._h, which, mode))
+        if which == 0:
+            self.nn_precision = mode
+        else:
+            self.nn_precision_enemy = mode
 
-    def choose_nn_precision(self, tol=5e-5, n_probe=48, seed=0):
+    def choose_nn_precision(self, tol=5e-5, n_probe=48, seed=0, which=0):
         """Pick the cheapest tower mode whose outputs agree with the hi/lo-split mode within `tol` on a set of probe
         positions (the split mode is within 1e-4 of fp32 even on trained nets). Random-init nets stay on
         the single-pass fp16 mode; trained nets switch to AO_NN_FP16X3."""
@@ -217,14 +226,14 @@ class Engine:
             if len(opp):
                 states[i, 1].flat[opp[-1]] = 0
             states[i, 4] = 1.0 if k % 2 == 0 else 0.0
-        self.set_nn_precision(AO_NN_FP16X3)
-        p3, v3 = self.nn_forward(states)
-        self.set_nn_precision(AO_NN_FP16)
-        p1, v1 = self.nn_forward(states)
+        self.set_nn_precision(AO_NN_FP16X3, which)
+        p3, v3 = self.nn_forward(states, which)
+        self.set_nn_precision(AO_NN_FP16, which)
+        p1, v1 = self.nn_forward(states, which)
         err = max(float(np.abs(p1 - p3).max()), float(np.abs(v1 - v3).max()))
         if err > tol:
-            self.set_nn_precision(AO_NN_FP16X3)
-        return self.nn_precision
+            self.set_nn_precision(AO_NN_FP16X3, which)
+        return self.nn_precision if which == 0 else self.nn_precision_enemy
 
     def games_reset(self, game_ids, keys=None):
         ids = np.ascontiguousarray(game_ids, np.int32)
@@ -250,13 +259,19 @@ class Engine:
     def search_raw(self, ids, roots, lens, visits, priors=None, real=None):
         check(lib().ao_search(self._h, ptr(ids), len(ids), ptr(roots), ptr(lens), ptr(visits), ptr(priors), ptr(real)))
 
-    def nn_forward(self, states):
+    def nn_forward(self, states, which=0):
         s = np.ascontiguousarray(states, np.float32)
         n = s.shape[0]
         p = np.empty((n, self.A), np.float32)
         v = np.empty(n, np.float32)
-        check(lib().ao_nn_forward(self._h, ptr(s), n, ptr(p), ptr(v)))
+        check(lib().ao_nn_forward_set(self._h, which, ptr(s), n, ptr(p), ptr(v)))
         return p, v
+
+    def arena_begin(self, n_slots, first_key=0, matches_per_slot=1, enemy_random=False, keep_records=True,
+                    n_mcts_player=0, n_mcts_enemy=0):
+        """eval_main.main's match loop on the device (ao_arena_begin); drive with selfplay_rounds()"""
+        check(lib().ao_arena_begin(self._h, n_slots, first_key, matches_per_slot, int(bool(enemy_random)),
+                                   int(bool(keep_records)), n_mcts_player, n_mcts_enemy))
 
     def selfplay_begin(self, n_games, first_key=0, recycle=False):
         check(lib().ao_selfplay_begin_mode(self._h, n_games, first_key, int(recycle)))

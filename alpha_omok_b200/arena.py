@@ -1,6 +1,7 @@
 """Batched arena: many concurrent matches between two agents, the B200 twin of eval_main.main's match loop
-(eval_main.py:204-333; `Evaluator.get_action` :153-170).  Each side owns its own search trees (one engine slot per
-match), ZeroAgents search with noise=False and tau=0 and pick `utils.argmax_onehot(pi)`, colours alternate by match
+(eval_main.py:204-333; `Evaluator.get_action` :153-170), played entirely on the device (csrc/tree.cu arena_move).
+Each side owns its own search tree (one engine slot per side and match) and its own network (two weight sets in one
+engine), ZeroAgents search with noise=False and tau=0 and pick `utils.argmax_onehot(pi)`, colours alternate by match
 parity (eval_main.py:233,316).  `elo` / `elo_sequence` restate the reference's rating update (eval_main.py:191-198,
 285-312); the web dashboard feed stays out of scope."""
 from __future__ import annotations
@@ -39,57 +40,93 @@ def elo_sequence(outcomes, player_elo=1500, enemy_elo=1500):
     return player_elo, enemy_elo, result, winrate
 
 
+def _n_blocks(model):
+    return getattr(model, "n_block", None) or len({k.split(".")[1] for k in model.state_dict() if k.startswith("layers.")})
+
+
+def decode_match_records(slab, board_size):
+    """uint8 [n, record_bytes] (ao_arena_begin's record slab) -> list of dict(moves, visits [plies][A], winner,
+    player_black, outcome 'player' | 'enemy' | 'draw' | None while unfinished)."""
+    A = board_size * board_size
+    buf = slab.cpu().numpy() if hasattr(slab, "cpu") else np.asarray(slab)
+    voff = (4 + 2 * A + 3) & ~3
+    out = []
+    for rec in buf:
+        k = int(rec[:2].view(np.int16)[0])
+        w, pb = int(rec[2]), bool(rec[3])
+        moves = [int(a) for a in rec[4:4 + 2 * A].view(np.int16)[:k]]
+        visits = rec[voff:voff + 4 * A * A].view(np.uint32).reshape(A, A)[:k].copy()
+        outcome = None if w == 0 else "draw" if w == 3 else ("player" if (w == 1) == pb else "enemy")
+        out.append(dict(moves=moves, visits=visits, winner=w, player_black=pb, outcome=outcome))
+    return out
+
+
 def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, num_mcts=800, inplanes=5, seed=0,
-                 enemy="zero", max_plies=None):
-    """player: ZeroAgent(player_model). enemy: 'zero' -> ZeroAgent(enemy_model), 'random' -> RandomAgent.
-    Returns dict(player_win, enemy_win, draw, black_win, white_win, plies)."""
-    B, A = board_size, board_size * board_size
-    sides = {}
-    sides["player"] = agents.BatchedZeroAgent(B, num_mcts, inplanes, n_matches, noise=False, seed=seed)
-    sides["player"].model = player_model
-    if enemy == "zero":
-        sides["enemy"] = agents.BatchedZeroAgent(B, num_mcts, inplanes, n_matches, noise=False, seed=seed + 1)
-        sides["enemy"].model = enemy_model
-    roots = [(0,) for _ in range(n_matches)]
-    boards = np.zeros((n_matches, A), np.int8)
-    winner = np.zeros(n_matches, np.int32)  # 0 running
-    player_is_black = (np.arange(n_matches) % 2) == 0
-    ply = 0
-    while (winner == 0).any() and (max_plies is None or ply < max_plies):
-        black_to_move = ply % 2 == 0
-        active = np.flatnonzero(winner == 0)
-        for name in ("player", "enemy"):
-            mine = active[(player_is_black[active] == black_to_move) == (name == "player")]
-            if len(mine) == 0:
-                continue
-            if name == "enemy" and enemy == "random":
-                acts = []
-                for m in mine:  # RandomAgent.get_pi + argmax_onehot (agents.py:637-657, eval_main.py:166-168)
-                    empty = (boards[m] == 0).astype("float")
-                    acts.append(int(utils.argmax_onehot(empty / empty.sum())[1]))
+                 enemy="zero", matches_per_slot=1, first_key=0, num_mcts_enemy=None, nn_precision="auto",
+                 rounds_per_call=256, max_rounds=None, engine_kwargs=None, return_records=False):
+    """`n_matches` concurrent runs of eval_main.main's match loop (eval_main.py:204-333), each `matches_per_slot`
+    matches long, entirely on the device (ao_arena_begin): the match loop, both sides' trees and both networks live in
+    one engine, the two towers run back to back every round.
+    player: ZeroAgent(player_model). enemy: 'zero' -> ZeroAgent(enemy_model), 'random' -> RandomAgent.
+    `player_model` / `enemy_model`: nn.Module with the reference's parameter names, or a state_dict (then pass
+    engine_kwargs=dict(n_blocks=...) if it is not a 10-block net).
+    Returns dict(player_win, enemy_win, draw, black_win, white_win, plies, unfinished, player_elo, enemy_elo, winrate
+    [, records])."""
+    B = board_size
+    kw = dict(engine_kwargs or {})
+
+    def sd_of(m):
+        return m if isinstance(m, dict) else m.state_dict()
+
+    if "n_blocks" not in kw and not isinstance(player_model, dict):
+        kw["n_blocks"] = _n_blocks(player_model)
+    kw.setdefault("device", _cabi.default_device(None if isinstance(player_model, dict) else player_model))
+    eng = _cabi.Engine(board_size=B, num_mcts=num_mcts, max_games=2 * n_matches, noise=False, inplanes=inplanes,
+                       seed=seed, **kw)
+    try:
+        if kw.get("eval_mode", _cabi.AO_EVAL_PVNET) == _cabi.AO_EVAL_PVNET:
+            eng.load_state_dict(sd_of(player_model), which=0)
+            if nn_precision == "auto":
+                eng.choose_nn_precision(which=0)
             else:
-                pis = sides[name].get_pi([roots[m] for m in mine], 0, game_ids=mine)
-                acts = [int(np.argmax(pi)) for pi in pis]  # pi is already the tie-broken one-hot
-            for m, a in zip(mine, acts):
-                roots[m] = roots[m] + (a,)
-                boards[m, a] = 1 if black_to_move else -1
-        w = _cabi.check_win_batch(boards[active], B)
-        winner[active] = w
-        ply += 1
-    res = dict(player_win=0, enemy_win=0, draw=0, black_win=int((winner == 1).sum()), white_win=int((winner == 2).sum()),
-               plies=[len(r) - 1 for r in roots], unfinished=int((winner == 0).sum()))
+                eng.set_nn_precision(nn_precision, which=0)
+            if enemy == "zero":
+                eng.load_state_dict(sd_of(enemy_model), which=1)
+                if nn_precision == "auto":
+                    eng.choose_nn_precision(which=1)
+                else:
+                    eng.set_nn_precision(nn_precision, which=1)
+        eng.arena_begin(n_matches, first_key=first_key, matches_per_slot=matches_per_slot,
+                        enemy_random=(enemy == "random"), keep_records=True, n_mcts_player=num_mcts,
+                        n_mcts_enemy=num_mcts_enemy or num_mcts)
+        st = eng.selfplay_rounds(rounds_per_call)
+        rounds = rounds_per_call
+        while st["running"] and (max_rounds is None or rounds < max_rounds):
+            st = eng.selfplay_rounds(rounds_per_call)
+            rounds += rounds_per_call
+        if st["errors"]:
+            raise _cabi.AoError("%d match tree(s) overflowed their arena; raise node_cap" % st["errors"])
+        from . import replay
+        recs = decode_match_records(replay.device_stream_records(eng), B)
+        precisions = (eng.nn_precision, eng.nn_precision_enemy)
+    finally:
+        eng.close()
+    res = dict(player_win=0, enemy_win=0, draw=0, black_win=0, white_win=0, plies=[len(r["moves"]) for r in recs],
+               unfinished=0, sims=st["sims"], nn_precision=precisions)
     outcomes = []
-    for m in range(n_matches):
-        if winner[m] == 3:
-            res["draw"] += 1
-            outcomes.append("draw")
-        elif winner[m] in (1, 2):
-            black_won = winner[m] == 1
-            mine = black_won == bool(player_is_black[m])
-            res["player_win" if mine else "enemy_win"] += 1
-            outcomes.append("player" if mine else "enemy")
-    # the reference plays the matches one after the other and updates the ratings after each (eval_main.py:285-312)
+    for r in recs:
+        if r["outcome"] is None:
+            res["unfinished"] += 1
+            continue
+        res["black_win"] += r["winner"] == 1
+        res["white_win"] += r["winner"] == 2
+        res[{"player": "player_win", "enemy": "enemy_win", "draw": "draw"}[r["outcome"]]] += 1
+        outcomes.append(r["outcome"])
+    # the reference plays its matches one after the other and updates the ratings after each (eval_main.py:285-312);
+    # here: in record order (slot-major)
     res["player_elo"], res["enemy_elo"], _, res["winrate"] = elo_sequence(outcomes)
+    if return_records:
+        res["records"] = recs
     return res
 
 
@@ -102,7 +139,8 @@ class Evaluator(object):
     name agents that are out of this repository's scope and raise NotImplementedError."""
 
     def __init__(self, board_size=9, n_mcts_player=800, n_mcts_enemy=800, n_mcts_monitor=800, n_blocks=10,
-                 in_planes=5, out_planes=128):
+                 in_planes=5, out_planes=128, engine_kwargs=None):
+        self.engine_kwargs = dict(engine_kwargs or {})
         self.board_size = board_size
         self.n_mcts = {"player": n_mcts_player, "enemy": n_mcts_enemy, "monitor": n_mcts_monitor}
         self.n_blocks, self.in_planes, self.out_planes = n_blocks, in_planes, out_planes
@@ -116,7 +154,8 @@ class Evaluator(object):
             return agents.RandomAgent(self.board_size)
         if path in ("puct", "uct", "human", "web"):
             raise NotImplementedError("agent '%s' (rollout / interactive) is outside the accelerated path" % path)
-        agent = agents.ZeroAgent(self.board_size, self.n_mcts[role], self.in_planes, noise=False)
+        agent = agents.ZeroAgent(self.board_size, self.n_mcts[role], self.in_planes, noise=False,
+                                 engine_kwargs=self.engine_kwargs)
         agent.model = model.PVNet(self.n_blocks, self.in_planes, self.out_planes, self.board_size)
         state = agent.model.state_dict()
         loaded = path if isinstance(path, dict) else torch.load(path, map_location="cpu")

@@ -62,12 +62,15 @@ struct ao_engine {
   bool own_stream;
   cudaStream_t stream;
   ao::TreeParams tp;
-  ao::TowerWeights tw;
-  bool weights_loaded;
+  // two weight sets: 0 = Agent.model (self-play, facades, the arena's player), 1 = the arena's enemy (eval_main.py:87-101)
+  struct WeightSet {
+    ao::TowerWeights tw;
+    bool loaded;
+    int precision;  // AO_NN_*
+    __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo;
+    float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
+  } ws[2];
   std::vector<void*> allocs;
-  // weights (device)
-  __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo;
-  float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
   // staging
   int32_t *d_ids, *d_lens, *d_real_root;
   int16_t* d_roots;
@@ -87,8 +90,9 @@ struct ao_engine {
   // changes; ao_selfplay_rounds replays it instead of issuing 4 stream operations per round
   cudaGraphExec_t round_graph;
   ao::TreeParams graph_tp;
-  ao::TowerWeights graph_tw;
-  int graph_n, graph_max_iters, graph_precision;
+  ao::TowerWeights graph_tw[2];
+  int graph_n, graph_max_iters, graph_precision[2];
+  unsigned long long graph_launches_per_round;
   bool graph_disabled;
   // optional per-kernel timing (bench roofline): event pairs recorded around every launch of a timed call
   bool timing;
@@ -112,16 +116,24 @@ int ealloc(ao_engine* h, T** p, size_t count) {
 
 // one lock-step round: tree step (consume NN output, select next leaf) then the tower on the emitted requests
 int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int timed_slot = -1) {
-  AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, sizeof(int32_t), h->stream));
+  AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, 2 * sizeof(int32_t), h->stream));
   AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
   if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 0], h->stream));
   AO_CUDA(ao::launch_tree_step(h->tp, ids_dev, n, max_iters, h->stream));
   if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 1], h->stream));
   h->launches += 1;
   if (h->cfg.eval_mode == AO_EVAL_PVNET) {
-    AO_CUDA(ao::launch_tower(h->tw, h->B, h->cfg.nn_precision, h->tp.nn_in, h->tp.nn_count, n, h->tp.nn_policy,
-                             h->tp.nn_value, h->num_sms, h->stream));
-    h->launches += 1;
+    const int M = h->tp.arena_M;
+    if (!(M > 0 && h->tp.arena_random[0])) {
+      AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, h->tp.nn_count, n, h->tp.nn_policy,
+                               h->tp.nn_value, h->num_sms, h->stream));
+      h->launches += 1;
+    }
+    if (M > 0 && !h->tp.arena_random[1]) {  // the enemy's requests: nn slots [M, 2M), weight set 1
+      AO_CUDA(ao::launch_tower(h->ws[1].tw, h->B, h->ws[1].precision, h->tp.nn_in + M, h->tp.nn_count + 1, n,
+                               h->tp.nn_policy + (size_t)M * h->A, h->tp.nn_value + M, h->num_sms, h->stream));
+      h->launches += 1;
+    }
   }
   if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 2], h->stream));
   return 0;
@@ -136,16 +148,19 @@ int run_rounds(ao_engine* h, int n, int max_iters, int rounds) {
   int done = 0;
   const bool graphable = !h->graph_disabled && rounds >= 2 * kGraphRounds;
   if (graphable) {
-    const bool stale = h->round_graph == nullptr || h->graph_n != n || h->graph_max_iters != max_iters ||
-                       h->graph_precision != h->cfg.nn_precision || memcmp(&h->graph_tp, &h->tp, sizeof h->tp) != 0 ||
-                       memcmp(&h->graph_tw, &h->tw, sizeof h->tw) != 0;
+    bool stale = h->round_graph == nullptr || h->graph_n != n || h->graph_max_iters != max_iters ||
+                 memcmp(&h->graph_tp, &h->tp, sizeof h->tp) != 0;
+    for (int k = 0; k < 2; ++k)
+      stale = stale || h->graph_precision[k] != h->ws[k].precision || memcmp(&h->graph_tw[k], &h->ws[k].tw, sizeof(ao::TowerWeights)) != 0;
     if (stale) {
       if (h->round_graph) cudaGraphExecDestroy(h->round_graph);
       h->round_graph = nullptr;
       // one direct round first: per-kernel attributes (dynamic smem opt-in) are set outside the capture
+      const unsigned long long launches_before_direct = h->launches;
       if ((rc = run_round(h, nullptr, n, max_iters)) != 0) return rc;
       ++done;
       cudaGraph_t graph = nullptr;
+      h->graph_launches_per_round = h->launches - launches_before_direct;
       const unsigned long long launches0 = h->launches;
       cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
       if (e == cudaSuccess) {
@@ -161,21 +176,32 @@ int run_rounds(ao_engine* h, int n, int max_iters, int rounds) {
         h->graph_disabled = true;
       } else {
         memcpy(&h->graph_tp, &h->tp, sizeof h->tp);
-        memcpy(&h->graph_tw, &h->tw, sizeof h->tw);
+        for (int k = 0; k < 2; ++k) {
+          memcpy(&h->graph_tw[k], &h->ws[k].tw, sizeof(ao::TowerWeights));
+          h->graph_precision[k] = h->ws[k].precision;
+        }
         h->graph_n = n;
         h->graph_max_iters = max_iters;
-        h->graph_precision = h->cfg.nn_precision;
       }
     }
     while (h->round_graph && rounds - done >= kGraphRounds) {
       AO_CUDA(cudaGraphLaunch(h->round_graph, h->stream));
-      h->launches += (h->cfg.eval_mode == AO_EVAL_PVNET ? 2ull : 1ull) * kGraphRounds;
+      h->launches += h->graph_launches_per_round * kGraphRounds;
       done += kGraphRounds;
     }
   }
   for (; done < rounds; ++done)
     if ((rc = run_round(h, nullptr, n, max_iters)) != 0) return rc;
   return 0;
+}
+
+// totals over the running self-play games, or over both sides of the running arena matches (running = matches)
+cudaError_t launch_sum_selfplay(ao_engine* h) {
+  const int M = h->tp.arena_M;
+  if (M > 0) {  // sides live in slots [0, n) and [M, M + n): sum over [0, M + n), count running matches in [0, n)
+    return ao::launch_sum_counters(h->tp, M + h->selfplay_games, h->selfplay_games, h->d_counters, h->stream);
+  }
+  return ao::launch_sum_counters(h->tp, h->selfplay_games, h->selfplay_games, h->d_counters, h->stream);
 }
 
 int poll_active(ao_engine* h, int* active) {
@@ -185,9 +211,10 @@ int poll_active(ao_engine* h, int* active) {
   return 0;
 }
 
-int require_weights(ao_engine* h) {
-  if (h->cfg.eval_mode == AO_EVAL_PVNET && !h->weights_loaded)
-    return fail(-3, "no weights loaded: call ao_load_weights before searching with the PVNet evaluator");
+int require_weights(ao_engine* h, int set = 0) {
+  if (h->cfg.eval_mode == AO_EVAL_PVNET && !h->ws[set].loaded)
+    return fail(-3, "no weights loaded%s: call ao_load_weights%s before searching with the PVNet evaluator",
+                set ? " for weight set 1 (the arena's enemy)" : "", set ? "_set" : "");
   return 0;
 }
 
@@ -218,13 +245,13 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
 
   ao_engine* h = new ao_engine();
   memset(&h->tp, 0, sizeof h->tp);
-  memset(&h->tw, 0, sizeof h->tw);
+  memset(h->ws, 0, sizeof h->ws);
+  h->ws[0].precision = h->ws[1].precision = cfg->nn_precision;
   h->cfg = *cfg;
   h->B = cfg->board_size;
   h->A = h->B * h->B;
   h->G = cfg->max_games;
   h->num_sms = prop.multiProcessorCount;
-  h->weights_loaded = false;
   h->selfplay_games = 0;
   h->d_stream = nullptr; h->stream_capacity = 0; h->d_stream_next = nullptr; h->stream_episodes = 0;
   h->round_graph = nullptr; h->graph_n = -1; h->graph_disabled = getenv("AO_NO_GRAPH") != nullptr;
@@ -271,7 +298,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   EA(tp.nn_in, (size_t)G);
   EA(tp.nn_policy, (size_t)G * A);
   EA(tp.nn_value, (size_t)G);
-  EA(tp.nn_count, 1);
+  EA(tp.nn_count, 2);
   EA(tp.n_active, 1);
   if (tp.nn_log_cap > 0) {
     EA(tp.nnlog_policy, (size_t)G * tp.nn_log_cap * A);
@@ -321,8 +348,15 @@ extern "C" int ao_synchronize(ao_engine* h) {
 // ---------------------------------------------------------------------------------------------------- weights
 extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* names, const float* const* ptrs,
                                const int64_t* numel) {
+  return ao_load_weights_set(h, 0, n_tensors, names, ptrs, numel);
+}
+
+extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const char* const* names,
+                                   const float* const* ptrs, const int64_t* numel) {
   if (!h) return fail(-1, "null engine");
+  if (set < 0 || set > 1) return fail(-1, "weight set %d out of range 0..1", set);
   DeviceGuard guard(h->cfg.device);
+  ao_engine::WeightSet* W = &h->ws[set];
   std::map<std::string, std::pair<const float*, int64_t>> sd;
   for (int i = 0; i < n_tensors; ++i) sd[names[i]] = {ptrs[i], numel[i]};
   const int A = h->A, C = 128, nb = h->cfg.n_blocks, CI = h->cfg.inplanes;
@@ -404,45 +438,45 @@ extern "C" int ao_load_weights(ao_engine* h, int n_tensors, const char* const* n
   for (int j = 0; j < C; ++j)
     for (int p = 0; p < A; ++p) vfc1_wT[(size_t)p * C + j] = v1w[(size_t)j * A + p];
 
-  if (!h->weights_loaded) {
+  if (!W->loaded) {
     int rc;
 #define EA(p, cnt) if ((rc = ealloc(h, &(p), (cnt))) != 0) return rc;
-    EA(h->d_conv_hi, total_halves);
-    EA(h->d_conv_lo, total_halves);
-    EA(h->d_conv_pair, total_halves);
-    EA(h->d_conv_pair_lo, total_halves);
-    EA(h->d_bias, bias.size());
-    EA(h->d_head_w, head_w.size());
-    EA(h->d_head_b, 4);
-    EA(h->d_pfc_wT, pfc_wT.size());
-    EA(h->d_pfc_b, (size_t)A);
-    EA(h->d_vfc1_wT, vfc1_wT.size());
-    EA(h->d_vfc1_b, (size_t)C);
-    EA(h->d_vfc2_w, (size_t)C);
+    EA(W->d_conv_hi, total_halves);
+    EA(W->d_conv_lo, total_halves);
+    EA(W->d_conv_pair, total_halves);
+    EA(W->d_conv_pair_lo, total_halves);
+    EA(W->d_bias, bias.size());
+    EA(W->d_head_w, head_w.size());
+    EA(W->d_head_b, 4);
+    EA(W->d_pfc_wT, pfc_wT.size());
+    EA(W->d_pfc_b, (size_t)A);
+    EA(W->d_vfc1_wT, vfc1_wT.size());
+    EA(W->d_vfc1_b, (size_t)C);
+    EA(W->d_vfc2_w, (size_t)C);
 #undef EA
   }
   AO_CUDA(cudaStreamSynchronize(h->stream));
-  AO_CUDA(cudaMemcpy(h->d_conv_hi, hi.data(), total_halves * 2, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_conv_lo, lo.data(), total_halves * 2, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_conv_pair, pr.data(), total_halves * 2, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_conv_pair_lo, prl.data(), total_halves * 2, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_pfc_wT, pfc_wT.data(), pfc_wT.size() * 4, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_pfc_b, pfc_b, (size_t)A * 4, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_vfc1_wT, vfc1_wT.data(), vfc1_wT.size() * 4, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_vfc1_b, v1b, (size_t)C * 4, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(h->d_vfc2_w, v2w, (size_t)C * 4, cudaMemcpyHostToDevice));
-  ao::TowerWeights& tw = h->tw;
+  AO_CUDA(cudaMemcpy(W->d_conv_hi, hi.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_conv_lo, lo.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_conv_pair, pr.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_conv_pair_lo, prl.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_pfc_wT, pfc_wT.data(), pfc_wT.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_pfc_b, pfc_b, (size_t)A * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_vfc1_wT, vfc1_wT.data(), vfc1_wT.size() * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_vfc1_b, v1b, (size_t)C * 4, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_vfc2_w, v2w, (size_t)C * 4, cudaMemcpyHostToDevice));
+  ao::TowerWeights& tw = W->tw;
 #ifdef AO_PROBE
   tw.xflags = getenv("AO_TOWER_XFLAGS") ? atoi(getenv("AO_TOWER_XFLAGS")) : 0;
 #endif
-  tw.conv_hi = h->d_conv_hi; tw.conv_lo = h->d_conv_lo; tw.conv_pair = h->d_conv_pair; tw.conv_pair_lo = h->d_conv_pair_lo; tw.bias = h->d_bias; tw.head_w = h->d_head_w; tw.head_b = h->d_head_b;
-  tw.pfc_wT = h->d_pfc_wT; tw.pfc_b = h->d_pfc_b; tw.vfc1_wT = h->d_vfc1_wT; tw.vfc1_b = h->d_vfc1_b; tw.vfc2_w = h->d_vfc2_w;
+  tw.conv_hi = W->d_conv_hi; tw.conv_lo = W->d_conv_lo; tw.conv_pair = W->d_conv_pair; tw.conv_pair_lo = W->d_conv_pair_lo; tw.bias = W->d_bias; tw.head_w = W->d_head_w; tw.head_b = W->d_head_b;
+  tw.pfc_wT = W->d_pfc_wT; tw.pfc_b = W->d_pfc_b; tw.vfc1_wT = W->d_vfc1_wT; tw.vfc1_b = W->d_vfc1_b; tw.vfc2_w = W->d_vfc2_w;
   tw.vfc2_b = v2b[0];
   tw.n_layers = n_layers;
-  h->weights_loaded = true;
+  W->loaded = true;
   return 0;
 }
 
@@ -453,6 +487,7 @@ extern "C" int ao_games_reset(ao_engine* h, const int32_t* game_ids, int n, cons
   if (n < 0 || n > h->G) return fail(-1, "n out of range");
   for (int i = 0; i < n; ++i)
     if (game_ids[i] < 0 || game_ids[i] >= h->G) return fail(-1, "game id %d out of range", game_ids[i]);
+  h->tp.arena_M = 0;
   AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   if (game_keys) AO_CUDA(cudaMemcpyAsync(h->d_keys, game_keys, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(ao::launch_reset_games(h->tp, h->d_ids, n, game_keys ? h->d_keys : nullptr, 0, h->stream));
@@ -486,6 +521,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
     seen[game_ids[i]] = 1;
     if (root_lens[i] < 1 || root_lens[i] > A) return fail(-1, "root id length %d out of range 1..%d", root_lens[i], A);
   }
+  h->tp.arena_M = 0;
   AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(cudaMemcpyAsync(h->d_lens, root_lens, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(cudaMemcpyAsync(h->d_roots, roots, (size_t)n * (A + 1) * 2, cudaMemcpyHostToDevice, h->stream));
@@ -505,7 +541,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
   if (visits) AO_CUDA(cudaMemcpyAsync(visits, h->d_visits, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
   if (priors) AO_CUDA(cudaMemcpyAsync(priors, h->d_priors, (size_t)n * A * 8, cudaMemcpyDeviceToHost, h->stream));
   if (is_real_root) AO_CUDA(cudaMemcpyAsync(is_real_root, h->d_real_root, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  AO_CUDA(ao::launch_sum_counters(h->tp, h->G, h->d_counters, h->stream));
+  AO_CUDA(ao::launch_sum_counters(h->tp, h->G, h->G, h->d_counters, h->stream));
   unsigned long long c[8];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
@@ -514,9 +550,14 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
 }
 
 extern "C" int ao_nn_forward(ao_engine* h, const float* states, int n, float* p, float* v) {
+  return ao_nn_forward_set(h, 0, states, n, p, v);
+}
+
+extern "C" int ao_nn_forward_set(ao_engine* h, int set, const float* states, int n, float* p, float* v) {
   if (!h) return fail(-1, "null engine");
+  if (set < 0 || set > 1) return fail(-1, "weight set %d out of range 0..1", set);
   DeviceGuard guard(h->cfg.device);
-  if (!h->weights_loaded) return fail(-3, "no weights loaded");
+  if (!h->ws[set].loaded) return fail(-3, "no weights loaded");
   if (h->B != 9 && h->B != 15) return fail(-1, "tower kernel supports board_size 9 and 15");
   const int A = h->A, C = h->cfg.inplanes;
   const int chunk = h->G;
@@ -533,7 +574,7 @@ extern "C" int ao_nn_forward(ao_engine* h, const float* states, int n, float* p,
     const int m = n - o < chunk ? n - o : chunk;
     cudaError_t e = cudaMemcpyAsync(d_states, states + (size_t)o * C * A, (size_t)m * C * A * 4, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = ao::launch_pack_states(d_states, m, h->B, C, h->tp.nn_in, d_bad, h->stream);
-    if (e == cudaSuccess) e = ao::launch_tower(h->tw, h->B, h->cfg.nn_precision, h->tp.nn_in, nullptr, m, h->tp.nn_policy, h->tp.nn_value, h->num_sms, h->stream);
+    if (e == cudaSuccess) e = ao::launch_tower(h->ws[set].tw, h->B, h->ws[set].precision, h->tp.nn_in, nullptr, m, h->tp.nn_policy, h->tp.nn_value, h->num_sms, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p + (size_t)o * A, h->tp.nn_policy, (size_t)m * A * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(v + o, h->tp.nn_value, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -556,6 +597,7 @@ extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_
   if (n_games < 1 || n_games > h->G) return fail(-1, "n_games = %d out of range 1..%d", n_games, h->G);
   int rc = require_weights(h);
   if (rc) return rc;
+  h->tp.arena_M = 0;
   std::vector<uint32_t> keys(n_games);
   for (int i = 0; i < n_games; ++i) keys[i] = first_key + (uint32_t)i;
   AO_CUDA(cudaMemcpyAsync(h->d_keys, keys.data(), (size_t)n_games * 4, cudaMemcpyHostToDevice, h->stream));
@@ -589,6 +631,7 @@ extern "C" int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t firs
     h->stream_capacity = (size_t)n_episodes;
   }
   if (!h->d_stream_next && (rc = ealloc(h, &h->d_stream_next, 1)) != 0) return rc;
+  h->tp.arena_M = 0;
   AO_CUDA(cudaMemsetAsync(h->d_stream, 0, (size_t)n_episodes * h->rec_bytes, h->stream));
   const uint32_t next = first_key + (uint32_t)n_slots;
   AO_CUDA(cudaMemcpyAsync(h->d_stream_next, &next, 4, cudaMemcpyHostToDevice, h->stream));
@@ -620,6 +663,46 @@ extern "C" int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size
   return 0;
 }
 
+// Arena (eval_main.main, eval_main.py:204-333) on the device: n_slots concurrent series of `matches_per_slot` matches,
+// the player (weight set 0) against the enemy (weight set 1, or a RandomAgent), each side with its own tree and
+// decision stream, colours swapped after every match.  Driven by ao_selfplay_rounds like self-play.
+extern "C" int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int matches_per_slot, int enemy_random,
+                              int keep_records, int n_mcts_player, int n_mcts_enemy) {
+  if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
+  if (n_slots < 1 || 2 * n_slots > h->G) return fail(-1, "n_slots = %d needs max_games >= %d (one game slot per side), have %d", n_slots, 2 * n_slots, h->G);
+  if (matches_per_slot < 1) return fail(-1, "matches_per_slot must be positive");
+  int rc = require_weights(h, 0);
+  if (rc) return rc;
+  if (!enemy_random && (rc = require_weights(h, 1)) != 0) return rc;
+  const size_t n_rec = keep_records ? (size_t)n_slots * (size_t)matches_per_slot : 0;
+  if (n_rec > h->stream_capacity) {
+    if (h->d_stream) cudaFree(h->d_stream);
+    h->d_stream = nullptr;
+    h->stream_capacity = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_stream), n_rec * h->rec_bytes);
+    if (e != cudaSuccess) return fail(-2, "cudaMalloc of the match record slab (%zu bytes) failed: %s", n_rec * h->rec_bytes, cudaGetErrorString(e));
+    h->stream_capacity = n_rec;
+  }
+  if (n_rec) AO_CUDA(cudaMemsetAsync(h->d_stream, 0, n_rec * h->rec_bytes, h->stream));
+  ao::TreeParams& tp = h->tp;
+  tp.stream_out = n_rec ? h->d_stream : nullptr;
+  tp.stream_rec_bytes = h->rec_bytes;
+  tp.arena_M = n_slots;
+  tp.arena_matches_per_slot = matches_per_slot;
+  tp.arena_num_mcts[0] = n_mcts_player > 0 ? n_mcts_player : h->cfg.num_mcts;
+  tp.arena_num_mcts[1] = n_mcts_enemy > 0 ? n_mcts_enemy : h->cfg.num_mcts;
+  tp.arena_random[0] = 0;
+  tp.arena_random[1] = enemy_random ? 1 : 0;
+  tp.synth_salt[0] = 0u;
+  tp.synth_salt[1] = 1u;
+  AO_CUDA(ao::launch_reset_arena(tp, n_slots, first_key, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  h->selfplay_games = n_slots;
+  h->stream_episodes = (int)n_rec;
+  return 0;
+}
+
 extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   if (!h) return fail(-1, "null engine");
   DeviceGuard guard(h->cfg.device);
@@ -628,7 +711,7 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   const int max_iters = synth ? (1 << 30) : 64;
   int rc;
   if ((rc = run_rounds(h, h->selfplay_games, max_iters, rounds)) != 0) return rc;
-  AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
+  AO_CUDA(launch_sum_selfplay(h));
   h->launches += 1;
   unsigned long long c[8];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
@@ -653,7 +736,7 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
   int rc;
   for (int r = 0; r < rounds; ++r)
     if ((rc = run_round(h, nullptr, h->selfplay_games, max_iters, r)) != 0) return rc;
-  AO_CUDA(ao::launch_sum_counters(h->tp, h->selfplay_games, h->d_counters, h->stream));
+  AO_CUDA(launch_sum_selfplay(h));
   h->launches += 1;
   unsigned long long c[8];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
@@ -680,27 +763,31 @@ extern "C" int ao_tower_debug(ao_engine* h, int enable, uint64_t* out8) {
   if (!h) return fail(-1, "null engine");
   DeviceGuard guard(h->cfg.device);
   AO_CUDA(cudaStreamSynchronize(h->stream));
-  if (out8 && h->tw.dbg) AO_CUDA(cudaMemcpy(out8, h->tw.dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  if (enable && !h->tw.dbg) {
+  if (out8 && h->ws[0].tw.dbg) AO_CUDA(cudaMemcpy(out8, h->ws[0].tw.dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (enable && !h->ws[0].tw.dbg) {
     unsigned long long* p = nullptr;
     int rc = ealloc(h, &p, 8);
     if (rc) return rc;
-    h->tw.dbg = p;
+    h->ws[0].tw.dbg = p;
   }
-  if (h->tw.dbg) AO_CUDA(cudaMemset(h->tw.dbg, 0, 8 * sizeof(uint64_t)));
-  if (!enable) h->tw.dbg = nullptr;
+  if (h->ws[0].tw.dbg) AO_CUDA(cudaMemset(h->ws[0].tw.dbg, 0, 8 * sizeof(uint64_t)));
+  if (!enable) h->ws[0].tw.dbg = nullptr;
   return 0;
 }
 #endif  // AO_PROBE
 
 // Switch the tower's operand mode at run time (AO_NN_*); the facades use it to pick the cheapest mode that meets the
 // 1e-4 contract for the loaded weights.
-extern "C" int ao_set_nn_precision(ao_engine* h, int mode) {
+extern "C" int ao_set_nn_precision(ao_engine* h, int mode) { return ao_set_nn_precision_set(h, 0, mode); }
+
+extern "C" int ao_set_nn_precision_set(ao_engine* h, int set, int mode) {
   if (!h) return fail(-1, "null engine");
+  if (set < 0 || set > 1) return fail(-1, "weight set %d out of range 0..1", set);
   DeviceGuard guard(h->cfg.device);
   if (mode != AO_NN_FP16 && mode != AO_NN_FP16X3 && mode != AO_NN_FP16_1CTA && mode != AO_NN_FP16_LOCKSTEP) return fail(-1, "unknown nn_precision %d", mode);
   AO_CUDA(cudaStreamSynchronize(h->stream));
-  h->cfg.nn_precision = mode;
+  h->ws[set].precision = mode;
+  if (set == 0) h->cfg.nn_precision = mode;
   return 0;
 }
 

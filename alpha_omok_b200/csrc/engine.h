@@ -45,6 +45,9 @@ struct __align__(16) Game {
   int32_t winner;
   int32_t error;
   uint32_t nn_log_count;
+  // arena mode (auto_play == 4), kept in the PLAYER slot of a match: side to move (0 player, 1 enemy), colours, index
+  // of the match this slot is playing (eval_main.main plays N_MATCH matches one after the other, colours swapped)
+  int32_t arena_cur, arena_player_black, arena_match;
   unsigned long long sims_total, nn_evals, terminal_sims, moves_played, games_finished;
 };
 
@@ -80,7 +83,7 @@ struct TreeParams {
   LeafIn* nn_in;         // [G]
   float* nn_policy;      // [G][A]
   float* nn_value;       // [G]
-  int32_t* nn_count;     // device counter
+  int32_t* nn_count;     // device counters [2]: requests of weight set 0 / 1 emitted this round
   int32_t* n_active;     // device counter
   float* nnlog_policy;   // [G][cap][A]
   float* nnlog_value;    // [G][cap]
@@ -90,6 +93,14 @@ struct TreeParams {
   size_t stream_rec_bytes;
   uint32_t* stream_next_key;   // device counter
   uint32_t stream_first_key, stream_key_end;
+  // arena (eval_main.py:204-333): matches [0, arena_M); side s (0 player, 1 enemy) of match m lives in game slot
+  // s * arena_M + m with its own tree and decision stream; network requests of side s go to nn slots
+  // [s * arena_M, ...) and are evaluated with weight set s.  0 = self-play / facade mode.
+  int arena_M;
+  int arena_matches_per_slot;   // consecutive matches a slot plays (colours swapped after each, streams continue)
+  int arena_num_mcts[2];        // N_MCTS_PLAYER / N_MCTS_ENEMY (eval_main.py:33-34)
+  int arena_random[2];          // side is a RandomAgent (agents.py:637-657): no tree, no network
+  uint32_t synth_salt[2];       // AO_EVAL_SYNTH: which synthetic "network" a side uses
 };
 
 // folded network parameters on the device (one weight set)
@@ -131,7 +142,8 @@ cudaError_t launch_export_roots(const TreeParams& p, const int32_t* game_ids_dev
                                 double* priors_dev, int32_t* real_root_dev, cudaStream_t s);
 cudaError_t launch_reset_games(const TreeParams& p, const int32_t* game_ids_dev, int n, const uint32_t* keys_dev,
                                int auto_play, cudaStream_t s);
-cudaError_t launch_sum_counters(const TreeParams& p, int n, unsigned long long* out5_dev, cudaStream_t s);
+cudaError_t launch_sum_counters(const TreeParams& p, int n, int n_running, unsigned long long* out5_dev, cudaStream_t s);
+cudaError_t launch_reset_arena(const TreeParams& p, int n_slots, uint32_t first_key, cudaStream_t s);
 cudaError_t launch_pack_records(const TreeParams& p, int n, uint8_t* out, size_t bytes_per_game, cudaStream_t s);
 
 cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr,

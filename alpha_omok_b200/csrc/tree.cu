@@ -112,7 +112,7 @@ __device__ void remix_root_noise(Ctx& c, int32_t root_node, int L, uint32_t& noi
 }
 
 // ---------------------------------------------------------------------------------------------- synthetic NN
-__device__ void synth_eval(Ctx& c, const uint8_t* root_moves, int n_root, int depth, float& value) {
+__device__ void synth_eval(Ctx& c, const uint8_t* root_moves, int n_root, int depth, float& value, uint32_t salt) {
   // FNV-1a style fold of the move sequence (root moves then the path actions), then Philox per action.
   unsigned long long hh = 0xCBF29CE484222325ull;
   for (int i = 0; i < n_root; ++i) hh = (hh ^ (unsigned long long)(root_moves[i] + 1)) * 0x100000001B3ull;
@@ -122,7 +122,7 @@ __device__ void synth_eval(Ctx& c, const uint8_t* root_moves, int n_root, int de
     hh = (hh ^ (unsigned long long)(a + 1)) * 0x100000001B3ull;
   }
   const uint32_t lo = (uint32_t)hh, hi = (uint32_t)(hh >> 32);
-  const uint2 k = make_uint2(0x5EEDu, 0x0A0Au);
+  const uint2 k = make_uint2(0x5EEDu, 0x0A0Au + salt);
   for (int a = c.lane; a < c.P.A; a += 32) {
     const uint4 r = philox4x32(make_uint4((uint32_t)a, 0u, lo, hi), k);
     c.sm->pol[a] = (float)((r.x >> 8) + 1u) * 5.9604644775390625e-08f;  // 2^-24, exact
@@ -501,6 +501,162 @@ __device__ void play_move(Ctx& c, Regs& g) {
   if (P.noise && g.root_node >= 0) remix_root_noise(c, g.root_node, P.A - g.n_moves, g.noise_draws);
 }
 
+// ---------------------------------------------------------------------------------------------- arena
+__device__ __forceinline__ int arena_side(const TreeParams& P, int game) { return game >= P.arena_M ? 1 : 0; }
+
+// pi = one-hot(argmax visits, uniform tie-break over ascending indices) (utils.py:198-205) from sm->dbuf
+__device__ int argmax_tiebreak(Ctx& c, Regs& g, int A) {
+  WarpSmem* sm = c.sm;
+  double mx = 0.0;
+  for (int a = c.lane; a < A; a += 32) mx = fmax(mx, sm->dbuf[a]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
+  int K = 0;
+  for (int b = 0; b < A; b += 32) {
+    const int a = b + c.lane;
+    K += __popc(__ballot_sync(kFull, a < A && sm->dbuf[a] == mx));
+  }
+  int r = draw_choice(c, g.rng_ctr, K);
+  int action = 0;
+  for (int b = 0; b < A; b += 32) {
+    const int a = b + c.lane;
+    const unsigned bal = __ballot_sync(kFull, a < A && sm->dbuf[a] == mx);
+    const int cnt = __popc(bal);
+    if (r < cnt) {
+      action = b + (int)__fns(bal, 0, r + 1);
+      break;
+    }
+    r -= cnt;
+  }
+  return action;
+}
+
+// The side whose search just finished (or a RandomAgent side) moves: eval_main.py:243-283.
+//   pi = get_pi(root_id, tau=0); action = argmax_onehot(pi)   (one tie-break draw when several maxima, no other draw)
+//   root_id = mover.root_id + (action,); env.step; then the OTHER side's next get_pi(root_id) finds the new root in its
+//   own tree (reused root, possibly with n == 0: agents.py:93-111) or not (real root).
+// One warp owns the match, so it updates both sides' trees in turn and goes on searching as the other side.
+// Returns true when the warp can go on (as the other side) within this launch.
+__device__ bool arena_move(Ctx& c, Regs& g) {
+  const TreeParams& P = c.P;
+  WarpSmem* sm = c.sm;
+  const int A = P.A, M = P.arena_M;
+  const int side = arena_side(P, c.game);
+  const int m = c.game - side * M;
+  Game* pg = &P.games[m];  // player slot: match-level fields
+  uint32_t* rec = P.rec_visits + ((size_t)m * A + (size_t)g.n_moves) * A;
+  for (int a = c.lane; a < A; a += 32) {
+    sm->dbuf[a] = 0.0;
+    rec[a] = 0u;
+  }
+  __syncwarp();
+  int action;
+  if (P.arena_random[side]) {
+    // RandomAgent.get_pi: uniform over the empty cells; argmax_onehot then draws one of them (ascending order)
+    const int L = A - g.n_moves;
+    int r = draw_choice(c, g.rng_ctr, L);
+    action = 0;
+    for (int b = 0; b < A; b += 32) {
+      const int a = b + c.lane;
+      const uint32_t occ = __shfl_sync(kFull, g.rb | g.rw, a < A ? a / P.B : 0);
+      const bool empty = a < A && ((occ >> (a % P.B)) & 1u) == 0u;
+      const unsigned bal = __ballot_sync(kFull, empty);
+      const int cnt = __popc(bal);
+      if (r < cnt) {
+        action = b + (int)__fns(bal, 0, r + 1);
+        break;
+      }
+      r -= cnt;
+    }
+    action = __shfl_sync(kFull, action, 0);
+  } else {
+    if (g.root_node >= 0) {
+      const size_t base = c.abase + (size_t)g.root_node;
+      const int L = A - g.n_moves;
+      for (int i = c.lane; i < L; i += 32) {
+        const int a = P.slot_act[base + i];
+        const uint32_t n = P.slot_nw[base + i].x;
+        sm->dbuf[a] = (double)n;
+        rec[a] = n;
+      }
+    }
+    __syncwarp();
+    action = argmax_tiebreak(c, g, A);
+  }
+  __syncwarp();
+  (void)advance_root(c, g, action);  // mover.root_id + (action,)
+  if (c.lane == 0) c.gm->moves_played += 1ull;
+  const int win = check_win_rows(g.rb, g.rw, P.B, g.n_moves, sm->rows, c.lane);
+  const int o = side ? m : M + m;  // the other side's slot
+  Game* og = &P.games[o];
+  if (win != 0) {
+    __syncwarp();  // lane 0's store of the last move (advance_root) must be visible to the lanes that copy the moves
+    const int k = pg->arena_match;
+    if (P.stream_out) {  // record of the finished match: same layout as pack_records_kernel, index = slot * mps + k
+      uint8_t* out = P.stream_out + ((size_t)m * P.arena_matches_per_slot + (size_t)k) * P.stream_rec_bytes;
+      if (c.lane == 0) {
+        reinterpret_cast<int16_t*>(out)[0] = (int16_t)g.n_moves;
+        out[2] = (uint8_t)win;
+        out[3] = (uint8_t)(pg->arena_player_black ? 1 : 0);
+      }
+      int16_t* mv = reinterpret_cast<int16_t*>(out) + 2;
+      for (int i = c.lane; i < A; i += 32) mv[i] = i < g.n_moves ? (int16_t)c.gm->moves[i] : (int16_t)-1;
+      uint32_t* vis = reinterpret_cast<uint32_t*>(out + ((4 + (size_t)A * 2 + 3) & ~(size_t)3));
+      const uint32_t* src = P.rec_visits + (size_t)m * A * A;
+      const int n_words = g.n_moves * A;
+      for (int i = c.lane; i < A * A; i += 32) vis[i] = i < n_words ? src[i] : 0u;
+    }
+    __syncwarp();
+    const bool more = k + 1 < P.arena_matches_per_slot;
+    const int pb = pg->arena_player_black ^ 1;  // colours swap (eval_main.py:316); both agents are reset (:333)
+    // the mover's side (registers) ...
+    g.rb = 0u; g.rw = 0u;
+    g.n_moves = 0; g.last1 = -1; g.last2 = -1;
+    g.root_node = CH_UNVISITED; g.root_n = 0u; g.root_w = 0.f; g.slot_count = 0u;
+    g.sims_done = 0; g.sims_target = P.arena_num_mcts[side] + 1;
+    g.status = more ? ST_SEARCH : ST_FINISHED;
+    // ... and the other side (global); the decision streams of both agents run on (np.random is never re-seeded)
+    if (c.lane < kRowsPad) {
+      og->rows_b[c.lane] = 0;
+      og->rows_w[c.lane] = 0;
+    }
+    if (c.lane == 0) {
+      c.gm->is_real_root = 1;
+      og->n_moves = 0; og->last1 = -1; og->last2 = -1;
+      og->root_node = CH_UNVISITED; og->root_n = 0u; og->root_w = 0.f; og->slot_count = 0u;
+      og->sims_done = 0; og->sims_target = P.arena_num_mcts[side ^ 1] + 1;
+      og->is_real_root = 1;
+      og->status = more ? ST_SEARCH : ST_FINISHED;
+      pg->winner = win;  // of the last finished match
+      pg->games_finished += 1ull;
+      pg->arena_match = k + 1;
+      pg->arena_player_black = pb;
+      pg->arena_cur = pb ? 0 : 1;  // black moves first
+    }
+    __syncwarp();
+    return false;  // the next launch picks the side that opens the next match
+  }
+  // ---- hand the position over to the other side: its get_pi(root_id) (agents.py:82-103)
+  const int mcts_other = P.arena_num_mcts[side ^ 1];
+  store_regs<1>(c, g);
+  __syncwarp();
+  c.gm = og;
+  c.game = o;
+  load_regs(c, g);
+  c.abase = arena_base(P, o, g.arena);
+  const bool in_tree = advance_root(c, g, action);
+  g.sims_done = 0;
+  g.sims_target = in_tree ? mcts_other : mcts_other + 1;
+  g.status = ST_SEARCH;
+  if (c.lane == 0) {
+    og->is_real_root = in_tree ? 0 : 1;
+    pg->arena_cur = side ^ 1;
+  }
+  if (in_tree && P.noise && g.root_node >= 0) remix_root_noise(c, g.root_node, P.A - g.n_moves, g.noise_draws);
+  __syncwarp();
+  return true;
+}
+
 // One warp advances one game until it needs a network evaluation (or finishes its search / game).
 template <int MAXJ>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -509,45 +665,51 @@ tree_step_kernel(TreeParams P, const int32_t* __restrict__ game_ids, int n, int 
   const int wib = threadIdx.x >> 5;
   const int w = blockIdx.x * kWarpsPerBlock + wib;
   if (w >= n) return;
-  const int game = game_ids ? game_ids[w] : w;
-  Game* gm = &P.games[game];
-  Ctx c{P, gm, &s_warp[wib], (int)(threadIdx.x & 31), game, 0, make_uint2(P.seed_lo, P.seed_hi)};
+  int game0 = game_ids ? game_ids[w] : w;
+  const bool arena = P.arena_M > 0;
+  if (arena) game0 = P.games[w].arena_cur ? P.arena_M + w : w;  // warp = match; slot of the side to move
+  Ctx c{P, &P.games[game0], &s_warp[wib], (int)(threadIdx.x & 31), game0, 0, make_uint2(P.seed_lo, P.seed_hi)};
   Regs g;
   load_regs(c, g);
   if (g.status != ST_SEARCH && g.status != ST_WAIT_NN) return;
-  c.abase = arena_base(P, game, g.arena);
+  c.abase = arena_base(P, c.game, g.arena);
   const int lane = c.lane;
   WarpSmem* sm = c.sm;
-  uint32_t* path = P.path + (size_t)game * (P.A + 1);
-  const bool auto_play = gm->auto_play != 0;
+  const bool auto_play = c.gm->auto_play != 0;
+  // c.gm / c.game change when an arena match hands over to the other side: always go through them
+  auto path = [&]() { return P.path + (size_t)c.game * (P.A + 1); };
 
   for (int it = 0; it < max_iters; ++it) {
     if (g.status == ST_WAIT_NN) {
       // -------- consume the network output for the pending leaf
-      const int slot = gm->nn_slot;
-      const int depth = gm->leaf_depth;
+      const int slot = c.gm->nn_slot;
+      const int depth = c.gm->leaf_depth;
       for (int a = lane; a < P.A; a += 32) sm->pol[a] = P.nn_policy[(size_t)slot * P.A + a];
       const float value = P.nn_value[slot];
-      sm->rows[0][lane] = lane < kRowsPad ? gm->leaf_rows_b[lane] : (uint16_t)0;
-      sm->rows[1][lane] = lane < kRowsPad ? gm->leaf_rows_w[lane] : (uint16_t)0;
+      sm->rows[0][lane] = lane < kRowsPad ? c.gm->leaf_rows_b[lane] : (uint16_t)0;
+      sm->rows[1][lane] = lane < kRowsPad ? c.gm->leaf_rows_w[lane] : (uint16_t)0;
       __syncwarp();
       if (P.nn_log_cap > 0) {
-        const uint32_t k = gm->nn_log_count;
+        const uint32_t k = c.gm->nn_log_count;
         if (k < (uint32_t)P.nn_log_cap) {
-          float* lp = P.nnlog_policy + ((size_t)game * P.nn_log_cap + k) * P.A;
+          float* lp = P.nnlog_policy + ((size_t)c.game * P.nn_log_cap + k) * P.A;
           for (int a = lane; a < P.A; a += 32) lp[a] = sm->pol[a];
-          if (lane == 0) P.nnlog_value[(size_t)game * P.nn_log_cap + k] = value;
+          if (lane == 0) P.nnlog_value[(size_t)c.game * P.nn_log_cap + k] = value;
         }
         __syncwarp();
-        if (lane == 0) gm->nn_log_count = k + 1u;
+        if (lane == 0) c.gm->nn_log_count = k + 1u;
       }
       g.status = ST_SEARCH;
       if (!expand_and_backup(c, g, depth, value, false)) {
         g.status = ST_ERROR;
-        if (lane == 0) gm->error = 1;
+        if (lane == 0) c.gm->error = 1;
         break;
       }
-      if (lane == 0) gm->sims_total += 1ull;
+      if (lane == 0) c.gm->sims_total += 1ull;
+      continue;
+    }
+    if (arena && (P.arena_random[arena_side(P, c.game)] || g.sims_done >= g.sims_target)) {
+      if (!arena_move(c, g)) break;
       continue;
     }
     if (g.sims_done >= g.sims_target) {
@@ -640,7 +802,7 @@ tree_step_kernel(TreeParams P, const int32_t* __restrict__ game_ids, int n, int 
             }
           }
         }
-        if (lane == 0) path[depth] = (uint32_t)(base + s_idx);
+        if (lane == 0) path()[depth] = (uint32_t)(base + s_idx);
         ++depth;
         const int y = (int)s_act / P.B, x = (int)s_act % P.B;
         if (lane == y) {
@@ -661,9 +823,9 @@ tree_step_kernel(TreeParams P, const int32_t* __restrict__ game_ids, int n, int 
     if (win != 0) {
       // terminal leaf: mark, backup reward (no network call; the reference's call is discarded, agents.py:171-178)
       if (lane == 0) {
-        if (depth > 0) P.slot_child[path[depth - 1]] = -(1 + win);
-        gm->terminal_sims += 1ull;
-        gm->sims_total += 1ull;
+        if (depth > 0) P.slot_child[path()[depth - 1]] = -(1 + win);
+        c.gm->terminal_sims += 1ull;
+        c.gm->sims_total += 1ull;
       }
       if (depth == 0) g.root_node = -(1 + win);
       __syncwarp();
@@ -676,29 +838,31 @@ tree_step_kernel(TreeParams P, const int32_t* __restrict__ game_ids, int n, int 
     __syncwarp();
     if (P.eval_mode == AO_EVAL_SYNTH) {
       float value;
-      synth_eval(c, gm->moves, g.n_moves, depth, value);
+      synth_eval(c, c.gm->moves, g.n_moves, depth, value, arena ? P.synth_salt[arena_side(P, c.game)] : P.synth_salt[0]);
       if (lane == 0) {
-        gm->nn_evals += 1ull;
-        gm->sims_total += 1ull;
+        c.gm->nn_evals += 1ull;
+        c.gm->sims_total += 1ull;
       }
       if (!expand_and_backup(c, g, depth, value, false)) {
         g.status = ST_ERROR;
-        if (lane == 0) gm->error = 1;
+        if (lane == 0) c.gm->error = 1;
         break;
       }
       continue;
     }
     // network request: the five planes of utils.get_state_pt (utils.py:139-168) as row masks
     {
+      // arena: requests of side s are evaluated with weight set s and live in nn slots [s * M, ...)
+      const int net = arena ? arena_side(P, c.game) : 0;
       int slot = 0;
-      if (lane == 0) slot = atomicAdd(P.nn_count, 1);
+      if (lane == 0) slot = atomicAdd(P.nn_count + net, 1) + net * P.arena_M;
       slot = __shfl_sync(kFull, slot, 0);
       // last two actions on the path to the leaf (or of the root position)
       int l1 = g.last1, l2 = g.last2;
       if (depth >= 1) {
         l2 = l1;
-        l1 = P.slot_act[path[depth - 1]];
-        if (depth >= 2) l2 = P.slot_act[path[depth - 2]];
+        l1 = P.slot_act[path()[depth - 1]];
+        if (depth >= 2) l2 = P.slot_act[path()[depth - 2]];
       }
       const bool black_to_move = (nm & 1) == 0;
       uint32_t own = black_to_move ? rb : rw, opp = black_to_move ? rw : rb;
@@ -711,16 +875,16 @@ tree_step_kernel(TreeParams P, const int32_t* __restrict__ game_ids, int n, int 
         in->plane[1][lane] = (uint16_t)opp_prev;
         in->plane[2][lane] = (uint16_t)own;
         in->plane[3][lane] = (uint16_t)opp;
-        gm->leaf_rows_b[lane] = (uint16_t)rb;
-        gm->leaf_rows_w[lane] = (uint16_t)rw;
+        c.gm->leaf_rows_b[lane] = (uint16_t)rb;
+        c.gm->leaf_rows_w[lane] = (uint16_t)rw;
       }
       if (lane == 0) {
         in->colour = black_to_move ? 1u : 0u;
-        in->game = game;
-        gm->leaf_depth = depth;
-        gm->leaf_n_moves = nm;
-        gm->nn_slot = slot;
-        gm->nn_evals += 1ull;
+        in->game = c.game;
+        c.gm->leaf_depth = depth;
+        c.gm->leaf_n_moves = nm;
+        c.gm->nn_slot = slot;
+        c.gm->nn_evals += 1ull;
       }
       g.status = ST_WAIT_NN;
       break;
@@ -837,7 +1001,29 @@ __global__ void export_roots_kernel(TreeParams P, const int32_t* __restrict__ id
   if (lane == 0 && real_root) real_root[w] = gm->is_real_root;
 }
 
-__global__ void sum_counters_kernel(TreeParams P, int n, unsigned long long* out) {
+// eval_main.main's start (eval_main.py:213-229): both agents empty, the player is black in even slots' first match
+__global__ void reset_arena_kernel(TreeParams P, int n_slots, uint32_t first_key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n_slots) return;
+  const int side = i >= n_slots ? 1 : 0, m = i - side * n_slots;
+  Game* gm = &P.games[side * P.arena_M + m];
+  for (int r = 0; r < kRowsPad; ++r) {
+    gm->rows_b[r] = 0; gm->rows_w[r] = 0; gm->leaf_rows_b[r] = 0; gm->leaf_rows_w[r] = 0;
+  }
+  gm->n_moves = 0; gm->last1 = -1; gm->last2 = -1;
+  gm->status = ST_SEARCH;
+  gm->arena = 0; gm->root_node = CH_UNVISITED; gm->root_n = 0u; gm->root_w = 0.f; gm->slot_count = 0u;
+  gm->sims_done = 0; gm->sims_target = P.arena_num_mcts[side] + 1; gm->is_real_root = 1; gm->auto_play = 4;
+  gm->rng_ctr = 0u; gm->noise_draws = 0u; gm->game_key = first_key + 2u * (uint32_t)m + (uint32_t)side;
+  gm->leaf_depth = 0; gm->leaf_n_moves = 0; gm->nn_slot = 0; gm->winner = 0; gm->error = 0; gm->nn_log_count = 0u;
+  gm->sims_total = 0ull; gm->nn_evals = 0ull; gm->terminal_sims = 0ull; gm->moves_played = 0ull;
+  gm->games_finished = 0ull;
+  gm->arena_match = 0;
+  gm->arena_player_black = (m & 1) == 0 ? 1 : 0;
+  gm->arena_cur = gm->arena_player_black ? 0 : 1;
+}
+
+__global__ void sum_counters_kernel(TreeParams P, int n, int n_running, unsigned long long* out) {
   unsigned long long sims = 0, running = 0, evals = 0, errors = 0, moves = 0, fin = 0, term = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const Game* gm = &P.games[i];
@@ -846,7 +1032,7 @@ __global__ void sum_counters_kernel(TreeParams P, int n, unsigned long long* out
     moves += gm->moves_played;
     fin += gm->games_finished;
     term += gm->terminal_sims;
-    running += (gm->status == ST_SEARCH || gm->status == ST_WAIT_NN) ? 1ull : 0ull;
+    running += (i < n_running && (gm->status == ST_SEARCH || gm->status == ST_WAIT_NN)) ? 1ull : 0ull;
     errors += gm->status == ST_ERROR ? 1ull : 0ull;
   }
   atomicAdd(&out[0], sims);
@@ -904,10 +1090,14 @@ cudaError_t launch_reset_games(const TreeParams& p, const int32_t* ids, int n, c
   reset_games_kernel<<<(n + 127) / 128, 128, 0, s>>>(p, ids, n, keys, auto_play);
   return cudaGetLastError();
 }
-cudaError_t launch_sum_counters(const TreeParams& p, int n, unsigned long long* out5, cudaStream_t s) {
+cudaError_t launch_sum_counters(const TreeParams& p, int n, int n_running, unsigned long long* out5, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(out5, 0, 8 * sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  sum_counters_kernel<<<32, 128, 0, s>>>(p, n, out5);
+  sum_counters_kernel<<<32, 128, 0, s>>>(p, n, n_running, out5);
+  return cudaGetLastError();
+}
+cudaError_t launch_reset_arena(const TreeParams& p, int n_slots, uint32_t first_key, cudaStream_t s) {
+  reset_arena_kernel<<<(2 * n_slots + 127) / 128, 128, 0, s>>>(p, n_slots, first_key);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_records(const TreeParams& p, int n, uint8_t* out, size_t bytes_per_game, cudaStream_t s) {

@@ -60,6 +60,11 @@ int ao_engine_destroy(ao_engine* h);
 int ao_load_weights(ao_engine* h, int n_tensors, const char* const* names, const float* const* ptrs,
                     const int64_t* numel);
 
+/* Second weight set: eval_main.Evaluator.set_agents builds TWO networks, player and enemy (eval_main.py:87-101).
+ * set 0 = Agent.model / the player (what ao_load_weights fills), set 1 = the arena's enemy. */
+int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const char* const* names, const float* const* ptrs,
+                        const int64_t* numel);
+
 /* ZeroAgent.reset() + a fresh GameState (agents.py:55-58, main.py:136).  game_keys[i] selects the decision stream. */
 int ao_games_reset(ao_engine* h, const int32_t* game_ids, int n, const uint32_t* game_keys);
 
@@ -77,6 +82,7 @@ int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int16_t* roots
 /* ZeroAgent.get_pv (agents.py:252-260) / PVNet.forward (model.py:97-104) on explicit states:
  * states float32 [n][inplanes][B][B] with {0,1} entries (utils.get_state_pt layout) -> p [n][A], v [n]. */
 int ao_nn_forward(ao_engine* h, const float* states, int n, float* p, float* v);
+int ao_nn_forward_set(ao_engine* h, int set, const float* states, int n, float* p, float* v);
 
 /* Batched twin of main.self_play (main.py:122-250): every game slot plays one episode on the device
  * (get_pi -> get_action -> env.step -> root advance), decisions from the per-game stream.
@@ -105,8 +111,23 @@ int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size_t* bytes_p
 /* ao_selfplay_rounds with CUDA events around every launch: summed device milliseconds of the tree-step kernels and of
  * the tower kernels over the `rounds` rounds (bench.py's roofline numbers). rounds <= 4096. */
 int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out8, float* tree_ms, float* tower_ms);
-/* Switch the tower's operand mode (AO_NN_*) at run time. */
+/* Switch the tower's operand mode (AO_NN_*) at run time (per weight set). */
 int ao_set_nn_precision(ao_engine* h, int mode);
+int ao_set_nn_precision_set(ao_engine* h, int set, int mode);
+
+/* eval_main.main's match loop (eval_main.py:204-333; Evaluator.get_action :153-170) on the device.  Every slot plays
+ * `matches_per_slot` consecutive matches like one run of eval_main.main: player (weight set 0, n_mcts_player sims) vs
+ * enemy (weight set 1 with n_mcts_enemy sims, or agents.RandomAgent when enemy_random != 0); per ply
+ * get_pi(root_id, tau=0) -> argmax_onehot -> root_id = mover.root_id + (action,) -> env.step; each side keeps its own
+ * tree, so the other side's next root is a reused root (possibly never visited, n == 0) or a real root
+ * (agents.py:82-111); colours swap after every match (the player is black first in even slots), both agents are reset,
+ * their decision streams (keys first_key + 2*slot + side) run on.  Needs max_games >= 2 * n_slots (one game slot per
+ * side).  Drive it with ao_selfplay_rounds (out[1] = slots still playing, out[5] = matches finished); with
+ * keep_records, ao_selfplay_stream_records_dev returns n_slots * matches_per_slot records (ao_records_dev layout,
+ * index = slot * matches_per_slot + match; visits[ply] = the mover's root visit counts, zeros for a RandomAgent ply;
+ * the pad byte after `winner` holds 1 when the player was black). n_mcts_* <= 0 selects ao_config.num_mcts. */
+int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int matches_per_slot, int enemy_random,
+                   int keep_records, int n_mcts_player, int n_mcts_enemy);
 /* Number of kernels this engine has launched so far (bench.py's gpu_launches). */
 int ao_launch_count(ao_engine* h, uint64_t* out);
 

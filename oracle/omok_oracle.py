@@ -442,6 +442,10 @@ class OracleZeroAgent:
         self.root_w = np.float32(self.root_w + (delta if sign > 0 else -delta))
         self.sims += 1
 
+    @property
+    def root_id(self):  # agents.py:83 (`self.root_id = root_id`)
+        return self.root_moves
+
     def get_pi(self, root_id, tau):  # agents.py:60-80
         self._set_root(root_id)
         n_sims = self.num_mcts + 1 if self.is_real_root else self.num_mcts
@@ -457,7 +461,9 @@ class OracleZeroAgent:
         self.visit, self.policy = visit, policy
         pi = visit / visit.sum()
         if tau == 0:
-            pi, _ = argmax_onehot(pi, self.stream)
+            # `host_stream` (optional): where draws made OUTSIDE `_mcts` come from - tests of the Python facades set it,
+            # because there the search draws happen on the device and this one in numpy's global generator
+            pi, _ = argmax_onehot(pi, getattr(self, "host_stream", None) or self.stream)
         return pi
 
 
@@ -497,4 +503,72 @@ def augment_dataset(memory, board_size):
             p_r = np.rot90(pi.reshape(board_size, board_size), k)
             out.append((s_r, p_r.flatten().copy(), z))
             out.append((np.flip(s_r, 2).copy(), np.fliplr(p_r).flatten().copy(), z))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Arena (eval_main.py:54-188 Evaluator, :204-333 main): two agents with their own trees, tau = 0, colours swapped
+# after every match.  Test infrastructure like everything else in this file.
+# --------------------------------------------------------------------------------------------------------------
+class OracleRandomAgent:
+    """agents.py:637-657 - pi uniform over the empty cells; the move is then argmax_onehot's uniform tie-break."""
+
+    def __init__(self, board_size, stream: DecisionStream):
+        self.B, self.A = board_size, board_size * board_size
+        self.stream = stream
+        self.root_id = None
+        self.visit = np.zeros(self.A)
+        self.is_real_root = True
+
+    def reset(self):
+        self.root_id = None
+
+    def get_pi(self, root_id, tau):
+        self.root_id = tuple(root_id)
+        empty = (get_board(self.root_id, self.B).reshape(-1) == 0).astype("float")
+        return empty / empty.sum()
+
+
+def arena_matches(board_size, player, enemy, n_match, forced=None, player_black_first=True):
+    """eval_main.py:204-333 for `n_match` consecutive matches: the player is black in match 0 (turn 0, enemy_turn 1,
+    :213-214), colours swap after every match (:316), both agents are reset after a match (:333).  Per ply
+    (eval_main.py:243-283): mover.get_pi(root_id, tau=0) -> utils.argmax_onehot (a second, draw-free arg-max for
+    ZeroAgents whose pi already is one-hot; THE uniform tie-break over the empty cells for a RandomAgent) -> root_id =
+    mover.root_id + (action,) -> env.step -> opponent.del_parents (memory only).
+    `player` / `enemy`: OracleZeroAgent or OracleRandomAgent, each drawing from its own DecisionStream.
+    Returns one dict per match: moves, visits [ply][A] of the mover's search, mover ('player'/'enemy') per ply,
+    real_root per ply, winner (1 black / 2 white / 3 draw), outcome ('player' / 'enemy' / 'draw').
+    `forced` = {(match, ply): action} overrides the move played (test hook: pushes the opponent onto a reply its tree
+    never visited); the mover's search and its random draws still happen.  `player_black_first=False` starts with the
+    colours the reference has in its second match (the device arena does that in odd slots)."""
+    out = []
+    forced = dict(forced or {})
+    env = OracleGameState(board_size)  # one env for all matches: lazy reset after a finished game (env_small.py:108-117)
+    turn, enemy_turn = 0, (1 if player_black_first else 0)
+    for m in range(n_match):
+        root_id, win_index = (0,), 0
+        rec = dict(moves=[], visits=[], movers=[], real_root=[])
+        while win_index == 0:
+            name, mover = ("player", player) if turn != enemy_turn else ("enemy", enemy)
+            pi = mover.get_pi(root_id, 0)
+            onehot, a = argmax_onehot(pi, getattr(mover, "host_stream", None) or mover.stream)
+            if (m, len(rec["moves"])) in forced:
+                a = int(forced[(m, len(rec["moves"]))])
+                onehot = np.zeros(len(pi))
+                onehot[a] = 1.0
+            root_id = mover.root_id + (a,)
+            _, _, win_index, turn, _ = env.step(onehot)
+            rec["moves"].append(a)
+            rec["visits"].append(np.asarray(mover.visit, np.int64).copy())
+            rec["movers"].append(name)
+            rec["real_root"].append(bool(mover.is_real_root))
+        rec["winner"] = win_index
+        # `turn` now belongs to the side that did NOT make the last move (eval_main.py:285-312)
+        rec["outcome"] = "draw" if win_index == 3 else ("player" if turn == enemy_turn else "enemy")
+        rec["player_black"] = enemy_turn == 1
+        out.append(rec)
+        enemy_turn = abs(enemy_turn - 1)
+        turn = 0
+        player.reset()
+        enemy.reset()
     return out

@@ -26,6 +26,21 @@ from oracle import omok_oracle as O  # noqa: E402
 from oracle import pvnet_ref  # noqa: E402
 
 
+FLASK_STUB = """
+class Blueprint:
+    def __init__(self, *a, **k): pass
+    def route(self, *a, **k): return lambda f: f
+class Flask(Blueprint):
+    def register_blueprint(self, *a, **k): pass
+    def run(self, *a, **k): pass
+def render_template(*a, **k): return ""
+def jsonify(*a, **k): return {}
+class _Req:
+    args = {}
+request = _Req()
+"""
+
+
 def import_reference():
     stub = tempfile.mkdtemp(prefix="pygame_stub_")
     os.makedirs(os.path.join(stub, "pygame"))
@@ -33,26 +48,31 @@ def import_reference():
         f.write("")
     with open(os.path.join(stub, "pygame", "locals.py"), "w") as f:
         f.write("QUIT = 12\n")
+    with open(os.path.join(stub, "flask.py"), "w") as f:   # eval_main.py:14 / webapi.py:1-2 (dashboard wiring only)
+        f.write(FLASK_STUB)
     sys.path.insert(0, stub)
     sys.path.insert(0, REF)
     import agents, model, utils  # noqa: E401
     from env import env_regular, env_small
+    import eval_main
     agents.PRINT_MCTS = False
-    return types.SimpleNamespace(agents=agents, model=model, utils=utils, env_small=env_small, env_regular=env_regular)
+    return types.SimpleNamespace(agents=agents, model=model, utils=utils, env_small=env_small, env_regular=env_regular,
+                                 eval_main=eval_main)
 
 
 # ------------------------------------------------------------------------------------------------ synthetic NN
-def synth_eval(moves, A):
-    """Hash 'network': exact float32 outputs, identical here, in the oracle tests and in csrc (EVAL_SYNTH)."""
+def synth_eval(moves, A, salt=0):
+    """Hash 'network': exact float32 outputs, identical here, in the oracle tests and in csrc (EVAL_SYNTH).
+    `salt` selects a different 'network' (the arena's two sides)."""
     hh = 0xCBF29CE484222325
     for m in moves[1:]:
-        hh = ((hh ^ (m + 1)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+        hh = ((hh ^ (int(m) + 1)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
     lo, hi = hh & 0xFFFFFFFF, hh >> 32
     pol = np.empty(A, np.float32)
     for a in range(A):
-        w = O.philox4x32((a, 0, lo, hi), (0x5EED, 0x0A0A))
+        w = O.philox4x32((a, 0, lo, hi), (0x5EED, 0x0A0A + salt))
         pol[a] = np.float32(((w[0] >> 8) + 1) * 2.0 ** -24)
-    w = O.philox4x32((0xFFFF, 0, lo, hi), (0x5EED, 0x0A0A))
+    w = O.philox4x32((0xFFFF, 0, lo, hi), (0x5EED, 0x0A0A + salt))
     val = np.float32((w[1] >> 8) * 2.0 ** -23 - 1.0)
     return pol, val
 
@@ -158,6 +178,231 @@ def gen_mcts_game(R, name, B, sims, seed, game, noise, tau_thres, max_moves, nn_
         out["nn_leaf_len"] = np.asarray([len(leaf) for leaf, _, _ in keep], np.int32)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(f"{name}: {len(ref['moves'])} moves, winner {ref['winner']}, {len(stub.log)} evals  OK (oracle == reference)")
+
+
+def gen_arena(R, name, sims, seed, n_match, enemy_kind="zero", forced=None):
+    """eval_main.main (eval_main.py:204-333) run UNMODIFIED (only `evaluator.set_agents`, which would read checkpoint
+    paths, is replaced by pre-built agents): two reference ZeroAgent(noise=False) sides with their own trees (or a
+    ZeroAgent against the reference RandomAgent), `get_pi(tau=0)` -> `argmax_onehot` -> `del_parents`, colours swapped
+    after every match.  Each agent draws from its own decision stream (key = side), each side has its own synthetic
+    network (salt = side).  `forced` = {(match, ply): action}: the move actually played is overridden (the searching
+    side's choice is discarded) - used to push the opponent onto a reply its tree never visited."""
+    import contextlib
+    import io
+    E = R.eval_main
+    B, A = 9, 81
+    forced = dict(forced or {})
+    streams = {"player": O.DecisionStream(seed, 0), "enemy": O.DecisionStream(seed, 1)}
+    log = []          # (agent name, root_id, visits, is_real_root)
+    actions = []      # action index per ply
+    boundaries = []   # len(actions) at every evaluator.reset()
+
+    def make(side):
+        if side == "enemy" and enemy_kind == "random":
+            agent = R.agents.RandomAgent(B)
+        else:
+            agent = R.agents.ZeroAgent(B, sims, 5, noise=False)
+            salt = 0 if side == "player" else 1
+            stub = StubModel(lambda leaf, x, salt=salt: synth_eval(leaf, A, salt))
+            agent.model = stub
+            orig_ee = agent._expansion_evaluation
+
+            def wrapped_ee(leaf_id, win_index, orig_ee=orig_ee, stub=stub):
+                stub.cur_leaf = leaf_id
+                return orig_ee(leaf_id, win_index)
+
+            agent._expansion_evaluation = wrapped_ee
+        orig = agent.get_pi
+
+        def get_pi(*a, side=side, agent=agent, orig=orig, **k):
+            PATCH.stream = streams[side]
+            pi = orig(*a, **k)
+            zero = isinstance(agent, R.agents.ZeroAgent)
+            log.append((side, tuple(a[0]), agent.visit.astype(np.int64).copy() if zero else np.zeros(A, np.int64),
+                        bool(agent.is_real_root) if zero else True))
+            return pi
+
+        agent.get_pi = get_pi
+        return agent
+
+    ev = E.evaluator
+    ev.player, ev.enemy = make("player"), make("enemy")
+    ev.monitor = R.agents.ZeroAgent(B, sims, 5, noise=False)
+    ev.monitor.model = StubModel(lambda leaf, x: (np.full(A, 1 / A, np.float32), np.float32(0)))
+    ev.env = R.env_small.GameState("text")
+    ev.set_agents = lambda *a: None
+    orig_get_action = ev.get_action
+    match_no = [0]
+
+    def get_action(root_id, board, turn, enemy_turn):
+        action, idx = orig_get_action(root_id, board, turn, enemy_turn)
+        key = (match_no[0], len(actions) - (boundaries[-1] if boundaries else 0))
+        if key in forced:
+            idx = forced[key]
+            action = np.zeros(A)
+            action[idx] = 1
+        actions.append(int(idx))
+        return action, idx
+
+    ev.get_action = get_action
+    orig_reset = ev.reset
+
+    def reset():
+        boundaries.append(len(actions))
+        match_no[0] += 1
+        orig_reset()
+
+    ev.reset = reset
+    E.N_MATCH = n_match
+    with contextlib.redirect_stdout(io.StringIO()):
+        E.main()
+    assert len(boundaries) == n_match and len(log) == len(actions)
+
+    # ---- cross-check the oracle restatement (same streams, same synthetic networks)
+    def omake(side):
+        st = O.DecisionStream(seed, 0 if side == "player" else 1)
+        if side == "enemy" and enemy_kind == "random":
+            return O.OracleRandomAgent(B, st)
+        salt = 0 if side == "player" else 1
+        return O.OracleZeroAgent(B, sims, lambda mv, salt=salt: synth_eval(mv, A, salt), st, noise=False)
+
+    ora = O.arena_matches(B, omake("player"), omake("enemy"), n_match, forced=forced)
+    out = dict(B=B, sims=sims, seed=seed, n_match=n_match, enemy_kind=enemy_kind,
+               forced=np.asarray([[m, p, a] for (m, p), a in sorted(forced.items())], np.int32).reshape(-1, 3))
+    lo = 0
+    n0 = 0
+    for m, hi in enumerate(boundaries):
+        mv = actions[lo:hi]
+        vis = np.stack([log[i][2] for i in range(lo, hi)])
+        movers = [log[i][0] for i in range(lo, hi)]
+        real = [log[i][3] for i in range(lo, hi)]
+        winner = R.utils.check_win(R.utils.get_board((0,) + tuple(mv), B), 5)
+        o = ora[m]
+        assert o["moves"] == mv and o["winner"] == winner and o["movers"] == movers and o["real_root"] == real, (name, m)
+        assert np.array_equal(np.stack(o["visits"]), vis), (name, m)
+        # reused roots the searching side had never visited (agents.py:93-111 with n == 0): num_mcts - 1 child visits
+        n0 += sum(1 for i in range(len(mv)) if (movers[i] != "enemy" or enemy_kind == "zero")
+                  and not real[i] and vis[i].sum() == sims - 1)
+        out[f"moves{m}"] = np.asarray(mv, np.int32)
+        out[f"visits{m}"] = vis.astype(np.int32)
+        out[f"player_mover{m}"] = np.asarray([x == "player" for x in movers], np.int8)
+        out[f"real_root{m}"] = np.asarray(real, np.int8)
+        out[f"winner{m}"] = winner
+        out[f"outcome{m}"] = o["outcome"]
+        lo = hi
+    assert n0 > 0, "no reused root with n == 0 in this golden"
+    out["n_unvisited_reused_roots"] = n0
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {n_match} matches, plies {[int(b) for b in np.diff([0] + boundaries)]}, "
+          f"{n0} reused roots with n == 0  OK (oracle == reference eval_main.main)")
+
+
+def pick_forced_replies(sims, seed, plies=(4, 9)):
+    """{(0, ply): action}: at the given plies of match 0 the move played becomes the highest empty cell instead of the
+    searcher's choice - with 60 simulations over ~75 children a cell neither side's tree has ever visited, so the
+    opponent's next root is a reused root with n == 0 and the mover's own next root an unvisited child as well"""
+    B, A = 9, 81
+    forced = {}
+    for p in plies:
+        def mk(side):
+            return O.OracleZeroAgent(B, sims, lambda mv, s=side: synth_eval(mv, A, s), O.DecisionStream(seed, side),
+                                     noise=False)
+        m = O.arena_matches(B, mk(0), mk(1), 1, forced=forced)[0]
+        assert len(m["moves"]) > p + 2, "match too short for the forced plies"
+        empty = [c for c in range(A) if c not in m["moves"][:p]]
+        forced[(0, p)] = max(c for c in empty if c != m["moves"][p])
+    return forced
+
+
+def find_long_15x15_game(sims, seed0, min_plies):
+    """scan decision-stream seeds with the oracle for a 15x15 self-play game that enters the CPython-set child-order
+    regime (>= 149 stones); the reference then replays the seed found"""
+    A = 225
+    for seed in range(seed0, seed0 + 400):
+        tape = O.make_gamma_tape(seed, 0, A + 2, A, 10 / A)
+        g = O.self_play_game(15, sims, lambda mv: synth_eval(mv, A), O.DecisionStream(seed, 0, tape))
+        if len(g["moves"]) >= min_plies:
+            return seed, len(g["moves"])
+    raise RuntimeError("no long 15x15 game found")
+
+
+def gen_late_roots(R, name, B, sims, seed, n_roots, lo, hi):
+    """ZeroAgent.get_pi (agents.py:60-132) of the unmodified reference on late-game roots - stone counts in the regime
+    where `legal_actions` comes out in CPython's hash-table order (63-79 stones on 9x9, 149-223 on 15x15),
+    which decides the child a tie-break index and a Dirichlet component refer to.  Every root is searched, then the
+    position two plies deeper (own most-visited move + most-visited reply: a reused, re-noised root)."""
+    A = B * B
+    rs = np.random.RandomState(seed)
+    roots = []
+    while len(roots) < n_roots:
+        k = int(rs.randint(lo, hi))
+        mv = (0,) + tuple(int(x) for x in rs.permutation(A)[:k])
+        if R.utils.check_win(R.utils.get_board(mv, B), 5) == 0:
+            assert R.utils.legal_actions(mv, B) != sorted(R.utils.legal_actions(mv, B))
+            roots.append(mv)
+    out = dict(B=B, sims=sims, seed=seed, n_roots=n_roots)
+    for g, root in enumerate(roots):
+        tape = O.make_gamma_tape(seed, g, 4, A, 10 / A)
+        PATCH.stream = O.DecisionStream(seed, g, tape)
+        agent = R.agents.ZeroAgent(B, sims, 5, noise=True)
+        stub = StubModel(lambda leaf, x: synth_eval(leaf, A))
+        agent.model = stub
+        orig = agent._expansion_evaluation
+
+        def wrapped(leaf_id, win_index, orig=orig, stub=stub):
+            stub.cur_leaf = leaf_id
+            return orig(leaf_id, win_index)
+
+        agent._expansion_evaluation = wrapped
+        ora = O.OracleZeroAgent(B, sims, lambda mv: synth_eval(mv, A), O.DecisionStream(seed, g, tape), noise=True)
+        cur, searched, vis, pri, real = root, [], [], [], []
+        for step in range(2):
+            agent.get_pi(cur, 1)
+            ora.get_pi(cur, 1)
+            assert np.array_equal(agent.visit, ora.visit) and np.array_equal(agent.policy, ora.policy), (name, g, step)
+            assert agent.is_real_root == ora.is_real_root
+            searched.append(np.asarray(cur + (-1,) * (A + 1 - len(cur)), np.int16))
+            vis.append(agent.visit.astype(np.int32))
+            pri.append(agent.policy.copy())
+            real.append(int(agent.is_real_root))
+            a = int(np.argmax(agent.visit))
+            sub = agent.tree[cur + (a,)]["child"]
+            if not sub:
+                break
+            b = max(sub, key=lambda c: agent.tree[cur + (a, c)]["n"])   # first maximum in child order
+            cur = cur + (a, int(b))
+            if R.utils.check_win(R.utils.get_board(cur, B), 5) != 0:
+                break
+        out[f"roots{g}"] = np.stack(searched)
+        out[f"visits{g}"] = np.stack(vis)
+        out[f"priors{g}"] = np.stack(pri)
+        out[f"real{g}"] = np.asarray(real, np.int8)
+        out[f"tape{g}"] = tape
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {n_roots} late roots ({lo}-{hi} stones), {sims} sims  OK (oracle == reference)")
+
+
+def gen_round2(R, parts=("arena", "trained", "long15", "late")):
+    """round-2 fixtures: arena (eval_main.main), trained-checkpoint self-play, a full-length 15x15 game, late roots"""
+    if "arena" in parts:
+        gen_arena(R, "arena_9_synth_s30", sims=30, seed=41, n_match=2)
+        gen_arena(R, "arena_9_synth_s200", sims=200, seed=42, n_match=2)
+        gen_arena(R, "arena_9_synth_s60_forced", sims=60, seed=44, n_match=1, forced=pick_forced_replies(60, 44))
+        gen_arena(R, "arena_9_random_enemy_s40", sims=40, seed=43, n_match=2, enemy_kind="random")
+    if "trained" in parts:
+        z = np.load(os.path.join(HERE, "trained_9x9_180927.npz"))
+        sd = {k: torch.from_numpy(z[k]) for k in z.files}
+        gen_mcts_game(R, "mcts_9_trained_s40", 9, 40, seed=16, game=0, noise=True, tau_thres=6, max_moves=None,
+                      nn_kind="pvnet", sd=sd)
+    if "long15" in parts:
+        # a whole 15x15 self-play game that runs into the >= 149-stone regime: 2 simulations per move keep the play
+        # close to uniform (games of two searching players end long before), the search code runs all the same
+        seed, plies = find_long_15x15_game(sims=2, seed0=100, min_plies=152)
+        print("15x15 long game: seed", seed, "plies", plies)
+        gen_mcts_game(R, "mcts_15_synth_long", 15, 2, seed=seed, game=0, noise=True, tau_thres=6, max_moves=None,
+                      nn_kind="synth")
+    if "late" in parts:
+        gen_late_roots(R, "search_15_late_roots", 15, 60, seed=51, n_roots=4, lo=149, hi=215)
 
 
 def gen_rules(R):
@@ -336,6 +581,10 @@ def main():
     if "--only-trained" in sys.argv:
         gen_trained_checkpoint()
         return
+    if "--only-round2" in sys.argv:
+        parts = [a[len("--parts="):].split(",") for a in sys.argv if a.startswith("--parts=")]
+        gen_round2(R, *parts)
+        return
     gen_rules(R)
     gen_nn(R)
     gen_train(R)
@@ -347,6 +596,7 @@ def main():
     gen_mcts_game(R, "mcts_15_synth_s50", 15, 50, seed=14, game=2, noise=True, tau_thres=6, max_moves=40, nn_kind="synth")
     sd = pvnet_ref.make_state_dict(0, 10, 5, 128, 9)
     gen_mcts_game(R, "mcts_9_pvnet_s40", 9, 40, seed=15, game=0, noise=True, tau_thres=6, max_moves=None, nn_kind="pvnet", sd=sd)
+    gen_round2(R)
 
 
 if __name__ == "__main__":

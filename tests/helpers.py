@@ -17,17 +17,17 @@ def unpad_id(row):
     return tuple(row[:row.index(-1)]) if -1 in row else tuple(row)
 
 
-def synth_eval(moves, A):
-    """Same hash 'network' as tests/golden/make_golden.py and csrc/tree.cu (AO_EVAL_SYNTH)."""
+def synth_eval(moves, A, salt=0):
+    """Same hash 'network' as tests/golden/make_golden.py and csrc/tree.cu (AO_EVAL_SYNTH); salt = arena side."""
     hh = 0xCBF29CE484222325
     for m in moves[1:]:
-        hh = ((hh ^ (m + 1)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+        hh = ((hh ^ (int(m) + 1)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
     lo, hi = hh & 0xFFFFFFFF, hh >> 32
     pol = np.empty(A, np.float32)
     for a in range(A):
-        w = O.philox4x32((a, 0, lo, hi), (0x5EED, 0x0A0A))
+        w = O.philox4x32((a, 0, lo, hi), (0x5EED, 0x0A0A + salt))
         pol[a] = np.float32(((w[0] >> 8) + 1) * 2.0 ** -24)
-    w = O.philox4x32((0xFFFF, 0, lo, hi), (0x5EED, 0x0A0A))
+    w = O.philox4x32((0xFFFF, 0, lo, hi), (0x5EED, 0x0A0A + salt))
     return pol, np.float32((w[1] >> 8) * 2.0 ** -23 - 1.0)
 
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load, oracle_game_from_fixture, unpad_id
+from helpers import load, oracle_game_from_fixture, synth_eval, unpad_id
 from oracle import omok_oracle as O
 from oracle import pvnet_ref
 
@@ -51,7 +51,8 @@ def test_pvnet_ref_golden(name):
     assert np.abs(v.numpy() - fx["v"]).max() < 2e-6
 
 
-@pytest.mark.parametrize("name", ["mcts_9_synth_s40", "mcts_9_synth_nonoise", "mcts_15_synth_s50", "mcts_9_synth_s400"])
+@pytest.mark.parametrize("name", ["mcts_9_synth_s40", "mcts_9_synth_nonoise", "mcts_15_synth_s50", "mcts_9_synth_s400",
+                                  "mcts_15_synth_long"])
 def test_mcts_synth_golden(name):
     fx = load(name)
     ora = oracle_game_from_fixture(fx)
@@ -60,9 +61,11 @@ def test_mcts_synth_golden(name):
     assert np.array_equal(np.asarray(ora["visits"]), fx["visits"])
 
 
-def test_mcts_pvnet_golden_nn_replay():
-    """reference game driven by the real PVNet: the oracle replays the logged NN outputs and must reproduce it"""
-    fx = load("mcts_9_pvnet_s40")
+@pytest.mark.parametrize("name", ["mcts_9_pvnet_s40", "mcts_9_trained_s40"])
+def test_mcts_pvnet_golden_nn_replay(name):
+    """reference game driven by the real PVNet (random-init; the shipped trained checkpoint): the oracle replays the
+    logged NN outputs and must reproduce it"""
+    fx = load(name)
     it = iter(range(len(fx["nn_value"])))
 
     def evaluate(mv):
@@ -74,6 +77,42 @@ def test_mcts_pvnet_golden_nn_replay():
     assert ora["moves"] == [int(m) for m in fx["moves"]]
     assert ora["winner"] == int(fx["winner"])
     assert np.array_equal(np.asarray(ora["visits"]), fx["visits"])
+
+
+@pytest.mark.parametrize("name", ["arena_9_synth_s30", "arena_9_synth_s200", "arena_9_synth_s60_forced",
+                                  "arena_9_random_enemy_s40"])
+def test_arena_golden(name):
+    """eval_main.main run unmodified (two agents with own trees, tau = 0, colours swapped, forced replies onto unvisited
+    cells in one fixture): the oracle's arena loop reproduces every ply"""
+    fx = load(name)
+    B, A, sims, seed, n_match = int(fx["B"]), int(fx["B"]) ** 2, int(fx["sims"]), int(fx["seed"]), int(fx["n_match"])
+    forced = {(int(m), int(p)): int(a) for m, p, a in fx["forced"]}
+    player = O.OracleZeroAgent(B, sims, lambda mv: synth_eval(mv, A, 0), O.DecisionStream(seed, 0), noise=False)
+    if str(fx["enemy_kind"]) == "random":
+        enemy = O.OracleRandomAgent(B, O.DecisionStream(seed, 1))
+    else:
+        enemy = O.OracleZeroAgent(B, sims, lambda mv: synth_eval(mv, A, 1), O.DecisionStream(seed, 1), noise=False)
+    ora = O.arena_matches(B, player, enemy, n_match, forced=forced)
+    n0 = 0
+    for m, o in enumerate(ora):
+        assert o["moves"] == [int(a) for a in fx[f"moves{m}"]]
+        assert np.array_equal(np.stack(o["visits"]), fx[f"visits{m}"])
+        assert o["winner"] == int(fx[f"winner{m}"]) and o["outcome"] == str(fx[f"outcome{m}"])
+        assert [x == "player" for x in o["movers"]] == [bool(x) for x in fx[f"player_mover{m}"]]
+        assert o["real_root"] == [bool(x) for x in fx[f"real_root{m}"]]
+        n0 += sum(1 for v, r in zip(o["visits"], o["real_root"]) if not r and v.sum() == sims - 1)
+    assert n0 >= int(fx["n_unvisited_reused_roots"]) > 0
+
+
+def test_late_roots_golden():
+    fx = load("search_15_late_roots")
+    B, A, sims, seed = int(fx["B"]), int(fx["B"]) ** 2, int(fx["sims"]), int(fx["seed"])
+    for g in range(int(fx["n_roots"])):
+        agent = O.OracleZeroAgent(B, sims, lambda mv: synth_eval(mv, A), O.DecisionStream(seed, g, fx[f"tape{g}"]))
+        for step, row in enumerate(fx[f"roots{g}"]):
+            agent.get_pi(unpad_id(row), 1)
+            assert np.array_equal(agent.visit, fx[f"visits{g}"][step])
+            assert np.array_equal(agent.policy, fx[f"priors{g}"][step])
 
 
 def test_decision_stream_properties():
