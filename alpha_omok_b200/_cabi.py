@@ -108,9 +108,7 @@ def probe_lib():
     """libalpha_omok_b200_probe.so (include/alpha_omok_b200_probe.h): product entry points + instrumentation."""
     global _probe
     if _probe is None:
-        path = _build.PROBE_LIB_PATH
-        if not os.path.exists(path):
-            path = _build.build(probe=True)
+        path = _build.build(probe=True)  # stamp-checked: rebuilt only when the sources changed
         L = _bind(C.CDLL(path))
         vp, i32 = C.c_void_p, C.c_int32
         L.ao_tower_debug.argtypes = [vp, i32, vp]

@@ -2,7 +2,8 @@
 """bench.py - MCTS node-expansions/s of the self-play hot path (BASELINE.json metric), one JSON line on stdout.
 
   python bench.py [--gpus N --steps K --warmup W]           our arm   (one process per GPU under torchrun for N>1)
-  python bench.py --impl reference [...]                    the reference arm: the CPU oracle port of the same path
+  python bench.py --impl reference [...]                    the reference arm: the UNMODIFIED reference (oracle/_ref,
+                                                            assembled by oracle/make_ref.py) on all host cores
 
 Workload (config[1] of BASELINE.json): 4096 concurrent 9x9 self-play games per GPU, 400 sims/move, seed-0
 random-init PVNet(10 blocks, 128 planes), Dirichlet noise on, tau threshold 6, synthetic (empty-board) starts.
@@ -11,6 +12,11 @@ completes) = one move's worth of search for every game.  Finished episodes are r
 full.  `value` = simulations completed by all ranks / max-over-ranks device time (CUDA events on the launch stream).
 `e2e` = the same metric through the reference-facing call (BatchedZeroAgent.get_pi -> ao_search) with root IDs in
 pinned host memory copied H2D and visit counts copied D2H inside the timed region, every step.
+At N = 1 the line also carries `legs`: the other BASELINE configs measured the same way (config 3: 4096 games of 15x15;
+config 5: the arena, 1024 concurrent matches at 800 sims/move, shipped trained checkpoint vs a random-init net, both
+networks in one engine; and 4096-game self-play with the trained checkpoint = the hi/lo split tower), each with its own
+roofline numbers.  `cpu_baseline` = the unmodified reference on the host: BASELINE config 1 verbatim (one 40-sims/move
+game, all torch threads) and the all-core aggregate at the bench's own 400 sims/move.
 """
 from __future__ import annotations
 
@@ -45,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-episodes", action="store_true", help="skip the games/s leg (all games played to the end)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the config 3 / config 5 / trained-net legs (N = 1 only)")
+    ap.add_argument("--leg-steps", type=int, default=2, help="timed steps per leg")
     return ap.parse_args()
 
 
@@ -57,42 +65,47 @@ def peaks():
         return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-# ---------------------------------------------------------------------------------------------- CPU oracle timing
-def _cpu_worker(args):
-    """One single-threaded worker: the oracle port (oracle/) of one game's search on torch CPU fp32."""
-    board, sims, seconds, widx = args
-    import torch
-    torch.set_num_threads(1)
-    from oracle import omok_oracle as O
-    from oracle import pvnet_ref
-    A = board * board
-    sd = pvnet_ref.make_state_dict(0, 10, 5, 128, board)
-
-    def evaluate(moves):
-        x = torch.from_numpy(O.get_state_pt(moves, board, 5).astype(np.float32))[None]
-        p, v = pvnet_ref.pvnet_forward(sd, x)
-        return p[0].numpy(), v[0].item()
-
-    stream = O.DecisionStream(1234, widx, O.make_gamma_tape(1234, widx, 4, A, 10 / A))
-    agent = O.OracleZeroAgent(board, sims, evaluate, stream, noise=True)
-    agent._set_root((0,))
-    evaluate((0,))  # warm-up (page-in, thread pools)
-    t0 = time.perf_counter()
-    n = 0
-    while time.perf_counter() - t0 < seconds and n < sims + 1:
-        agent._simulate()
-        n += 1
-    return n, time.perf_counter() - t0
+# ---------------------------------------------------------------------------------------------- CPU reference timing
+def host_workers():
+    cores = os.cpu_count() or 1
+    return cores, max(1, min(cores, 64))
 
 
-def cpu_oracle_throughput(board, sims, seconds, workers):
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(workers) as pool:
-        res = pool.map(_cpu_worker, [(board, sims, seconds, i) for i in range(workers)])
-    total = sum(n for n, _ in res)
-    elapsed = max(t for _, t in res)
-    return total / elapsed, total, elapsed
+def cpu_aggregate(board, sims, steps, warmup, workers):
+    """`workers` single-thread processes, each playing its own self-play game with the reference's own agents /
+    model / env (oracle/ref_runner.py); one step = one move (= one get_pi of `sims` (+1) simulations) per worker.
+    Returns (expansions/s over the timed steps, total sims, seconds, kind, per-step seconds)."""
+    from oracle import ref_runner
+    pool = ref_runner.HostPool(board, sims, workers)
+    try:
+        for _ in range(warmup):
+            pool.step()
+        tot, secs, per = 0, 0.0, []
+        for _ in range(steps):
+            n, t, _ = pool.step()
+            tot += n
+            secs += t
+            per.append(t)
+    finally:
+        pool.close()
+    return tot / secs, tot, secs, pool.kind, per
+
+
+def cpu_baseline_block(board, sims, cores, workers, agg_steps=2, with_config1=True):
+    from oracle import ref_runner
+    v, n, secs, kind, _ = cpu_aggregate(board, sims, agg_steps, 0, workers)
+    out = {"value": v, "unit": "expansions/s", "cores": workers, "kind": kind,
+           "sample": f"{workers} single-thread processes, each playing its own {board}x{board} self-play game at {sims} sims/move "
+                     f"with the {'unmodified reference (agents.ZeroAgent + model.PVNet on torch CPU fp32 + env)' if kind == 'reference' else 'oracle port'}: "
+                     f"{agg_steps} moves per process = {n} simulations in {secs:.1f} s; host has {cores} cpus"}
+    if with_config1:
+        c1 = ref_runner.run_config1_subprocess(workers)
+        out["config1"] = {"what": "BASELINE config 1 verbatim: one 9x9 self-play game, 40 sims/move, seeds 0, random-init "
+                                  "PVNet(10,5,128,9), main.py:144-248 loop, torch threads = cores",
+                          "sims_per_s": c1["sims"] / c1["seconds"], "games_per_s": 1.0 / c1["seconds"], "sims": c1["sims"],
+                          "moves": c1["moves"], "winner": c1["winner"], "seconds": c1["seconds"], "threads": c1["threads"],
+                          "visit_sha256_16": c1["visit_sha256_16"], "kind": c1["kind"]}
+    return out
 
 
 def workload_config(a, world):
@@ -108,25 +121,26 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 64))
-    per_step = max(2.0, min(20.0, 150.0 / max(1, a.steps + a.warmup)))
-    for _ in range(a.warmup):
-        cpu_oracle_throughput(a.board, a.sims, min(per_step, 3.0), workers)
-    tot, t = 0, 0.0
-    for _ in range(a.steps):
-        v, n, el = cpu_oracle_throughput(a.board, a.sims, per_step, workers)
-        tot += n
-        t += el
-    value = tot / t
-    sample = (f"{workers} single-thread workers, each running the oracle port of ZeroAgent's simulation loop "
-              f"(first move of a {a.board}x{a.board} game, {a.sims} sims budget, torch CPU fp32 PVNet) for {per_step:.0f} s per step")
+    cores, workers = host_workers()
+    value, tot, secs, kind, per = cpu_aggregate(a.board, a.sims, a.steps, a.warmup, workers)
+    sample = (f"{workers} single-thread processes, each playing its own {a.board}x{a.board} self-play game at {a.sims} sims/move with the "
+              f"{'unmodified reference (oracle/_ref: agents.ZeroAgent, model.PVNet on torch CPU fp32, env)' if kind == 'reference' else 'oracle port'}; "
+              f"one step = one move (one get_pi) per process; host has {cores} cpus")
+    cb = {"value": value, "unit": "expansions/s", "cores": workers, "kind": kind, "sample": sample}
+    try:
+        from oracle import ref_runner
+        c1 = ref_runner.run_config1_subprocess(workers)
+        cb["config1"] = {"sims_per_s": c1["sims"] / c1["seconds"], "games_per_s": 1.0 / c1["seconds"], "sims": c1["sims"],
+                         "moves": c1["moves"], "winner": c1["winner"], "threads": c1["threads"],
+                         "visit_sha256_16": c1["visit_sha256_16"], "kind": c1["kind"]}
+    except Exception as e:  # the aggregate above is the line's value; config 1 is extra evidence
+        cb["config1"] = {"error": repr(e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "expansions/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / max(1, a.steps), "higher_is_better": True,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / max(1, a.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, a.gpus),
-        "cpu_baseline": {"value": value, "unit": "expansions/s", "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,6 +190,112 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- legs
+def _trained_state_dict():
+    """the reference's shipped 9x9 checkpoint (tests/golden/trained_9x9_180927.npz = data/180927_9400_297233_step_model.pickle)"""
+    import torch
+    z = np.load(os.path.join(ROOT, "tests", "golden", "trained_9x9_180927.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _timed_steps(eng, rounds, steps, warmup, stream, torch):
+    """`warmup` untimed + `steps` timed steps of `rounds` lock-step rounds; device time from CUDA events on the launch
+    stream, tower / tree time from the per-launch events of ao_selfplay_rounds_timed."""
+    st0 = None
+    for _ in range(max(1, warmup)):
+        st0 = eng.selfplay_rounds(rounds)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tower_ms = tree_ms = 0.0
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        st = st0
+        for _ in range(steps):
+            st = eng.selfplay_rounds_timed(rounds)
+            tower_ms += st["tower_ms"]
+            tree_ms += st["tree_ms"]
+        e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if st["errors"]:
+        raise SystemExit(f"bench.py: {st['errors']} game tree(s) overflowed their arena")
+    return {"ms": ms, "sims": st["sims"] - st0["sims"], "evals": st["nn_evals"] - st0["nn_evals"],
+            "moves": st["moves"] - st0["moves"], "finished": st["games_finished"] - st0["games_finished"],
+            "tower_ms": tower_ms, "tree_ms": tree_ms, "launches": steps * rounds}
+
+
+def _leg_line(name, workload, board, m, steps, rounds, passes_per_eval=1):
+    sustained, burst, peak_src = peaks()
+    achieved = m["evals"] * FLOP_PER_EXPANSION[board] / (m["tower_ms"] * 1e-3) / 1e12 if m["tower_ms"] > 0 else None
+    return {"workload": workload, "value": m["sims"] / (m["ms"] * 1e-3), "unit": "expansions/s", "steps": steps,
+            "rounds_per_step": rounds, "ms_per_step": m["ms"] / steps, "moves_per_s": m["moves"] / (m["ms"] * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": achieved / sustained if achieved else None, "frac_of_burst": achieved / burst if achieved else None,
+                         "peak_source": peak_src + ", bf16 sustained", "flop_per_expansion": FLOP_PER_EXPANSION[board],
+                         "mma_passes_per_k_step": passes_per_eval,
+                         "raw_mma_tflops": achieved * passes_per_eval if achieved else None,
+                         "tower_ms_per_round": m["tower_ms"] / (steps * rounds), "tree_ms_per_round": m["tree_ms"] / (steps * rounds),
+                         "kernel_share_of_step": m["tower_ms"] / (m["tower_ms"] + m["tree_ms"]) if m["tower_ms"] else None,
+                         "traffic": None}}
+
+
+def run_legs(a, local, stream, _cabi):
+    import torch
+    from alpha_omok_b200.model import seeded_state_dict
+    legs = {}
+    steps = max(1, a.leg_steps)
+    # ---- config 3: 4096 parallel 15x15 self-play games, 400 sims/move, random-init PVNet(10,5,128,15)
+    G, S = a.games, a.sims
+    eng = _cabi.Engine(board_size=15, num_mcts=S, max_games=G, seed=2000, device=local, stream=stream.cuda_stream)
+    eng.load_state_dict(seeded_state_dict(0, 10, 5, 128, 15))
+    eng.selfplay_begin(G, first_key=0, recycle=True)
+    m = _timed_steps(eng, S, steps, 1, stream, torch)
+    legs["board15"] = _leg_line("board15", f"BASELINE config 3: {G} parallel 15x15 self-play games, {S} sims/move, PVNet 10x128 random-init, "
+                                "single-pass fp16 tower (tower_stag_kernel<15>)", 15, m, steps, S)
+    eng.close()
+    # ---- trained-net self-play: the shipped checkpoint needs the hi/lo split tower (3 MMAs per k-step) for 1e-4
+    eng = _cabi.Engine(board_size=9, num_mcts=S, max_games=G, seed=2001, device=local, stream=stream.cuda_stream)
+    eng.load_state_dict(_trained_state_dict())
+    mode = eng.choose_nn_precision()
+    eng.selfplay_begin(G, first_key=0, recycle=True)
+    m = _timed_steps(eng, S, steps, 1, stream, torch)
+    legs["trained_selfplay"] = _leg_line("trained_selfplay", f"{G} parallel 9x9 self-play games, {S} sims/move, the reference's shipped trained "
+                                         f"checkpoint; tower mode picked by the 1e-4 probe: {'fp16 hi/lo split (AO_NN_FP16X3)' if mode == 1 else 'single-pass fp16'}",
+                                         9, m, steps, S, passes_per_eval=3 if mode == 1 else 1)
+    eng.close()
+    # ---- config 5: arena, 1024 concurrent matches, 800 sims/move, trained (split tower) vs random-init (fp16 tower)
+    M, SA = 1024, 800
+    eng = _cabi.Engine(board_size=9, num_mcts=SA, max_games=2 * M, noise=False, seed=2002, device=local, stream=stream.cuda_stream)
+    eng.load_state_dict(_trained_state_dict(), which=0)
+    eng.load_state_dict(seeded_state_dict(1, 10, 5, 128, 9), which=1)
+    pm, em = eng.choose_nn_precision(which=0), eng.choose_nn_precision(which=1)
+    eng.arena_begin(M, first_key=0, matches_per_slot=1 << 20, keep_records=False)   # steady state: slots keep playing
+    m = _timed_steps(eng, SA, steps, 1, stream, torch)
+    leg = _leg_line("arena", f"BASELINE config 5: eval_main arena, {M} concurrent 9x9 matches, {SA} sims/move, noise off, tau 0; player = shipped "
+                    f"trained checkpoint (tower mode {pm}), enemy = random-init PVNet seed 1 (tower mode {em}); both networks in one "
+                    "engine, two tower launches per round", 9, m, steps, SA)
+    # all 1024 matches played to the end: winners
+    from alpha_omok_b200 import arena as arena_mod, replay
+    eng.arena_begin(M, first_key=5000, matches_per_slot=1, keep_records=True)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        f0.record(stream)
+        st = eng.selfplay_rounds(SA)
+        while st["running"]:
+            st = eng.selfplay_rounds(SA)
+        f1.record(stream)
+    torch.cuda.synchronize()
+    recs = arena_mod.decode_match_records(replay.device_stream_records(eng), 9)
+    outc = [r["outcome"] for r in recs]
+    leg["full_matches"] = {"matches": M, "seconds": f0.elapsed_time(f1) * 1e-3, "expansions_per_s": st["sims"] / (f0.elapsed_time(f1) * 1e-3),
+                           "player_win": outc.count("player"), "enemy_win": outc.count("enemy"), "draw": outc.count("draw"),
+                           "mean_plies": float(np.mean([len(r["moves"]) for r in recs])), "tree_overflows": st["errors"]}
+    legs["arena"] = leg
+    eng.close()
+    return legs
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -307,6 +427,12 @@ def run_ours(a):
                     allgather_ok=bool(torch.equal(gathered[rank * G:(rank + 1) * G], local)))
         del gathered
 
+    eng.close()
+    # ---------------- the other BASELINE configs (N = 1 only; extra keys, the headline above is unchanged)
+    legs = None
+    if world == 1 and not a.no_legs:
+        legs = run_legs(a, local, stream, _cabi)
+
     # ---------------- reduce over ranks
     t = torch.tensor([ms, float(sims), float(evals), float(moves), float(games_done), tower_ms, tree_ms,
                       float(launches), e2e["ms"] if e2e else 0.0, float(e2e["sims"]) if e2e else 0.0,
@@ -358,16 +484,13 @@ def run_ours(a):
             line["replay_allgather"] = {"ms": ag_ms_max, "bytes_gathered_per_rank": full["allgather_bytes"],
                                         "records": "pack kernel + NCCL all_gather_into_tensor of fixed-size record slabs",
                                         "verified_own_shard": bool(tot[15] == world)}
+        if legs is not None:
+            line["legs"] = legs
         if not a.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            workers = max(1, min(cores, 64))
-            v, n, el = cpu_oracle_throughput(B, S, a.cpu_seconds, workers)
-            line["cpu_baseline"] = {"value": v, "unit": "expansions/s", "cores": workers, "kind": "port",
-                                    "sample": f"{workers} single-thread workers x {a.cpu_seconds:.0f} s of the oracle port's simulation loop "
-                                              f"(first move, {B}x{B}, {S} sims budget, torch CPU fp32 PVNet); host has {cores} cpus"}
+            cores, workers = host_workers()
+            line["cpu_baseline"] = cpu_baseline_block(B, S, cores, workers)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

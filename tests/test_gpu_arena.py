@@ -182,19 +182,18 @@ def test_evaluator_dropin_vs_oracle_arena(cabi, monkeypatch):
 
     class Side(O.OracleZeroAgent):  # facade agents take decision-stream key = episode number (bumped by reset())
         def __init__(self, hs):
-            self.episode = 0
             super().__init__(B, sims, lambda mv: synth_eval(mv, A), O.DecisionStream(seed, 0), noise=False)
             self.host_stream = hs
+            self.episode = 0
 
         def reset(self):
             super().reset()
-            if hasattr(self, "episode"):
+            if hasattr(self, "episode"):  # not during __init__
                 self.episode += 1
                 self.stream = O.DecisionStream(seed, self.episode)
 
     hs = O.DecisionStream(777, 0)
     p, e = Side(hs), Side(hs)
-    p.episode = e.episode = 0
     ora = O.arena_matches(B, p, e, 2)
     flat = [(mv, v, rr, who) for m in ora for mv, v, rr, who in zip(m["moves"], m["visits"], m["real_root"], m["movers"])]
     assert len(flat) == len(log)

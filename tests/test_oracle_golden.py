@@ -136,3 +136,17 @@ def test_env_step_semantics():
     assert valid and win == 0 and turn == 1 and a == 40 and board[4, 4] == 1
     board, valid, win, turn, a = env.step(onehot)  # occupied: flagged invalid but overwritten (env_small.py:161-176)
     assert not valid and board[4, 4] == -1 and turn == 0
+
+
+def test_reference_copy_reproduces_config1_and_the_oracle():
+    """oracle/_ref (the unmodified reference assembled by oracle/make_ref.py - what bench.py times as the CPU baseline)
+    plays BASELINE config 1 to the survey's golden result (39 moves, black wins, 1561 simulations, visit-count hash
+    ceddffce5bfb2897) and its files are byte-identical to the recorded upstream hashes"""
+    from oracle import make_ref, ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref not assembled (needs /root/reference: python oracle/make_ref.py)")
+    assert make_ref.verify()
+    r = ref_runner.run_config1_subprocess(threads=4)
+    assert r["kind"] == "reference"
+    assert (r["moves"], r["winner"], r["sims"]) == (39, 1, 1561)
+    assert r["visit_sha256_16"] == "ceddffce5bfb2897"
