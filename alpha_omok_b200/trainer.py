@@ -61,10 +61,92 @@ def train_step(net, optimizer, s_batch, pi_batch, z_batch, group=None):
     return loss.item(), v_loss.item(), p_loss.item()
 
 
-def train_batches(net, optimizer, states, pis, zs, batch_size=32, n_epochs=1, group=None, batch_sizes=None):
+class GraphedTrainStep:
+    """main.py:286-305 (forward in train-mode BN, loss, backward, Adam step) for ONE fixed batch size, captured once
+    into a CUDA graph and replayed: at batch 32 the eager step is ~400 tiny kernels and entirely launch-bound
+    (5.7 ms/step on a B200 in round 1); replaying the same kernels from a graph removes the host from the loop.
+    The arithmetic is the eager step's, kernel for kernel; only Adam's bias correction is evaluated on the device
+    (`capturable=True`) instead of in Python floats.  Losses stay on the device until `losses()` is called.
+
+    Capture needs warm-up iterations on real memory; they run on the static buffers and every bit of state they touch
+    (parameters, BatchNorm statistics, Adam moments and step counters) is put back afterwards, so a graphed run performs
+    exactly the optimizer steps an eager run performs."""
+
+    def __init__(self, net, optimizer, batch_size, board_size, inplanes=5, capacity=4096):
+        dev = next(net.parameters()).device
+        assert dev.type == "cuda", "CUDA graphs need the model on a GPU"
+        A = board_size * board_size
+        self.net, self.opt, self.bs = net, optimizer, batch_size
+        for g in optimizer.param_groups:
+            g["capturable"] = True
+        self.s = torch.zeros((batch_size, inplanes, board_size, board_size), device=dev)
+        self.pi = torch.full((batch_size, A), 1.0 / A, device=dev)
+        self.z = torch.zeros((batch_size,), device=dev)
+        self.out = torch.zeros(3, device=dev)
+        self.log = torch.zeros((capacity, 3), device=dev)
+        self.n = 0
+        model_snap = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        opt_snap = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                    for p, st in optimizer.state.items()}
+        net.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                optimizer.zero_grad(set_to_none=True)
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self._body()
+        # undo the warm-up / capture iterations in place (the graph holds the addresses of all of these tensors)
+        with torch.no_grad():
+            for k, v in net.state_dict().items():
+                v.copy_(model_snap[k])
+            for p, st in optimizer.state.items():
+                old = opt_snap.get(id(p))
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()
+        torch.cuda.synchronize(dev)
+
+    def _body(self):
+        p_batch, v_batch = self.net(self.s)
+        v_loss = (v_batch - self.z).pow(2).mean()
+        p_loss = -(self.pi * p_batch.log()).sum(dim=-1).mean()
+        loss = v_loss + p_loss
+        loss.backward()
+        self.opt.step()
+        self.out.copy_(torch.stack((loss.detach(), v_loss.detach(), p_loss.detach())))
+
+    def step(self, s_batch, pi_batch, z_batch):
+        assert s_batch.shape[0] == self.bs
+        if self.n == self.log.shape[0]:
+            self.log = torch.cat((self.log, torch.zeros_like(self.log)))
+        self.s.copy_(s_batch)
+        self.pi.copy_(pi_batch)
+        self.z.copy_(z_batch)
+        self.graph.replay()
+        self.log[self.n].copy_(self.out)
+        self.n += 1
+
+    def losses(self):
+        """(loss, v_loss, p_loss) of every step since the last call, as Python floats (one device sync)"""
+        out = [tuple(r) for r in self.log[:self.n].cpu().tolist()]
+        self.n = 0
+        return out
+
+
+def train_batches(net, optimizer, states, pis, zs, batch_size=32, n_epochs=1, group=None, batch_sizes=None,
+                  graphed=None):
     """main.py:253-336 for an already sampled train_memory given as tensors [N,5,B,B], [N,A], [N]:
     `DataLoader(train_memory, batch_size=BATCH_SIZE, shuffle=False)` = consecutive slices, a short last batch kept.
-    `batch_sizes` (optional) gives the row count of every consecutive batch explicitly (multi-rank shards)."""
+    `batch_sizes` (optional) gives the row count of every consecutive batch explicitly (multi-rank shards).
+    `graphed`: a GraphedTrainStep for full batches (single-rank CUDA runs); other batch sizes run eagerly."""
     net.train()
     dev = next(net.parameters()).device
     states, pis, zs = states.to(dev).float(), pis.to(dev).float(), zs.to(dev).float()
@@ -76,8 +158,15 @@ def train_batches(net, optimizer, states, pis, zs, batch_size=32, n_epochs=1, gr
     for _ in range(n_epochs):
         i = 0
         for b in batch_sizes:
-            log.append(train_step(net, optimizer, states[i:i + b], pis[i:i + b], zs[i:i + b], group))
+            if graphed is not None and b == graphed.bs:
+                graphed.step(states[i:i + b], pis[i:i + b], zs[i:i + b])
+                log.append(None)  # filled in below, in order
+            else:
+                log.append(train_step(net, optimizer, states[i:i + b], pis[i:i + b], zs[i:i + b], group))
             i += b
+    if graphed is not None:
+        it = iter(graphed.losses())
+        log = [x if x is not None else next(it) for x in log]
     return log
 
 
@@ -147,7 +236,7 @@ class Trainer:
 
     def __init__(self, board_size=9, n_mcts=400, tau_thres=6, seed=0, n_blocks=10, in_planes=5, out_planes=128,
                  n_selfplay=100, memory_size=30000, n_epochs=1, batch_size=32, lr=2e-4, l2=0.0, device=None,
-                 data_dir="data", group=None, max_slots=4096, nn_precision="auto"):
+                 data_dir="data", group=None, max_slots=4096, nn_precision="auto", graph_train=True):
         self.BOARD_SIZE, self.N_MCTS, self.TAU_THRES, self.SEED = board_size, n_mcts, tau_thres, seed
         self.N_BLOCKS, self.IN_PLANES, self.OUT_PLANES = n_blocks, in_planes, out_planes
         self.N_SELFPLAY, self.MEMORY_SIZE, self.N_EPOCHS, self.BATCH_SIZE = n_selfplay, memory_size, n_epochs, batch_size
@@ -170,6 +259,8 @@ class Trainer:
         self.result = {"Black": 0, "White": 0, "Draw": 0}
         self._engine = None
         self._episodes = 0
+        self.graph_train = graph_train  # replay the batch-32 training step from a CUDA graph (single rank)
+        self._graphed = None
 
     # ---------------------------------------------------------------- self-play (main.py:122-250)
     def self_play(self, n_selfplay=None):
@@ -233,8 +324,10 @@ class Trainer:
             if cnt[0].item() != -cnt[1].item():
                 raise RuntimeError("ranks disagree on the number of training batches")
         s, pi, z = self.rep_memory.gather(idx)
+        if self.graph_train and self.world == 1 and self.device.type == "cuda" and self._graphed is None:
+            self._graphed = GraphedTrainStep(self.model, self.optimizer, self.BATCH_SIZE, self.BOARD_SIZE, self.IN_PLANES)
         log = train_batches(self.model, self.optimizer, s, pi, z, self.BATCH_SIZE // self.world,
-                            n_epochs or self.N_EPOCHS, self.group, batch_sizes=sizes)
+                            n_epochs or self.N_EPOCHS, self.group, batch_sizes=sizes, graphed=self._graphed)
         self.step += len(log)
         self.total_epoch += n_epochs or self.N_EPOCHS
         if log:

@@ -417,14 +417,14 @@ def run_ours(a):
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            local = replay.device_records(eng, G)          # pack kernel on the engine stream (synchronised inside)
-            gathered = replay.allgather_records(local)     # NCCL all_gather_into_tensor of the fixed-size slabs
+            own = replay.device_records(eng, G)            # pack kernel on the engine stream (synchronised inside)
+            gathered = replay.allgather_records(own)       # NCCL all_gather_into_tensor of the fixed-size slabs
             g1.record()
             torch.cuda.synchronize()
             if not timed:
                 del gathered
         full.update(allgather_ms=g0.elapsed_time(g1), allgather_bytes=int(gathered.numel()),
-                    allgather_ok=bool(torch.equal(gathered[rank * G:(rank + 1) * G], local)))
+                    allgather_ok=bool(torch.equal(gathered[rank * G:(rank + 1) * G], own)))
         del gathered
 
     eng.close()

@@ -255,3 +255,38 @@ def test_self_play_facade_continuous_mode_equals_batch_mode():
     assert ra == rb and len(a) == len(b) > 14 * 9
     for (s1, p1, z1), (s2, p2, z2) in zip(a, b):
         assert np.array_equal(s1, s2) and np.array_equal(p1, p2) and z1 == z2
+
+
+def test_graphed_train_step_equals_eager_step():
+    """trainer.GraphedTrainStep (the batch-32 training step of main.py:286-305 replayed from a CUDA graph) performs the
+    same optimizer steps as the eager `train_step` that tests/test_trainer_host.py pins against the reference: same
+    losses step by step and the same weights afterwards; the warm-up / capture iterations leave no trace."""
+    from helpers import load
+    from alpha_omok_b200 import model, trainer
+    fx = load("train_9_small")
+    dev = torch.device("cuda", 0)
+    s = torch.from_numpy(fx["states"][:64]).to(dev)
+    pi = torch.from_numpy(fx["pis"][:64]).float().to(dev)
+    z = torch.from_numpy(fx["zs"][:64]).float().to(dev)
+    sd = pvnet_ref.make_state_dict(int(fx["sd_seed"]), int(fx["n_block"]), 5, 128, 9, bn_jitter=True)
+    runs = []
+    for graphed in (False, True):
+        net = model.PVNet(int(fx["n_block"]), 5, 128, 9).to(dev)
+        net.load_state_dict(sd, strict=False)
+        opt = trainer.make_optimizer(net)
+        g = trainer.GraphedTrainStep(net, opt, 32, 9) if graphed else None
+        if graphed:  # capture must not have moved anything
+            for k, v in net.state_dict().items():
+                if k in sd:
+                    assert torch.equal(v.cpu(), sd[k]), k
+        log = trainer.train_batches(net, opt, s, pi, z, batch_size=32, n_epochs=3, graphed=g)
+        runs.append((np.asarray(log), {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}))
+    (le, we), (lg, wg) = runs
+    assert le.shape == lg.shape == (6, 3)
+    np.testing.assert_allclose(lg, le, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(le[:2], fx["losses"][:2], rtol=1e-4, atol=1e-5)   # the reference's own first two steps
+    for k in we:
+        if we[k].is_floating_point():
+            np.testing.assert_allclose(wg[k].numpy(), we[k].numpy(), rtol=2e-4, atol=2e-6, err_msg=k)
+        else:
+            assert torch.equal(wg[k], we[k]), k      # num_batches_tracked: 6 steps, not 6 + warm-up
