@@ -572,3 +572,144 @@ def arena_matches(board_size, player, enemy, n_match, forced=None, player_black_
         player.reset()
         enemy.reset()
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# PUCTAgent / UCTAgent (agents.py:263-634): pure-MCTS baselines with random rollouts, selectable as arena sides by
+# string in eval_main.py:67-84.  Both rebuild their tree on every get_pi (`_init_mcts` overwrites the root with n = 0,
+# so the first simulation re-creates all children), run num_mcts + 1 simulations, keep every statistic in Python
+# floats (float64) and evaluate a non-root leaf by one uniformly random play-out.
+# --------------------------------------------------------------------------------------------------------------
+def valid_actions(board: np.ndarray) -> list:
+    """utils.py:8-19 - empty cells in ascending index order."""
+    return [int(i) for i in np.flatnonzero(board.reshape(-1) == 0)]
+
+
+def get_reward(win_index: int, leaf_id) -> float:
+    """utils.py:208-223."""
+    turn = get_turn(leaf_id)
+    if win_index == 1:
+        return 1.0 if turn == 1 else -1.0
+    if win_index == 2:
+        return -1.0 if turn == 1 else 1.0
+    return 0.0
+
+
+class _RNode:
+    __slots__ = ("acts", "n", "w", "child")
+
+    def __init__(self, acts):
+        self.acts = list(acts)
+        self.n = [0.0] * len(acts)
+        self.w = [0.0] * len(acts)
+        self.child = [-1] * len(acts)
+
+
+class OracleRolloutAgent:
+    """kind = 'puct' (agents.py:263-453: uniform prior, u = c_puct * p * sqrt(sum n) / (n + 1), move = most visited
+    child) or 'uct' (agents.py:456-634: u = inf for unvisited children else sqrt(2 ln(sum n) / n), move = child with the
+    largest q, unvisited children counting as q = 0)."""
+
+    def __init__(self, kind, board_size, num_mcts, stream: DecisionStream):
+        assert kind in ("puct", "uct")
+        self.kind, self.B, self.A, self.num_mcts = kind, board_size, board_size * board_size, num_mcts
+        self.win_mark = 3 if board_size == 3 else 5
+        self.c_puct = 5
+        self.stream = stream
+        self.root_id = None
+        self.visit = np.zeros(self.A)
+        self.q = np.zeros(self.A)
+        self.is_real_root = True
+        self.rollout_moves = 0
+
+    def reset(self):
+        self.root_id = None
+
+    def _simulate(self, st):
+        nodes = st["nodes"]
+        moves = list(self.root_id)
+        path = []
+        node = st["root_node"]
+        win = 0
+        leaf_is_root = True
+        if st["root_n"] > 0:
+            while True:  # node has n > 0: it was expanded (or is terminal)
+                win = check_win(get_board(tuple(moves), self.B), self.win_mark)
+                if win != 0:
+                    break
+                nd = nodes[node]
+                total_n = 0.0
+                for x in nd.n:
+                    total_n += x
+                best, ties = None, []
+                for i in range(len(nd.acts)):
+                    q = nd.w[i] / nd.n[i] if nd.n[i] > 0 else 0.0
+                    if self.kind == "puct":
+                        u = self.c_puct * (1 / len(nd.acts)) * np.sqrt(total_n) / (nd.n[i] + 1)
+                    else:
+                        u = np.inf if nd.n[i] == 0 else np.sqrt(2 * np.log(total_n) / nd.n[i])
+                    v = q + u
+                    if best is None or v > best:
+                        best, ties = v, [i]
+                    elif v == best:
+                        ties.append(i)
+                i = ties[self.stream.choice(len(ties))]
+                path.append((node, i))
+                moves.append(nd.acts[i])
+                leaf_is_root = False
+                if nd.n[i] == 0:
+                    win = check_win(get_board(tuple(moves), self.B), self.win_mark)
+                    node = -1
+                    break
+                node = nd.child[i]
+        leaf_id = tuple(moves)
+        if win == 0:
+            board = get_board(leaf_id, self.B)
+            nodes.append(_RNode(valid_actions(board)))
+            if leaf_is_root:
+                st["root_node"] = len(nodes) - 1
+                reward = 0.0  # "root node don't simulation"
+            else:
+                pn, pi_ = path[-1]
+                nodes[pn].child[pi_] = len(nodes) - 1
+                turn_sim = get_turn(leaf_id)
+                while True:  # uniformly random play-out (agents.py:391-411)
+                    acts = valid_actions(board)
+                    a = acts[self.stream.choice(len(acts))]
+                    board[a // self.B, a % self.B] = 1.0 if turn_sim == 0 else -1.0
+                    self.rollout_moves += 1
+                    w = check_win(board, self.win_mark)
+                    if w == 0:
+                        turn_sim = abs(turn_sim - 1)
+                    else:
+                        reward = get_reward(w, leaf_id)
+                        break
+        else:
+            reward = 1.0  # "terminal node don't expansion"
+        sign = 1.0
+        for pn, pi_ in reversed(path):
+            nodes[pn].n[pi_] += 1
+            nodes[pn].w[pi_] += reward * sign
+            sign = -sign
+        st["root_n"] += 1
+        st["root_w"] += reward * sign
+
+    def get_pi(self, root_id, tau=0):
+        """get_pi(root_id, board, turn, tau) of the reference: board and turn follow from root_id"""
+        self.root_id = tuple(root_id)
+        st = dict(nodes=[], root_node=-1, root_n=0.0, root_w=0.0)
+        for _ in range(self.num_mcts + 1):
+            self._simulate(st)
+        visit = np.zeros(self.A)
+        q = np.ones(self.A) * -np.inf
+        if st["root_node"] >= 0:
+            nd = st["nodes"][st["root_node"]]
+            for i, a in enumerate(nd.acts):
+                visit[a] = nd.n[i]
+                q[a] = nd.w[i] / nd.n[i] if nd.n[i] > 0 else 0.0
+        self.visit, self.q = visit, q
+        score = visit if self.kind == "puct" else q
+        idx = np.flatnonzero(score == score.max())
+        pi = np.zeros(self.A)
+        pi[idx[(getattr(self, "host_stream", None) or self.stream).choice(len(idx))]] = 1
+        return pi
