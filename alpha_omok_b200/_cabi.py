@@ -13,6 +13,8 @@ from . import _build
 AO_EVAL_PVNET, AO_EVAL_SYNTH = 0, 1
 AO_NOISE_DEVICE, AO_NOISE_TAPE = 0, 1
 AO_NN_FP16, AO_NN_FP16X3, AO_NN_FP16_1CTA, AO_NN_FP16_LOCKSTEP = 0, 1, 2, 3
+AO_SIDE_ZERO, AO_SIDE_RANDOM, AO_SIDE_PUCT, AO_SIDE_UCT = 0, 1, 2, 3
+SIDE_KINDS = {"zero": AO_SIDE_ZERO, "random": AO_SIDE_RANDOM, "puct": AO_SIDE_PUCT, "uct": AO_SIDE_UCT}
 
 
 class AoConfig(C.Structure):
@@ -32,7 +34,8 @@ EXPORTS = [  # every symbol include/alpha_omok_b200.h declares (checked by tests
     "ao_launch_count", "ao_set_nn_precision", "ao_selfplay_fetch", "ao_get_nn_log", "ao_records_dev",
     "ao_records_pack", "ao_augment_records_dev", "ao_replay_extend_dev", "ao_replay_gather_dev", "ao_synchronize",
     "ao_check_win", "ao_encode_state", "ao_legal_actions",
-    "ao_load_weights_set", "ao_nn_forward_set", "ao_set_nn_precision_set", "ao_arena_begin",
+    "ao_load_weights_set", "ao_nn_forward_set", "ao_set_nn_precision_set", "ao_arena_begin", "ao_rollout_search",
+    "ao_set_log_table",
 ]
 PROBE_EXPORTS = ["ao_tower_debug", "ao_umma_probe", "ao_umma_probe_masked", "ao_umma_rate"]  # alpha_omok_b200_probe.h
 
@@ -52,7 +55,9 @@ def _bind(L):
     L.ao_load_weights_set.argtypes = [vp, i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_int64)]
     L.ao_nn_forward_set.argtypes = [vp, i32, vp, i32, vp, vp]
     L.ao_set_nn_precision_set.argtypes = [vp, i32, i32]
-    L.ao_arena_begin.argtypes = [vp, i32, u32, i32, i32, i32, i32, i32]
+    L.ao_arena_begin.argtypes = [vp, i32, u32, i32, i32, i32, i32, i32, i32]
+    L.ao_rollout_search.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp]
+    L.ao_set_log_table.argtypes = [vp, vp, i32]
     L.ao_games_reset.argtypes = [vp, vp, i32, vp]
     L.ao_set_gamma_tape.argtypes = [vp, i32, vp, i32]
     L.ao_search.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
@@ -266,10 +271,41 @@ class Engine:
         return p, v
 
     def arena_begin(self, n_slots, first_key=0, matches_per_slot=1, enemy_random=False, keep_records=True,
-                    n_mcts_player=0, n_mcts_enemy=0):
-        """eval_main.main's match loop on the device (ao_arena_begin); drive with selfplay_rounds()"""
-        check(lib().ao_arena_begin(self._h, n_slots, first_key, matches_per_slot, int(bool(enemy_random)),
-                                   int(bool(keep_records)), n_mcts_player, n_mcts_enemy))
+                    n_mcts_player=0, n_mcts_enemy=0, player_kind="zero", enemy_kind=None):
+        """eval_main.main's match loop on the device (ao_arena_begin); drive with selfplay_rounds().
+        player_kind / enemy_kind: 'zero' | 'random' | 'puct' | 'uct' (eval_main.py:67-84)."""
+        if enemy_kind is None:
+            enemy_kind = "random" if enemy_random else "zero"
+        pk, ek = SIDE_KINDS[player_kind], SIDE_KINDS[enemy_kind]
+        if AO_SIDE_UCT in (pk, ek):
+            self.ensure_log_table(max(n_mcts_player or self.num_mcts, n_mcts_enemy or self.num_mcts) + 2)
+        check(lib().ao_arena_begin(self._h, n_slots, first_key, matches_per_slot, pk, ek, int(bool(keep_records)),
+                                   n_mcts_player, n_mcts_enemy))
+
+    def ensure_log_table(self, n):
+        """UCT's log(sum n) values, computed by THIS numpy one scalar at a time like agents.py:556 does"""
+        if getattr(self, "_log_n", 0) >= n:
+            return
+        n = max(n, 1024)
+        with np.errstate(divide="ignore"):
+            tab = np.asarray([float(np.log(float(k))) for k in range(n)], np.float64)
+        tab[0] = 0.0
+        check(lib().ao_set_log_table(self._h, ptr(tab), n))
+        self._log_n = n
+
+    def rollout_search(self, kind, game_ids, root_ids, num_mcts=0):
+        """PUCTAgent / UCTAgent search (fresh tree, num_mcts + 1 simulations with random play-outs)
+        -> visits uint32 [n][A], w float32 [n][A] of the root's children"""
+        k = SIDE_KINDS[kind]
+        if k == AO_SIDE_UCT:
+            self.ensure_log_table((num_mcts or self.num_mcts) + 2)
+        ids = np.ascontiguousarray(game_ids, np.int32)
+        roots, lens = pad_ids(root_ids, self.A)
+        n = len(ids)
+        visits = np.empty((n, self.A), np.uint32)
+        w = np.empty((n, self.A), np.float32)
+        check(lib().ao_rollout_search(self._h, k, ptr(ids), n, ptr(roots), ptr(lens), num_mcts, ptr(visits), ptr(w)))
+        return visits, w
 
     def selfplay_begin(self, n_games, first_key=0, recycle=False):
         check(lib().ao_selfplay_begin_mode(self._h, n_games, first_key, int(recycle)))

@@ -156,6 +156,88 @@ class RandomAgent(Agent):
         return None
 
 
+class _RolloutAgent(Agent):
+    """Shared body of PUCTAgent / UCTAgent (agents.py:263-634): pure MCTS with uniformly random play-outs, no network.
+    Same constructor and `get_pi(root_id, board, turn, tau)` as the reference; the search (a fresh tree and
+    num_mcts + 1 simulations per call) runs in csrc/rollout.cuh through `ao_rollout_search`, the final arg-max with its
+    tie-break is the reference's own numpy code."""
+
+    kind = None
+
+    def __init__(self, board_size, num_mcts, seed=0, engine_kwargs=None):
+        super(_RolloutAgent, self).__init__(board_size)
+        self.board_size = board_size
+        self.num_mcts = num_mcts
+        self.win_mark = 3 if board_size == 3 else 5
+        self.c_puct = 5
+        self.root_id = None
+        self.board = None
+        self.turn = None
+        self.is_real_root = True
+        self._seed = seed
+        self._engine_kwargs = dict(engine_kwargs or {})
+        self._engine = None
+        self._episode = 0
+
+    def _ensure_engine(self):
+        if self._engine is None:
+            kw = dict(self._engine_kwargs)
+            kw.setdefault("device", _cabi.default_device())
+            kw.setdefault("eval_mode", _cabi.AO_EVAL_SYNTH)  # no network on this path
+            self._engine = _cabi.Engine(board_size=self.board_size, num_mcts=self.num_mcts, max_games=1, noise=False,
+                                        seed=self._seed, node_cap=max(2048, self.num_mcts + 8), **kw)
+            self._engine.games_reset([0], keys=[self._episode])
+        return self._engine
+
+    def reset(self):
+        self.is_real_root = True
+        self.root_id = None
+        self.board = None
+        self.turn = None
+        self._episode += 1
+        if self._engine is not None:
+            self._engine.games_reset([0], keys=[self._episode])
+
+    def _search(self, root_id, board, turn):
+        self.root_id, self.board, self.turn = tuple(int(a) for a in root_id), board, turn
+        visits, w = self._ensure_engine().rollout_search(self.kind, [0], [self.root_id], self.num_mcts)
+        self.visit = visits[0].astype("float")
+        self.message = "simulation: {}\r".format(self.num_mcts + 1)
+        return self.visit, w[0].astype("float")
+
+    def del_parents(self, root_id):
+        return None  # every get_pi rebuilds the tree (`_init_mcts` overwrites the root): nothing is kept
+
+
+class PUCTAgent(_RolloutAgent):
+    """agents.py:263-453"""
+    kind = "puct"
+
+    def get_pi(self, root_id, board, turn, tau):
+        visit, _ = self._search(root_id, board, turn)
+        pi = np.zeros(self.board_size ** 2, "float")
+        max_idx = np.argwhere(visit == visit.max())
+        pi[max_idx[np.random.choice(len(max_idx))]] = 1     # agents.py:293-294
+        return pi
+
+
+class UCTAgent(_RolloutAgent):
+    """agents.py:456-634"""
+    kind = "uct"
+
+    def get_pi(self, root_id, board, turn, tau):
+        visit, w = self._search(root_id, board, turn)
+        q = np.ones(self.board_size ** 2, "float") * -np.inf
+        occupied = set(self.root_id[1:])
+        for a in range(self.board_size ** 2):
+            if a not in occupied:                            # the root's children (agents.py:469-471)
+                q[a] = w[a] / visit[a] if visit[a] > 0 else 0.0
+        pi = np.zeros(self.board_size ** 2, "float")
+        max_idx = np.argwhere(q == q.max())
+        pi[max_idx[np.random.choice(len(max_idx))]] = 1     # agents.py:473-474
+        return pi
+
+
 class BatchedZeroAgent(_EngineOwner):
     """get_pi for many independent games per call (slot g of the engine = game g).
 

@@ -67,7 +67,8 @@ def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, n
     """`n_matches` concurrent runs of eval_main.main's match loop (eval_main.py:204-333), each `matches_per_slot`
     matches long, entirely on the device (ao_arena_begin): the match loop, both sides' trees and both networks live in
     one engine, the two towers run back to back every round.
-    player: ZeroAgent(player_model). enemy: 'zero' -> ZeroAgent(enemy_model), 'random' -> RandomAgent.
+    player: ZeroAgent(player_model). enemy: 'zero' -> ZeroAgent(enemy_model), 'random' -> RandomAgent, 'puct' / 'uct'
+    -> PUCTAgent / UCTAgent(num_mcts_enemy) (eval_main.py:67-84).
     `player_model` / `enemy_model`: nn.Module with the reference's parameter names, or a state_dict (then pass
     engine_kwargs=dict(n_blocks=...) if it is not a 10-block net).
     Returns dict(player_win, enemy_win, draw, black_win, white_win, plies, unfinished, player_elo, enemy_elo, winrate
@@ -96,9 +97,8 @@ def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, n
                     eng.choose_nn_precision(which=1)
                 else:
                     eng.set_nn_precision(nn_precision, which=1)
-        eng.arena_begin(n_matches, first_key=first_key, matches_per_slot=matches_per_slot,
-                        enemy_random=(enemy == "random"), keep_records=True, n_mcts_player=num_mcts,
-                        n_mcts_enemy=num_mcts_enemy or num_mcts)
+        eng.arena_begin(n_matches, first_key=first_key, matches_per_slot=matches_per_slot, enemy_kind=enemy,
+                        keep_records=True, n_mcts_player=num_mcts, n_mcts_enemy=num_mcts_enemy or num_mcts)
         st = eng.selfplay_rounds(rounds_per_call)
         rounds = rounds_per_call
         while st["running"] and (max_rounds is None or rounds < max_rounds):
@@ -135,8 +135,9 @@ def play_matches(player_model, enemy_model=None, n_matches=1024, board_size=9, n
 # one match at a time through the reference-shaped single-game agents (each ZeroAgent = a batch of 1 on the device).
 class Evaluator(object):
     """eval_main.py:54-188.  `set_agents(player, enemy, monitor)`: each argument is 'random' or a checkpoint path
-    (-> ZeroAgent(noise=False) + PVNet with the reference's tolerant key-by-key load); 'puct' / 'uct' / 'human' / 'web'
-    name agents that are out of this repository's scope and raise NotImplementedError."""
+    (-> ZeroAgent(noise=False) + PVNet with the reference's tolerant key-by-key load), 'puct' / 'uct' (the play-out
+    agents of agents.py:263-634, searched on the device too); 'human' / 'web' are interactive I/O and raise
+    NotImplementedError."""
 
     def __init__(self, board_size=9, n_mcts_player=800, n_mcts_enemy=800, n_mcts_monitor=800, n_blocks=10,
                  in_planes=5, out_planes=128, engine_kwargs=None):
@@ -152,8 +153,12 @@ class Evaluator(object):
         from . import model
         if path == "random":
             return agents.RandomAgent(self.board_size)
-        if path in ("puct", "uct", "human", "web"):
-            raise NotImplementedError("agent '%s' (rollout / interactive) is outside the accelerated path" % path)
+        if path == "puct":
+            return agents.PUCTAgent(self.board_size, self.n_mcts[role], engine_kwargs=self.engine_kwargs)
+        if path == "uct":
+            return agents.UCTAgent(self.board_size, self.n_mcts[role], engine_kwargs=self.engine_kwargs)
+        if path in ("human", "web"):
+            raise NotImplementedError("agent '%s' (interactive pygame / Flask input) is outside the accelerated path" % path)
         agent = agents.ZeroAgent(self.board_size, self.n_mcts[role], self.in_planes, noise=False,
                                  engine_kwargs=self.engine_kwargs)
         agent.model = model.PVNet(self.n_blocks, self.in_planes, self.out_planes, self.board_size)
@@ -192,27 +197,55 @@ class Evaluator(object):
         self.enemy.reset()
 
 
-def run_matches(evaluator, n_match=12, verbose=False):
-    """eval_main.main (eval_main.py:204-333) minus the dashboard objects: alternating colours, the opponent's tree
-    pruned after every move (`del_parents`), ELO and win-rate bookkeeping.  Returns (result, player_elo, enemy_elo)."""
+def run_matches(evaluator, n_match=12, verbose=False, dashboard=None):
+    """eval_main.main (eval_main.py:204-333): alternating colours, the opponent's tree pruned after every move
+    (`del_parents`), ELO and win-rate bookkeeping.  `dashboard` (an `info.Dashboard`) receives the updates the
+    reference makes to webapi's game_info / player_agent_info / enemy_agent_info at the same points of the loop, so a
+    web front end polling `dashboard.periodic_status()` sees what the reference's would.
+    Returns (result, player_elo, enemy_elo)."""
     B = evaluator.board_size
     env = evaluator.return_env()
     result = {"Player": 0, "Enemy": 0, "Draw": 0}
     turn, enemy_turn = 0, 1
     player_elo, enemy_elo = 1500, 1500
+    gi = pi_ = ei = None
+    if dashboard is not None:
+        gi, pi_, ei = dashboard.game_info, dashboard.player_agent_info, dashboard.enemy_agent_info
+        pi_.agent, ei.agent = evaluator.player, evaluator.enemy      # eval_main.py:206-207
+        gi.enemy_turn, gi.game_status = enemy_turn, 0                # :221-222
+    interactive = ()                                                 # HumanAgent / WebAgent: not built here
     for i in range(n_match):
         board = np.zeros([B, B])
         root_id, win_index, action_index = (0,), 0, None
+        if gi is not None:
+            gi.game_board, gi.game_status = board, 0                 # :230, :236
         while win_index == 0:
             if verbose:
                 utils.render_str(board, B, action_index)
-            evaluator.monitor.get_pv(root_id)
+            p, v = evaluator.monitor.get_pv(root_id)
             action, action_index = evaluator.get_action(root_id, board, turn, enemy_turn)
             mover = evaluator.player if turn != enemy_turn else evaluator.enemy
             root_id = (mover.root_id if mover.root_id is not None else root_id) + (int(action_index),)
             board, _, win_index, turn, _ = env.step(action)
-            (evaluator.enemy if turn == enemy_turn else evaluator.player).del_parents(root_id)
+            if gi is not None:                                       # :259-262
+                gi.game_board, gi.action_index, gi.win_index, gi.curr_turn = board, int(action_index), win_index, turn
+            move = np.count_nonzero(board)
+            if turn == enemy_turn:                                   # the player just moved (:266-277)
+                if pi_ is not None:
+                    src = evaluator.monitor if isinstance(evaluator.player, interactive) else evaluator.player
+                    pi_.visit, pi_.p = src.get_visit(), src.get_policy()
+                    pi_.add_value(move, v)
+                evaluator.enemy.del_parents(root_id)
+            else:                                                    # the enemy just moved (:279-283)
+                if ei is not None:
+                    ei.visit, ei.p = evaluator.enemy.get_visit(), evaluator.enemy.get_policy()
+                    ei.add_value(move, v)
+                evaluator.player.del_parents(root_id)
             if win_index != 0:
+                if pi_ is not None:                                  # :286-290
+                    pi_.clear_values()
+                    ei.clear_values()
+                    gi.game_status = win_index
                 if win_index == 3:
                     result["Draw"] += 1
                     player_elo, enemy_elo = elo(player_elo, enemy_elo, 0.5, 0.5)
@@ -224,5 +257,7 @@ def run_matches(evaluator, n_match=12, verbose=False):
                     player_elo, enemy_elo = elo(player_elo, enemy_elo, 0, 1)
                 enemy_turn = abs(enemy_turn - 1)      # swap colours (eval_main.py:316)
                 turn = 0
+                if gi is not None:
+                    gi.enemy_turn, gi.curr_turn = enemy_turn, turn   # :318-319
                 evaluator.reset()
     return result, player_elo, enemy_elo

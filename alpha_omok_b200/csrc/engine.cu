@@ -100,6 +100,8 @@ struct ao_engine {
   unsigned long long launches;  // kernels launched by this engine (bench's gpu_launches)
   float* d_fwd_states;          // ao_nn_forward staging (lazily allocated)
   int* d_fwd_bad;
+  float* d_wsum;                // ao_rollout_search: w of the root's children
+  int log_table_n;
 };
 
 namespace {
@@ -124,12 +126,12 @@ int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int ti
   h->launches += 1;
   if (h->cfg.eval_mode == AO_EVAL_PVNET) {
     const int M = h->tp.arena_M;
-    if (!(M > 0 && h->tp.arena_random[0])) {
+    if (!(M > 0 && h->tp.arena_kind[0] != AO_SIDE_ZERO)) {
       AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, h->tp.nn_count, n, h->tp.nn_policy,
                                h->tp.nn_value, h->num_sms, h->stream));
       h->launches += 1;
     }
-    if (M > 0 && !h->tp.arena_random[1]) {  // the enemy's requests: nn slots [M, 2M), weight set 1
+    if (M > 0 && h->tp.arena_kind[1] == AO_SIDE_ZERO) {  // the enemy's requests: nn slots [M, 2M), weight set 1
       AO_CUDA(ao::launch_tower(h->ws[1].tw, h->B, h->ws[1].precision, h->tp.nn_in + M, h->tp.nn_count + 1, n,
                                h->tp.nn_policy + (size_t)M * h->A, h->tp.nn_value + M, h->num_sms, h->stream));
       h->launches += 1;
@@ -259,6 +261,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->launches = 0;
   h->h_pinned = nullptr;
   h->d_fwd_states = nullptr; h->d_fwd_bad = nullptr;
+  h->d_wsum = nullptr; h->log_table_n = 0;
   if (cfg->stream) {
     h->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
     h->own_stream = false;
@@ -666,15 +669,20 @@ extern "C" int ao_selfplay_stream_records_dev(ao_engine* h, void** dev_ptr, size
 // Arena (eval_main.main, eval_main.py:204-333) on the device: n_slots concurrent series of `matches_per_slot` matches,
 // the player (weight set 0) against the enemy (weight set 1, or a RandomAgent), each side with its own tree and
 // decision stream, colours swapped after every match.  Driven by ao_selfplay_rounds like self-play.
-extern "C" int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int matches_per_slot, int enemy_random,
-                              int keep_records, int n_mcts_player, int n_mcts_enemy) {
+extern "C" int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int matches_per_slot, int player_kind,
+                              int enemy_kind, int keep_records, int n_mcts_player, int n_mcts_enemy) {
   if (!h) return fail(-1, "null engine");
   DeviceGuard guard(h->cfg.device);
   if (n_slots < 1 || 2 * n_slots > h->G) return fail(-1, "n_slots = %d needs max_games >= %d (one game slot per side), have %d", n_slots, 2 * n_slots, h->G);
   if (matches_per_slot < 1) return fail(-1, "matches_per_slot must be positive");
-  int rc = require_weights(h, 0);
-  if (rc) return rc;
-  if (!enemy_random && (rc = require_weights(h, 1)) != 0) return rc;
+  if (player_kind < AO_SIDE_ZERO || player_kind > AO_SIDE_UCT || enemy_kind < AO_SIDE_ZERO || enemy_kind > AO_SIDE_UCT)
+    return fail(-1, "agent kinds must be AO_SIDE_ZERO / RANDOM / PUCT / UCT");
+  int rc;
+  if (player_kind == AO_SIDE_ZERO && (rc = require_weights(h, 0)) != 0) return rc;
+  if (enemy_kind == AO_SIDE_ZERO && (rc = require_weights(h, 1)) != 0) return rc;
+  const int mcts_p = n_mcts_player > 0 ? n_mcts_player : h->cfg.num_mcts, mcts_e = n_mcts_enemy > 0 ? n_mcts_enemy : h->cfg.num_mcts;
+  if ((player_kind == AO_SIDE_UCT && h->log_table_n < mcts_p + 2) || (enemy_kind == AO_SIDE_UCT && h->log_table_n < mcts_e + 2))
+    return fail(-1, "UCT sides need ao_set_log_table with at least num_mcts + 2 entries");
   const size_t n_rec = keep_records ? (size_t)n_slots * (size_t)matches_per_slot : 0;
   if (n_rec > h->stream_capacity) {
     if (h->d_stream) cudaFree(h->d_stream);
@@ -690,16 +698,72 @@ extern "C" int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int
   tp.stream_rec_bytes = h->rec_bytes;
   tp.arena_M = n_slots;
   tp.arena_matches_per_slot = matches_per_slot;
-  tp.arena_num_mcts[0] = n_mcts_player > 0 ? n_mcts_player : h->cfg.num_mcts;
-  tp.arena_num_mcts[1] = n_mcts_enemy > 0 ? n_mcts_enemy : h->cfg.num_mcts;
-  tp.arena_random[0] = 0;
-  tp.arena_random[1] = enemy_random ? 1 : 0;
+  tp.arena_num_mcts[0] = mcts_p;
+  tp.arena_num_mcts[1] = mcts_e;
+  tp.arena_kind[0] = player_kind;
+  tp.arena_kind[1] = enemy_kind;
+  tp.rollout_sims_per_round = 8;
   tp.synth_salt[0] = 0u;
   tp.synth_salt[1] = 1u;
   AO_CUDA(ao::launch_reset_arena(tp, n_slots, first_key, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->selfplay_games = n_slots;
   h->stream_episodes = (int)n_rec;
+  return 0;
+}
+
+// log(k) for k in [0, n) exactly as the caller's numpy computes it: UCTAgent's exploration term sqrt(2 log(sum n) / n)
+// (agents.py:556) is compared for equality between children, so the device must not use a different libm.
+extern "C" int ao_set_log_table(ao_engine* h, const double* table, int n) {
+  if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
+  if (!table || n < 2) return fail(-1, "log table needs at least 2 entries");
+  double* d = nullptr;
+  int rc = ealloc(h, &d, (size_t)n);
+  if (rc) return rc;
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  AO_CUDA(cudaMemcpy(d, table, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  h->tp.log_table = d;
+  h->tp.log_table_n = n;
+  h->log_table_n = n;
+  return 0;
+}
+
+// PUCTAgent / UCTAgent.get_pi (agents.py:283-296 / 461-476) minus the final arg-max: a fresh search of num_mcts + 1
+// simulations with random play-outs for each listed slot from the given root ID.
+extern "C" int ao_rollout_search(ao_engine* h, int kind, const int32_t* game_ids, int n, const int16_t* roots,
+                                 const int32_t* root_lens, int num_mcts, uint32_t* visits, float* w) {
+  if (!h) return fail(-1, "null engine");
+  DeviceGuard guard(h->cfg.device);
+  if (kind != AO_SIDE_PUCT && kind != AO_SIDE_UCT) return fail(-1, "kind must be AO_SIDE_PUCT or AO_SIDE_UCT");
+  if (n < 1 || n > h->G) return fail(-1, "n = %d out of range 1..%d", n, h->G);
+  if (num_mcts < 1) num_mcts = h->cfg.num_mcts;
+  if (kind == AO_SIDE_UCT && h->log_table_n < num_mcts + 2) return fail(-1, "UCT needs ao_set_log_table with at least num_mcts + 2 entries");
+  const int A = h->A;
+  std::vector<uint8_t> seen((size_t)h->G, 0);
+  for (int i = 0; i < n; ++i) {
+    if (game_ids[i] < 0 || game_ids[i] >= h->G) return fail(-1, "game id %d out of range", game_ids[i]);
+    if (seen[game_ids[i]]) return fail(-1, "game id %d listed twice", game_ids[i]);
+    seen[game_ids[i]] = 1;
+    if (root_lens[i] < 1 || root_lens[i] > A) return fail(-1, "root id length %d out of range 1..%d", root_lens[i], A);
+  }
+  h->tp.arena_M = 0;
+  if (!h->d_wsum) {
+    int rc = ealloc(h, &h->d_wsum, (size_t)h->G * A);
+    if (rc) return rc;
+  }
+  AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(cudaMemcpyAsync(h->d_lens, root_lens, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(cudaMemcpyAsync(h->d_roots, roots, (size_t)n * (A + 1) * 2, cudaMemcpyHostToDevice, h->stream));
+  AO_CUDA(ao::launch_rollout_search(h->tp, kind, num_mcts, h->d_ids, n, h->d_roots, h->d_lens, h->d_visits, h->d_wsum, h->stream));
+  h->launches += 1;
+  if (visits) AO_CUDA(cudaMemcpyAsync(visits, h->d_visits, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (w) AO_CUDA(cudaMemcpyAsync(w, h->d_wsum, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(ao::launch_sum_counters(h->tp, h->G, h->G, h->d_counters, h->stream));
+  unsigned long long c[8];
+  AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  AO_CUDA(cudaStreamSynchronize(h->stream));
+  if (c[3] != 0) return fail(-7, "%llu game tree(s) overflowed their arena (raise node_cap)", c[3]);
   return 0;
 }
 

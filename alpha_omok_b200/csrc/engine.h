@@ -99,7 +99,10 @@ struct TreeParams {
   int arena_M;
   int arena_matches_per_slot;   // consecutive matches a slot plays (colours swapped after each, streams continue)
   int arena_num_mcts[2];        // N_MCTS_PLAYER / N_MCTS_ENEMY (eval_main.py:33-34)
-  int arena_random[2];          // side is a RandomAgent (agents.py:637-657): no tree, no network
+  int arena_kind[2];            // AO_SIDE_*: ZeroAgent | RandomAgent (agents.py:637-657) | PUCTAgent | UCTAgent (:263-634)
+  int rollout_sims_per_round;   // PUCT / UCT sides run this many play-out simulations per lock-step round
+  const double* log_table;      // log(k), k < log_table_n, as numpy computes it (UCT's exploration term)
+  int log_table_n;
   uint32_t synth_salt[2];       // AO_EVAL_SYNTH: which synthetic "network" a side uses
 };
 
@@ -144,6 +147,9 @@ cudaError_t launch_reset_games(const TreeParams& p, const int32_t* game_ids_dev,
                                int auto_play, cudaStream_t s);
 cudaError_t launch_sum_counters(const TreeParams& p, int n, int n_running, unsigned long long* out5_dev, cudaStream_t s);
 cudaError_t launch_reset_arena(const TreeParams& p, int n_slots, uint32_t first_key, cudaStream_t s);
+cudaError_t launch_rollout_search(const TreeParams& p, int kind, int num_mcts, const int32_t* game_ids_dev, int n,
+                                  const int16_t* roots_dev, const int32_t* lens_dev, uint32_t* visits_dev, float* w_dev,
+                                  cudaStream_t s);
 cudaError_t launch_pack_records(const TreeParams& p, int n, uint8_t* out, size_t bytes_per_game, cudaStream_t s);
 
 cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr,

@@ -262,14 +262,15 @@ __device__ void compact_subtree(Ctx& c, Regs& g, int32_t old_root, int L0) {
 
 // Advance the root by one action: stones, stats, subtree compaction (tree reuse of the reference's persistent dict).
 // Returns false when the new root is not "in the tree" (only possible in facade mode).
-__device__ bool advance_root(Ctx& c, Regs& g, int action) {
+// keep_tree = false (RandomAgent / PUCT / UCT sides, which never reuse a tree): only the stone is placed.
+__device__ bool advance_root(Ctx& c, Regs& g, int action, bool keep_tree = true) {
   const TreeParams& P = c.P;
   const int L = P.A - g.n_moves;  // children of the current root
   int32_t child = CH_UNVISITED;
   uint32_t cn = 0;
   float cw = 0.f;
   bool found = false;
-  if (g.root_node >= 0) {
+  if (keep_tree && g.root_node >= 0) {
     const size_t base = c.abase + (size_t)g.root_node;
     for (int b = 0; b < L; b += 32) {
       const int i = b + c.lane;
@@ -501,13 +502,15 @@ __device__ void play_move(Ctx& c, Regs& g) {
   if (P.noise && g.root_node >= 0) remix_root_noise(c, g.root_node, P.A - g.n_moves, g.noise_draws);
 }
 
+#include "rollout.cuh"
+
 // ---------------------------------------------------------------------------------------------- arena
 __device__ __forceinline__ int arena_side(const TreeParams& P, int game) { return game >= P.arena_M ? 1 : 0; }
 
 // pi = one-hot(argmax visits, uniform tie-break over ascending indices) (utils.py:198-205) from sm->dbuf
 __device__ int argmax_tiebreak(Ctx& c, Regs& g, int A) {
   WarpSmem* sm = c.sm;
-  double mx = 0.0;
+  double mx = __longlong_as_double(0xFFF0000000000000ll);  // -inf: UCT scores can all be negative
   for (int a = c.lane; a < A; a += 32) mx = fmax(mx, sm->dbuf[a]);
 #pragma unroll
   for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
@@ -551,7 +554,11 @@ __device__ bool arena_move(Ctx& c, Regs& g) {
   }
   __syncwarp();
   int action;
-  if (P.arena_random[side]) {
+  const int kind = P.arena_kind[side];
+  if (kind == SIDE_PUCT || kind == SIDE_UCT) {
+    rollout_scores(c, g, kind, rec);
+    action = argmax_tiebreak(c, g, A);
+  } else if (kind == SIDE_RANDOM) {
     // RandomAgent.get_pi: uniform over the empty cells; argmax_onehot then draws one of them (ascending order)
     const int L = A - g.n_moves;
     int r = draw_choice(c, g.rng_ctr, L);
@@ -584,7 +591,7 @@ __device__ bool arena_move(Ctx& c, Regs& g) {
     action = argmax_tiebreak(c, g, A);
   }
   __syncwarp();
-  (void)advance_root(c, g, action);  // mover.root_id + (action,)
+  (void)advance_root(c, g, action, kind == SIDE_ZERO);  // mover.root_id + (action,)
   if (c.lane == 0) c.gm->moves_played += 1ull;
   const int win = check_win_rows(g.rb, g.rw, P.B, g.n_moves, sm->rows, c.lane);
   const int o = side ? m : M + m;  // the other side's slot
@@ -644,9 +651,10 @@ __device__ bool arena_move(Ctx& c, Regs& g) {
   c.game = o;
   load_regs(c, g);
   c.abase = arena_base(P, o, g.arena);
-  const bool in_tree = advance_root(c, g, action);
+  const int okind = P.arena_kind[side ^ 1];
+  const bool in_tree = advance_root(c, g, action, okind == SIDE_ZERO);
   g.sims_done = 0;
-  g.sims_target = in_tree ? mcts_other : mcts_other + 1;
+  g.sims_target = in_tree ? mcts_other : mcts_other + 1;  // PUCT / UCT: always a fresh tree, num_mcts + 1 simulations
   g.status = ST_SEARCH;
   if (c.lane == 0) {
     og->is_real_root = in_tree ? 0 : 1;
@@ -708,9 +716,28 @@ tree_step_kernel(TreeParams P, const int32_t* __restrict__ game_ids, int n, int 
       if (lane == 0) c.gm->sims_total += 1ull;
       continue;
     }
-    if (arena && (P.arena_random[arena_side(P, c.game)] || g.sims_done >= g.sims_target)) {
-      if (!arena_move(c, g)) break;
-      continue;
+    if (arena) {
+      const int kind = P.arena_kind[arena_side(P, c.game)];
+      if (kind == SIDE_PUCT || kind == SIDE_UCT) {
+        // a play-out agent's turn: a slice of its search per lock-step round, so that the network sides of the other
+        // matches are not held up by a whole search
+        if (g.sims_done == 0) rollout_fresh_tree(g);
+        bool ok = true;
+        int ran = 0;
+        for (; ok && ran < P.rollout_sims_per_round && g.sims_done < g.sims_target; ++ran)
+          ok = rollout_sim<MAXJ>(c, g, kind);
+        if (lane == 0) c.gm->sims_total += (unsigned long long)ran;
+        if (!ok) {
+          g.status = ST_ERROR;
+          if (lane == 0) c.gm->error = 1;
+          break;
+        }
+        if (g.sims_done < g.sims_target) break;  // to be continued next round
+      }
+      if (kind != SIDE_ZERO || g.sims_done >= g.sims_target) {
+        if (!arena_move(c, g)) break;
+        continue;
+      }
     }
     if (g.sims_done >= g.sims_target) {
       if (!auto_play) {
@@ -976,6 +1003,71 @@ set_roots_kernel(TreeParams P, const int32_t* __restrict__ ids, int n, const int
   store_regs<1>(c, g);
 }
 
+// PUCTAgent / UCTAgent.get_pi minus the final arg-max (agents.py:283-296 / 461-476): a fresh search of num_mcts + 1
+// simulations from the given root ID in the listed slots; visits[a] = n(child a), w[a] = w(child a) (q = w / n).
+template <int MAXJ>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rollout_search_kernel(TreeParams P, int kind, int num_mcts, const int32_t* __restrict__ ids, int n,
+                      const int16_t* __restrict__ roots, const int32_t* __restrict__ lens, uint32_t* __restrict__ visits,
+                      float* __restrict__ wsum) {
+  __shared__ WarpSmem s_warp[kWarpsPerBlock];
+  const int wib = threadIdx.x >> 5;
+  const int w = blockIdx.x * kWarpsPerBlock + wib;
+  if (w >= n) return;
+  const int game = ids[w];
+  Game* gm = &P.games[game];
+  Ctx c{P, gm, &s_warp[wib], (int)(threadIdx.x & 31), game, 0, make_uint2(P.seed_lo, P.seed_hi)};
+  Regs g;
+  load_regs(c, g);
+  c.abase = arena_base(P, game, g.arena);
+  const int16_t* rid = roots + (size_t)w * (P.A + 1);
+  const int m = lens[w] - 1;
+  g.rb = 0u; g.rw = 0u;
+  for (int i = 0; i < m; ++i) {
+    const int a = rid[1 + i];
+    if (c.lane == a / P.B) {
+      if ((i & 1) == 0) g.rb |= 1u << (a % P.B);
+      else g.rw |= 1u << (a % P.B);
+    }
+    if (c.lane == 0) gm->moves[i] = (uint8_t)a;
+  }
+  g.n_moves = m;
+  g.last1 = m >= 1 ? rid[m] : -1;
+  g.last2 = m >= 2 ? rid[m - 1] : -1;
+  rollout_fresh_tree(g);
+  g.sims_done = 0;
+  g.sims_target = num_mcts + 1;
+  g.status = ST_SEARCH_DONE;
+  bool ok = true;
+  while (ok && g.sims_done < g.sims_target) ok = rollout_sim<MAXJ>(c, g, kind);
+  if (!ok) {
+    g.status = ST_ERROR;
+    if (c.lane == 0) gm->error = 1;
+  }
+  for (int a = c.lane; a < P.A; a += 32) {
+    visits[(size_t)w * P.A + a] = 0u;
+    wsum[(size_t)w * P.A + a] = 0.f;
+  }
+  __syncwarp();
+  if (g.root_node >= 0) {
+    const size_t base = c.abase + (size_t)g.root_node;
+    const int L = P.A - g.n_moves;
+    for (int i = c.lane; i < L; i += 32) {
+      const int a = P.slot_act[base + i];
+      const uint2 nw = P.slot_nw[base + i];
+      visits[(size_t)w * P.A + a] = nw.x;
+      wsum[(size_t)w * P.A + a] = __uint_as_float(nw.y);
+    }
+  }
+  if (c.lane == 0) {
+    gm->is_real_root = 1;
+    gm->auto_play = 0;
+    gm->sims_total += (unsigned long long)g.sims_done;
+  }
+  __syncwarp();
+  store_regs<1>(c, g);
+}
+
 // visit[a] = n(child a), policy[a] = p(child a)  (agents.py:64-73)
 __global__ void export_roots_kernel(TreeParams P, const int32_t* __restrict__ ids, int n, uint32_t* __restrict__ visits,
                                     double* __restrict__ priors, int32_t* __restrict__ real_root) {
@@ -1094,6 +1186,13 @@ cudaError_t launch_sum_counters(const TreeParams& p, int n, int n_running, unsig
   cudaError_t e = cudaMemsetAsync(out5, 0, 8 * sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
   sum_counters_kernel<<<32, 128, 0, s>>>(p, n, n_running, out5);
+  return cudaGetLastError();
+}
+cudaError_t launch_rollout_search(const TreeParams& p, int kind, int num_mcts, const int32_t* ids, int n,
+                                  const int16_t* roots, const int32_t* lens, uint32_t* visits, float* w, cudaStream_t s) {
+  const int blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (p.A <= 96) rollout_search_kernel<3><<<blocks, kWarpsPerBlock * 32, 0, s>>>(p, kind, num_mcts, ids, n, roots, lens, visits, w);
+  else rollout_search_kernel<8><<<blocks, kWarpsPerBlock * 32, 0, s>>>(p, kind, num_mcts, ids, n, roots, lens, visits, w);
   return cudaGetLastError();
 }
 cudaError_t launch_reset_arena(const TreeParams& p, int n_slots, uint32_t first_key, cudaStream_t s) {

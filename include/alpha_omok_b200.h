@@ -22,6 +22,10 @@ typedef struct ao_engine ao_engine;
 
 enum { AO_EVAL_PVNET = 0, AO_EVAL_SYNTH = 1 };    /* synthetic hash "network": exact floats, used by parity tests */
 enum { AO_NOISE_DEVICE = 0, AO_NOISE_TAPE = 1 };  /* Dirichlet gammas: on-device Philox generator, or host tape    */
+enum { AO_SIDE_ZERO = 0,     /* agents.ZeroAgent (network-guided PUCT search)                    eval_main.py:85-101 */
+       AO_SIDE_RANDOM = 1,   /* agents.RandomAgent (agents.py:637-657)                            eval_main.py:70-72  */
+       AO_SIDE_PUCT = 2,     /* agents.PUCTAgent: uniform prior + random play-outs (:263-453)      eval_main.py:73-75  */
+       AO_SIDE_UCT = 3 };    /* agents.UCTAgent: UCB1 + random play-outs (:456-634)                eval_main.py:76-78  */
 enum { AO_NN_FP16 = 0,       /* fp16 operands, one MMA per k-step, issued by CTA pairs (tcgen05 cta_group::2), the
                                 two tiles of a CTA staggered so that epilogues hide behind MMAs (tower_stag.cu)    */
        AO_NN_FP16X3 = 1,     /* hi/lo split operands, 3 MMAs per k-step (1e-4 on trained nets), CTA pairs       */
@@ -117,7 +121,8 @@ int ao_set_nn_precision_set(ao_engine* h, int set, int mode);
 
 /* eval_main.main's match loop (eval_main.py:204-333; Evaluator.get_action :153-170) on the device.  Every slot plays
  * `matches_per_slot` consecutive matches like one run of eval_main.main: player (weight set 0, n_mcts_player sims) vs
- * enemy (weight set 1 with n_mcts_enemy sims, or agents.RandomAgent when enemy_random != 0); per ply
+ * enemy (weight set 1 with n_mcts_enemy sims); player_kind / enemy_kind = AO_SIDE_* choose the agent class of a side
+ * as eval_main.Evaluator.set_agents does by name (ZeroAgent, RandomAgent, PUCTAgent, UCTAgent); per ply
  * get_pi(root_id, tau=0) -> argmax_onehot -> root_id = mover.root_id + (action,) -> env.step; each side keeps its own
  * tree, so the other side's next root is a reused root (possibly never visited, n == 0) or a real root
  * (agents.py:82-111); colours swap after every match (the player is black first in even slots), both agents are reset,
@@ -126,8 +131,18 @@ int ao_set_nn_precision_set(ao_engine* h, int set, int mode);
  * keep_records, ao_selfplay_stream_records_dev returns n_slots * matches_per_slot records (ao_records_dev layout,
  * index = slot * matches_per_slot + match; visits[ply] = the mover's root visit counts, zeros for a RandomAgent ply;
  * the pad byte after `winner` holds 1 when the player was black). n_mcts_* <= 0 selects ao_config.num_mcts. */
-int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int matches_per_slot, int enemy_random,
-                   int keep_records, int n_mcts_player, int n_mcts_enemy);
+int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int matches_per_slot, int player_kind,
+                   int enemy_kind, int keep_records, int n_mcts_player, int n_mcts_enemy);
+
+/* PUCTAgent / UCTAgent.get_pi(root_id, board, turn, tau) minus the final arg-max (agents.py:283-296, 461-476): every
+ * call starts a fresh tree, runs num_mcts + 1 simulations (uniform prior or UCB1 selection, one uniformly random
+ * play-out per non-root leaf, agents.py:319-432 / 503-613) and returns visits[n][A] = n(child) and w[n][A] = w(child)
+ * (q = w / n; w is integer-valued).  kind = AO_SIDE_PUCT | AO_SIDE_UCT; num_mcts <= 0 selects ao_config.num_mcts. */
+int ao_rollout_search(ao_engine* h, int kind, const int32_t* game_ids, int n, const int16_t* roots,
+                      const int32_t* root_lens, int num_mcts, uint32_t* visits, float* w);
+/* table[k] = log(k) for k < n (k = 0 unused) as the caller's numpy computes it: UCT compares its exploration terms for
+ * equality, so the device takes the logarithms from the host instead of its own libm.  Needed before AO_SIDE_UCT. */
+int ao_set_log_table(ao_engine* h, const double* table, int n);
 /* Number of kernels this engine has launched so far (bench.py's gpu_launches). */
 int ao_launch_count(ao_engine* h, uint64_t* out);
 

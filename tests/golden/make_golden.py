@@ -34,7 +34,7 @@ class Flask(Blueprint):
     def register_blueprint(self, *a, **k): pass
     def run(self, *a, **k): pass
 def render_template(*a, **k): return ""
-def jsonify(*a, **k): return {}
+def jsonify(*a, **k): return a[0] if a else k
 class _Req:
     args = {}
 request = _Req()
@@ -200,6 +200,8 @@ def gen_arena(R, name, sims, seed, n_match, enemy_kind="zero", forced=None):
     def make(side):
         if side == "enemy" and enemy_kind == "random":
             agent = R.agents.RandomAgent(B)
+        elif side == "enemy" and enemy_kind in ("puct", "uct"):
+            agent = (R.agents.PUCTAgent if enemy_kind == "puct" else R.agents.UCTAgent)(B, sims)
         else:
             agent = R.agents.ZeroAgent(B, sims, 5, noise=False)
             salt = 0 if side == "player" else 1
@@ -218,8 +220,13 @@ def gen_arena(R, name, sims, seed, n_match, enemy_kind="zero", forced=None):
             PATCH.stream = streams[side]
             pi = orig(*a, **k)
             zero = isinstance(agent, R.agents.ZeroAgent)
-            log.append((side, tuple(a[0]), agent.visit.astype(np.int64).copy() if zero else np.zeros(A, np.int64),
-                        bool(agent.is_real_root) if zero else True))
+            vis = np.zeros(A, np.int64)
+            if zero:
+                vis = agent.visit.astype(np.int64).copy()
+            elif isinstance(agent, (R.agents.PUCTAgent, R.agents.UCTAgent)):
+                for act in agent.tree[agent.root_id]["child"]:
+                    vis[act] = agent.tree[agent.root_id + (act,)]["n"]
+            log.append((side, tuple(a[0]), vis, bool(agent.is_real_root) if zero else True))
             return pi
 
         agent.get_pi = get_pi
@@ -263,6 +270,8 @@ def gen_arena(R, name, sims, seed, n_match, enemy_kind="zero", forced=None):
         st = O.DecisionStream(seed, 0 if side == "player" else 1)
         if side == "enemy" and enemy_kind == "random":
             return O.OracleRandomAgent(B, st)
+        if side == "enemy" and enemy_kind in ("puct", "uct"):
+            return O.OracleRolloutAgent(enemy_kind, B, sims, st)
         salt = 0 if side == "player" else 1
         return O.OracleZeroAgent(B, sims, lambda mv, salt=salt: synth_eval(mv, A, salt), st, noise=False)
 
@@ -290,11 +299,84 @@ def gen_arena(R, name, sims, seed, n_match, enemy_kind="zero", forced=None):
         out[f"winner{m}"] = winner
         out[f"outcome{m}"] = o["outcome"]
         lo = hi
-    assert n0 > 0, "no reused root with n == 0 in this golden"
+    assert n0 > 0 or enemy_kind in ("puct", "uct"), "no reused root with n == 0 in this golden"
     out["n_unvisited_reused_roots"] = n0
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(f"{name}: {n_match} matches, plies {[int(b) for b in np.diff([0] + boundaries)]}, "
           f"{n0} reused roots with n == 0  OK (oracle == reference eval_main.main)")
+
+
+def gen_rollout_agents(R, name, sims, seed):
+    """PUCTAgent / UCTAgent.get_pi (agents.py:263-634) of the unmodified reference on a handful of 9x9 and 15x15 positions:
+    visit counts and w sums of the root's children, the move, and the number of decision-stream blocks consumed (every
+    selection tie-break and every play-out move is one draw).  Cross-checked against oracle.OracleRolloutAgent."""
+    import contextlib
+    import io
+    rs = np.random.RandomState(seed)
+    out = dict(sims=sims, seed=seed)
+    cases = []
+    for kind, cls in (("puct", R.agents.PUCTAgent), ("uct", R.agents.UCTAgent)):
+        for B, lo, hi in ((9, 0, 12), (9, 30, 60), (15, 100, 180)):
+            A = B * B
+            while True:
+                k = int(rs.randint(lo, hi))
+                root = (0,) + tuple(int(x) for x in rs.permutation(A)[:k])
+                if R.utils.check_win(R.utils.get_board(root, B), 5) == 0:
+                    break
+            key = len(cases)
+            PATCH.stream = O.DecisionStream(seed, key)
+            agent = cls(B, sims)
+            with contextlib.redirect_stdout(io.StringIO()):
+                pi = agent.get_pi(root, R.utils.get_board(root, B), R.utils.get_turn(root), 0)
+            vis, w = np.zeros(A, np.int64), np.zeros(A)
+            for a in agent.tree[root]["child"]:
+                vis[a], w[a] = agent.tree[root + (a,)]["n"], agent.tree[root + (a,)]["w"]
+            ora = O.OracleRolloutAgent(kind, B, sims, O.DecisionStream(seed, key))
+            po = ora.get_pi(root)
+            assert np.array_equal(pi, po) and np.array_equal(vis, ora.visit) and PATCH.stream.ctr == ora.stream.ctr, (kind, B)
+            i = len(cases)
+            cases.append((kind, B))
+            out[f"kind{i}"], out[f"B{i}"] = kind, B
+            out[f"root{i}"] = np.asarray(root, np.int16)
+            out[f"visits{i}"], out[f"w{i}"] = vis.astype(np.int32), w.astype(np.float32)
+            out[f"move{i}"], out[f"draws{i}"] = int(np.argmax(pi)), PATCH.stream.ctr
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {len(cases)} searches ({sims} sims)  OK (oracle == reference)")
+
+
+def fill_dashboard(gi, pa, ea, B, player_agent, enemy_agent):
+    """deterministic contents for the dashboard objects (used identically by tests/test_cabi_and_host.py)"""
+    rs = np.random.RandomState(99)
+    board = np.zeros(B * B)
+    cells = rs.permutation(B * B)[:23]
+    board[cells[0::2]], board[cells[1::2]] = 1, -1
+    gi.game_board = board.reshape(B, B)
+    gi.win_index, gi.curr_turn, gi.enemy_turn, gi.action_index, gi.game_status = 0, 1, 1, int(cells[-1]), 0
+    pa.agent, ea.agent = player_agent, enemy_agent
+    pa.visit, pa.p = rs.randint(0, 50, B * B).astype("float"), rs.dirichlet(np.ones(B * B))
+    ea.visit, ea.p = rs.randint(0, 50, B * B).astype("float"), rs.dirichlet(np.ones(B * B))
+    for mv, v in ((1, 0.25), (3, -0.5), (5, 0.875)):
+        pa.add_value(mv, v)
+    for mv, v in ((2, -0.125), (4, 0.0)):
+        ea.add_value(mv, v)
+    player_agent.message, enemy_agent.message = "simulation: 800\r", "Hello"
+
+
+def gen_dashboard(R):
+    """payloads of the reference's /periodic_status and /prompt_status routes (webapi.py:28-76) for a fixed state of its
+    GameInfo / AgentInfo objects (info/*.py) - the only thing the web dashboard ever reads from the arena"""
+    import json
+    import webapi
+    B = 9
+    fill_dashboard(webapi.game_info, webapi.player_agent_info, webapi.enemy_agent_info, B,
+                   R.agents.ZeroAgent(B, 800, 5, noise=False), R.agents.RandomAgent(B))
+    out = {"periodic_status": webapi.periodic_status(), "prompt_status": webapi.prompt_status()}
+    webapi.player_agent_info.clear_values()
+    out["after_clear"] = webapi.periodic_status()
+    with open(os.path.join(HERE, "dashboard_feed.json"), "w") as f:
+        json.dump(out, f)
+    print("dashboard_feed.json OK", len(out["periodic_status"]), "keys")
 
 
 def pick_forced_replies(sims, seed, plies=(4, 9)):
@@ -382,7 +464,7 @@ def gen_late_roots(R, name, B, sims, seed, n_roots, lo, hi):
     print(f"{name}: {n_roots} late roots ({lo}-{hi} stones), {sims} sims  OK (oracle == reference)")
 
 
-def gen_round2(R, parts=("arena", "trained", "long15", "late")):
+def gen_round2(R, parts=("arena", "trained", "long15", "late", "rollout", "dashboard")):
     """round-2 fixtures: arena (eval_main.main), trained-checkpoint self-play, a full-length 15x15 game, late roots"""
     if "arena" in parts:
         gen_arena(R, "arena_9_synth_s30", sims=30, seed=41, n_match=2)
@@ -403,6 +485,12 @@ def gen_round2(R, parts=("arena", "trained", "long15", "late")):
                       nn_kind="synth")
     if "late" in parts:
         gen_late_roots(R, "search_15_late_roots", 15, 60, seed=51, n_roots=4, lo=149, hi=215)
+    if "dashboard" in parts:
+        gen_dashboard(R)
+    if "rollout" in parts:
+        gen_rollout_agents(R, "rollout_agents_s40", sims=40, seed=61)
+        gen_arena(R, "arena_9_puct_enemy_s30", sims=30, seed=45, n_match=2, enemy_kind="puct")
+        gen_arena(R, "arena_9_uct_enemy_s30", sims=30, seed=46, n_match=2, enemy_kind="uct")
 
 
 def gen_rules(R):

@@ -247,3 +247,28 @@ def test_weights_are_uploaded_once_per_change_not_once_per_search():
     agent._sync_weights()
     assert agent._engine.uploads == 4
     agent._engine = None                     # do not let __del__ paths touch the fake
+
+
+def test_dashboard_feed_payloads_match_reference():
+    """info.AgentInfo / GameInfo / periodic_status / prompt_status against the payloads the reference's own objects and
+    Flask routes produce for the same state (tests/golden/dashboard_feed.json, webapi.py:28-76, info/*.py)"""
+    import json
+    from alpha_omok_b200 import agents, info
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mg", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    src = open(os.path.join(ROOT, "tests", "golden", "make_golden.py")).read()
+    ns = {"np": np}
+    start = src.index("def fill_dashboard(")
+    exec(src[start:src.index("\n\n\n", start)], ns)       # the very function that filled the reference's objects
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "dashboard_feed.json")))
+    d = info.Dashboard(9)
+
+    class ZeroAgent(agents.Agent):      # get_name() is the class name shown in the dashboard (webapi.py:41-42)
+        pass
+
+    ns["fill_dashboard"](d.game_info, d.player_agent_info, d.enemy_agent_info, 9, ZeroAgent(9), agents.RandomAgent(9))
+    assert d.periodic_status() == want["periodic_status"]
+    assert d.prompt_status() == want["prompt_status"]
+    d.player_agent_info.clear_values()
+    assert d.periodic_status() == want["after_clear"]

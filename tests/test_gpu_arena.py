@@ -203,3 +203,96 @@ def test_evaluator_dropin_vs_oracle_arena(cabi, monkeypatch):
     outcomes = [m["outcome"] for m in ora]
     assert result == {"Player": outcomes.count("player"), "Enemy": outcomes.count("enemy"), "Draw": outcomes.count("draw")}
     assert (pe, ee) == arena.elo_sequence(outcomes)[:2]
+
+
+# ------------------------------------------------------------------------------------------------ PUCT / UCT agents
+def test_rollout_agents_reproduce_reference_golden(cabi):
+    """PUCTAgent / UCTAgent.get_pi of the UNMODIFIED reference (rollout_agents_s40.npz: 9x9 early / mid-game and 15x15
+    late positions): the device search - fresh tree, num_mcts + 1 simulations, UCB / PUCT selection in float64, one
+    uniformly random play-out per leaf - gives the same child visit counts and w sums and consumes the same number of
+    decision-stream blocks (checked through the next draw)"""
+    fx = load("rollout_agents_s40")
+    sims, seed = int(fx["sims"]), int(fx["seed"])
+    for i in range(int(fx["n_cases"])):
+        kind, B = str(fx[f"kind{i}"]), int(fx[f"B{i}"])
+        root = tuple(int(a) for a in fx[f"root{i}"])
+        eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=1, noise=False, seed=seed, eval_mode=cabi.AO_EVAL_SYNTH)
+        eng.games_reset([0], keys=[i])
+        vis, w = eng.rollout_search(kind, [0], [root], sims)
+        assert np.array_equal(vis[0], fx[f"visits{i}"].astype(np.uint32)), (i, kind, B)
+        assert np.array_equal(w[0], fx[f"w{i}"]), (i, kind, B)
+        # a second search in the same slot continues the slot's decision stream exactly where the reference's would
+        ora = O.OracleRolloutAgent(kind, B, sims, O.DecisionStream(seed, i))
+        ora.stream.ctr = int(fx[f"draws{i}"]) - (1 if _final_tiebreak_drew(fx, i, kind) else 0)
+        ora.get_pi(root)
+        vis2, _ = eng.rollout_search(kind, [0], [root], sims)
+        assert np.array_equal(vis2[0], ora.visit.astype(np.uint32)), (i, kind, B)
+        eng.close()
+
+
+def _final_tiebreak_drew(fx, i, kind):
+    """did get_pi's closing arg-max draw from the stream (more than one maximum)? The device search stops before it."""
+    vis, w = fx[f"visits{i}"].astype(np.float64), fx[f"w{i}"].astype(np.float64)
+    if kind == "puct":
+        score = vis
+    else:
+        root = set(int(a) for a in fx[f"root{i}"][1:])
+        score = np.full(len(vis), -np.inf)
+        for a in range(len(vis)):
+            if a not in root:
+                score[a] = w[a] / vis[a] if vis[a] > 0 else 0.0
+    return int((score == score.max()).sum()) > 1
+
+
+@pytest.mark.parametrize("name", ["arena_9_puct_enemy_s30", "arena_9_uct_enemy_s30"])
+def test_device_arena_with_rollout_enemy_reproduces_eval_main_golden(cabi, name):
+    """eval_main.main with enemy = 'puct' / 'uct' (eval_main.py:73-78), run unmodified: the device arena slices the
+    play-out agent's search over the lock-step rounds and still reproduces every ply"""
+    from alpha_omok_b200 import arena, replay
+    fx = load(name)
+    B, sims, n_match, kind = int(fx["B"]), int(fx["sims"]), int(fx["n_match"]), str(fx["enemy_kind"])
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=2, noise=False, seed=int(fx["seed"]),
+                      eval_mode=cabi.AO_EVAL_SYNTH)
+    eng.arena_begin(1, first_key=0, matches_per_slot=n_match, enemy_kind=kind)
+    st = _run(eng)
+    assert st["games_finished"] == n_match
+    recs = arena.decode_match_records(replay.device_stream_records(eng), B)
+    for m, r in enumerate(recs):
+        assert r["moves"] == [int(a) for a in fx[f"moves{m}"]], m
+        assert np.array_equal(r["visits"], fx[f"visits{m}"].astype(np.uint32)), m
+        assert r["winner"] == int(fx[f"winner{m}"]) and r["outcome"] == str(fx[f"outcome{m}"]), m
+    eng.close()
+
+
+def test_evaluator_accepts_rollout_agents_by_name(cabi, monkeypatch):
+    """Evaluator.set_agents('puct' | 'uct') (eval_main.py:73-78) through the drop-in facade agents: one match each against
+    the oracle's eval_main loop with the facades' host draws routed to a shared stream"""
+    from alpha_omok_b200 import agents, arena
+    from oracle import pvnet_ref
+    B, A, sims = 9, 81, 24
+    sd = pvnet_ref.make_state_dict(3, 2, 5, 128, B)
+    for kind in ("puct", "uct"):
+        host = O.DecisionStream(555, 1)
+        monkeypatch.setattr(np.random, "choice", lambda a, size=None, replace=True, p=None, host=host: host.choice(int(a)))
+        ev = arena.Evaluator(board_size=B, n_mcts_player=sims, n_mcts_enemy=sims, n_mcts_monitor=sims, n_blocks=2,
+                             engine_kwargs=dict(eval_mode=cabi.AO_EVAL_SYNTH))
+        ev.set_agents(sd, kind, sd)
+        assert type(ev.enemy).__name__ == ("PUCTAgent" if kind == "puct" else "UCTAgent")
+        moves = []
+        orig = ev.get_action
+
+        def get_action(*a, orig=orig, moves=moves):
+            action, idx = orig(*a)
+            moves.append(int(idx))
+            return action, idx
+
+        ev.get_action = get_action
+        result, _, _ = arena.run_matches(ev, n_match=1)
+        hs = O.DecisionStream(555, 1)
+        p = O.OracleZeroAgent(B, sims, lambda mv: synth_eval(mv, A), O.DecisionStream(0, 0), noise=False)
+        p.host_stream = hs
+        e = O.OracleRolloutAgent(kind, B, sims, O.DecisionStream(0, 0))
+        e.host_stream = hs
+        o = O.arena_matches(B, p, e, 1)[0]
+        assert moves == o["moves"], kind
+        assert sum(result.values()) == 1

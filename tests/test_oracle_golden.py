@@ -150,3 +150,28 @@ def test_reference_copy_reproduces_config1_and_the_oracle():
     assert r["kind"] == "reference"
     assert (r["moves"], r["winner"], r["sims"]) == (39, 1, 1561)
     assert r["visit_sha256_16"] == "ceddffce5bfb2897"
+
+
+def test_rollout_agents_golden():
+    """PUCTAgent / UCTAgent of the unmodified reference (agents.py:263-634): visits, w sums, move and stream consumption"""
+    fx = load("rollout_agents_s40")
+    sims, seed = int(fx["sims"]), int(fx["seed"])
+    for i in range(int(fx["n_cases"])):
+        kind, B = str(fx[f"kind{i}"]), int(fx[f"B{i}"])
+        root = tuple(int(a) for a in fx[f"root{i}"])
+        ag = O.OracleRolloutAgent(kind, B, sims, O.DecisionStream(seed, i))
+        pi = ag.get_pi(root)
+        assert np.array_equal(ag.visit, fx[f"visits{i}"]) and int(np.argmax(pi)) == int(fx[f"move{i}"])
+        assert ag.stream.ctr == int(fx[f"draws{i}"])
+
+
+@pytest.mark.parametrize("name", ["arena_9_puct_enemy_s30", "arena_9_uct_enemy_s30"])
+def test_arena_rollout_enemy_golden(name):
+    fx = load(name)
+    B, A, sims, seed, n_match = 9, 81, int(fx["sims"]), int(fx["seed"]), int(fx["n_match"])
+    player = O.OracleZeroAgent(B, sims, lambda mv: synth_eval(mv, A, 0), O.DecisionStream(seed, 0), noise=False)
+    enemy = O.OracleRolloutAgent(str(fx["enemy_kind"]), B, sims, O.DecisionStream(seed, 1))
+    for m, o in enumerate(O.arena_matches(B, player, enemy, n_match)):
+        assert o["moves"] == [int(a) for a in fx[f"moves{m}"]]
+        assert np.array_equal(np.stack(o["visits"]), fx[f"visits{m}"])
+        assert o["winner"] == int(fx[f"winner{m}"]) and o["outcome"] == str(fx[f"outcome{m}"])
