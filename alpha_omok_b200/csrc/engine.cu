@@ -142,6 +142,7 @@ int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int ti
 }
 
 constexpr int kGraphRounds = 16;
+constexpr int kPollEvery = 4;  // ao_search: host polls of the running-games counter
 
 // `rounds` lock-step rounds over the first n game slots; whole multiples of kGraphRounds are replayed from a CUDA graph
 // (captured from run_round itself, so both paths launch exactly the same work), the rest is issued directly.
@@ -537,7 +538,9 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
   while (active > 0) {
     if ((rc = run_round(h, h->d_ids, n, max_iters)) != 0) return rc;
     ++rounds;
-    if (rounds >= blind && (rc = poll_active(h, &active)) != 0) return rc;
+    // rounds after a search has finished are no-ops for that game (the tree step returns at once, the tower sees no
+    // request), so the host only looks every few rounds instead of synchronising after each one
+    if (rounds >= blind && ((rounds - blind) % kPollEvery == 0) && (rc = poll_active(h, &active)) != 0) return rc;
     if (rounds > 4 * (h->cfg.num_mcts + 2) + 64) return fail(-6, "search did not converge after %d rounds", rounds);
   }
   AO_CUDA(ao::launch_export_roots(h->tp, h->d_ids, n, h->d_visits, h->d_priors, h->d_real_root, h->stream));

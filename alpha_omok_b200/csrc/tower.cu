@@ -1,19 +1,24 @@
-// PVNet.forward (model.py:97-104) as ONE persistent sm_100a kernel: the whole residual tower of a pair of 9x9 games
-// (or one 15x15 game) runs inside one CTA with the activations resident in shared memory and the accumulators in
-// TMEM; only the leaf descriptors (136 B) are read from and policy/value written to HBM, the fp16 weights stream
-// from L2 through a 1-D TMA ring.
+// PVNet.forward (model.py:97-104): the lock-step tower kernels - the hi/lo split-precision mode every trained net runs
+// (AO_NN_FP16X3, CTA pairs) and two comparison variants of the single-pass mode (AO_NN_FP16_LOCKSTEP: CTA pairs,
+// AO_NN_FP16_1CTA: cta_group::1).  The default single-pass kernel is tower_stag.cu; data layout and MMAs are shared:
 //
-// Implicit GEMM without im2col: activations live in smem as [16 k-chunks][ROWS][8 halves] (K-major, no swizzle,
-// 16 B per row and chunk).  Board cells are laid out with one zero column per row and one zero row per game
-// (row stride S = B+1), so tap (dy,dx) of the 3x3 stencil is the SAME buffer addressed from a start row shifted by
-// dy*S+dx: 9 taps x 8 k-steps of tcgen05.mma (M=128,N=128,K=16) per 128-row tile, no data movement.
-// Two 128-row tiles per CTA (rows 0..255 = 2 games of 100 rows at 9x9, 1 game of 256 rows at 15x15).
-// TMEM: per tile 128 columns accA (conv1 of a block) + 128 columns accB (stem / conv2).  accB keeps the fp32 block
-// input x, so `out += residual` (model.py:29) is the accumulate flag of conv2's first MMA - no second smem buffer.
+// One persistent CTA per SM; the whole residual tower of a pass (3 games of 9x9 or 1 game of 15x15 = two 128-row tiles)
+// runs with the activations resident in shared memory and the accumulators in TMEM; only the leaf descriptors (136 B)
+// are read from and policy / value written to HBM, the fp16 weights stream from L2 through a 1-D bulk-copy ring.
+//
+// Implicit GEMM without im2col and without padding: activations live in smem as [16 k-chunks][Rows][8 halves] (K-major,
+// no swizzle, 16 B per row and chunk).  Board cells are packed densely (row = game * A + cell, row stride S = B), so tap
+// (dy,dx) of the 3x3 stencil is the SAME buffer addressed from a start row shifted by dy*B+dx; taps that fall off the
+// board are dropped with tcgen05.mma's disable-output-lane masks (a disabled accumulator row is not updated = a zero
+// contribution).  9 taps x 8 k-steps of tcgen05.mma (K = 16) per tile and layer.
+// TMEM: per tile 128 columns accA + 128 columns accB.  Single-pass mode: accB keeps the fp32 block input x, so
+// `out += residual` (model.py:29) is the accumulate flag of conv2's first MMA.  Split mode: every layer accumulates in a
+// fresh accA (low-order terms first, see the MMA issuer), accB is the epilogue's fp32 stash of x and the residual add
+// is a round-to-nearest fp32 add in the epilogue.
 // BN (eval) is folded: scale into the fp16 weights, shift into the fp32 bias added in the epilogue.
 //
-// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp%4, tile = warp/4), warp 8 weight producer, warp 9 MMA
-// issuer + TMEM owner.
+// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp%4, tile = warp/4), warp 8 weight producer, warp 9 (and, for
+// CTA pairs, warp 10) MMA issuer + TMEM owner.
 #include <cuda_fp16.h>
 #include <stdio.h>
 

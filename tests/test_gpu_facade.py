@@ -236,12 +236,23 @@ def test_evaluator_dropin_trained_vs_random(golden_dir):
     ev = arena.Evaluator(board_size=9, n_mcts_player=50, n_mcts_enemy=50, n_mcts_monitor=50)
     ev.set_agents(ckpt, "random", ckpt)
     assert isinstance(ev.player, agents.ZeroAgent) and isinstance(ev.enemy, agents.RandomAgent) and not ev.player.noise
-    result, p_elo, e_elo = arena.run_matches(ev, n_match=2)
+    from alpha_omok_b200 import info
+    dash = info.Dashboard(9)
+    result, p_elo, e_elo = arena.run_matches(ev, n_match=2, dashboard=dash)
     assert result == {"Player": 2, "Enemy": 0, "Draw": 0}
     exp_p, exp_e = arena.elo(*arena.elo(1500, 1500, 1, 0), 1, 0)
     assert (p_elo, e_elo) == (exp_p, exp_e)
+    # dashboard feed (webapi.py:28-76): what the web front end polls reflects the last position and the agents' fields
+    st = dash.periodic_status()
+    assert st["success"] and st["player_agent_name"] == "ZeroAgent" and st["enemy_agent_name"] == "RandomAgent"
+    assert st["game_board_size"] == 9 and st["win_index"] in (1, 2) and st["enemy_turn"] == 1   # swapped twice
+    assert st["player_agent_visit_values"] == ev.player.get_visit().reshape(-1).tolist()
+    assert abs(sum(st["player_agent_p_values"]) - 1) < 1e-9 and st["player_agent_moves"] == []  # cleared at game end
+    assert dash.prompt_status()["player_message"].startswith("simulation: 5")
     with pytest.raises(NotImplementedError):
-        ev.set_agents(ckpt, "puct", ckpt)
+        ev.set_agents(ckpt, "human", ckpt)
+    ev.set_agents(ckpt, "uct", ckpt)
+    assert isinstance(ev.enemy, agents.UCTAgent)
 
 
 def test_self_play_facade_continuous_mode_equals_batch_mode():
