@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-2 profiling session (run under gpurun, one GPU): launch list of bench.py's timed region + one `ncu --set full`
+# capture per hot kernel and configuration.  Outputs under gpurun_out/; summaries are copied to profiles/ by hand.
+set -x
+O=gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -s 2500 -c 400 --csv --log-file $O/r02_launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-legs --no-cpu-baseline --no-full-episodes --no-e2e > $O/r02_bench_under_ncu.json 2> $O/r02_bench_under_ncu.err
+ncu --set full --clock-control none --import-source on -k regex:tower_stag -s 40 -c 1 -f -o $O/r02_tower_stag9 python tools/perf_leg.py selfplay9 48 > $O/r02_ncu_stag9.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tower_stag -s 40 -c 1 -f -o $O/r02_tower_stag15 python tools/perf_leg.py selfplay15 48 > $O/r02_ncu_stag15.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tower_kernel -s 40 -c 1 -f -o $O/r02_tower_x3 python tools/perf_leg.py trained9 48 > $O/r02_ncu_x3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tree_step -s 60 -c 1 -f -o $O/r02_tree_step_arena python tools/perf_leg.py arena 48 > $O/r02_ncu_tree_arena.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 90 --csv --log-file $O/r02_launches_arena.csv python tools/perf_leg.py arena 80 > $O/r02_launches_arena.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rollout_search -c 1 -f -o $O/r02_rollout_search python tools/perf_leg.py rollout > $O/r02_ncu_rollout.log 2>&1
+for leg in selfplay9 selfplay15 trained9 arena rollout; do python tools/perf_leg.py $leg 400; done > $O/r02_perf_legs.log 2>&1
+tail -8 $O/r02_perf_legs.log

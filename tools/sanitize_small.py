@@ -42,3 +42,23 @@ for _ in range(3):
 s, p, z = buf.sample(64)
 torch.cuda.synchronize()
 print("replay ring ok", len(buf), flush=True)
+# round 2: the arena match loop (two weight sets, both towers per round), RandomAgent / PUCT / UCT sides, rollout search
+sd0, sd1 = seeded_state_dict(0, 2, 5, 128, 9), seeded_state_dict(1, 2, 5, 128, 9)
+eng = _cabi.Engine(board_size=9, num_mcts=12, max_games=8, n_blocks=2, noise=False, seed=3)
+eng.load_state_dict(sd0, which=0)
+eng.load_state_dict(sd1, which=1)
+eng.set_nn_precision(_cabi.AO_NN_FP16X3, which=0)
+for kind in ("zero", "random", "puct", "uct"):
+    eng.arena_begin(4, first_key=0, matches_per_slot=2, enemy_kind=kind)
+    st = eng.selfplay_rounds(40)
+    n = 0
+    while st["running"] and n < 60:
+        st = eng.selfplay_rounds(40)
+        n += 1
+    assert st["errors"] == 0 and st["games_finished"] >= 1, st
+    print("arena enemy", kind, "ok", st["games_finished"], "matches", flush=True)
+for kind in ("puct", "uct"):
+    vis, w = eng.rollout_search(kind, [0, 1], [(0,), (0, 40, 41)], 24)
+    assert vis.sum(axis=1).tolist() == [24, 24]
+    print("rollout", kind, "ok", flush=True)
+eng.close()
