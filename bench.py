@@ -34,7 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_EXPANSION = {9: 478_800_004, 15: 1_330_129_156}  # one PVNet forward, 2*MAC, padded taps
-TOWER_DRAM_BYTES_PER_LAUNCH = {(9, 4096): 6_716_160}  # ncu capture of bench.py itself, round 1 v7 (profiles/r01_tower_stag_kernel_v7_ncu_full_summary.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE tower launch, `ncu --set full` captures of round 2
+# (profiles/r02_kernels_ncu_full_summary.txt); key = (board, leaves per launch, tower mode)
+TOWER_DRAM_BYTES_PER_LAUNCH = {(9, 4096, "fp16"): 6_716_416, (15, 4096, "fp16"): 7_138_560, (9, 4096, "split"): 12_632_064}
 METRIC = "MCTS node-expansions/sec, 9x9 Omok self-play @400 sims/move"
 
 
@@ -226,7 +228,7 @@ def _timed_steps(eng, rounds, steps, warmup, stream, torch):
             "tower_ms": tower_ms, "tree_ms": tree_ms, "launches": steps * rounds}
 
 
-def _leg_line(name, workload, board, m, steps, rounds, passes_per_eval=1):
+def _leg_line(name, workload, board, m, steps, rounds, passes_per_eval=1, traffic=None):
     sustained, burst, peak_src = peaks()
     achieved = m["evals"] * FLOP_PER_EXPANSION[board] / (m["tower_ms"] * 1e-3) / 1e12 if m["tower_ms"] > 0 else None
     return {"workload": workload, "value": m["sims"] / (m["ms"] * 1e-3), "unit": "expansions/s", "steps": steps,
@@ -238,7 +240,7 @@ def _leg_line(name, workload, board, m, steps, rounds, passes_per_eval=1):
                          "raw_mma_tflops": achieved * passes_per_eval if achieved else None,
                          "tower_ms_per_round": m["tower_ms"] / (steps * rounds), "tree_ms_per_round": m["tree_ms"] / (steps * rounds),
                          "kernel_share_of_step": m["tower_ms"] / (m["tower_ms"] + m["tree_ms"]) if m["tower_ms"] else None,
-                         "traffic": None}}
+                         "traffic": traffic}}
 
 
 def run_legs(a, local, stream, _cabi):
@@ -253,7 +255,8 @@ def run_legs(a, local, stream, _cabi):
     eng.selfplay_begin(G, first_key=0, recycle=True)
     m = _timed_steps(eng, S, steps, 1, stream, torch)
     legs["board15"] = _leg_line("board15", f"BASELINE config 3: {G} parallel 15x15 self-play games, {S} sims/move, PVNet 10x128 random-init, "
-                                "single-pass fp16 tower (tower_stag_kernel<15>)", 15, m, steps, S)
+                                "single-pass fp16 tower (tower_stag_kernel<15>)", 15, m, steps, S,
+                                traffic=TOWER_DRAM_BYTES_PER_LAUNCH.get((15, G, "fp16")))
     eng.close()
     # ---- trained-net self-play: the shipped checkpoint needs the hi/lo split tower (3 MMAs per k-step) for 1e-4
     eng = _cabi.Engine(board_size=9, num_mcts=S, max_games=G, seed=2001, device=local, stream=stream.cuda_stream)
@@ -263,7 +266,8 @@ def run_legs(a, local, stream, _cabi):
     m = _timed_steps(eng, S, steps, 1, stream, torch)
     legs["trained_selfplay"] = _leg_line("trained_selfplay", f"{G} parallel 9x9 self-play games, {S} sims/move, the reference's shipped trained "
                                          f"checkpoint; tower mode picked by the 1e-4 probe: {'fp16 hi/lo split (AO_NN_FP16X3)' if mode == 1 else 'single-pass fp16'}",
-                                         9, m, steps, S, passes_per_eval=3 if mode == 1 else 1)
+                                         9, m, steps, S, passes_per_eval=3 if mode == 1 else 1,
+                                         traffic=TOWER_DRAM_BYTES_PER_LAUNCH.get((9, G, "split" if mode == 1 else "fp16")))
     eng.close()
     # ---- config 5: arena, 1024 concurrent matches, 800 sims/move, trained (split tower) vs random-init (fp16 tower)
     M, SA = 1024, 800
@@ -466,8 +470,8 @@ def run_ours(a):
                          "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": peak_src + ", bf16 sustained",
                          "frac_of_burst": achieved / burst,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (4096 leaves), from the committed
-                         # ncu --set full capture profiles/r01_tower_stag_kernel_v7_ncu_full_summary.txt
-                         "traffic": TOWER_DRAM_BYTES_PER_LAUNCH.get((B, G)),
+                         # ncu --set full capture profiles/r02_kernels_ncu_full_summary.txt
+                         "traffic": TOWER_DRAM_BYTES_PER_LAUNCH.get((B, G, "fp16")),
                          "kernel_share_of_step": tot[5] / (tot[5] + tot[6]) if tot[5] + tot[6] > 0 else None,
                          "tower_ms_per_launch": tower_ms_rank / (a.steps * S), "tree_ms_per_launch": tot[6] / world / (a.steps * S),
                          "flop_per_expansion": FLOP_PER_EXPANSION[B]},
