@@ -102,6 +102,11 @@ struct ao_engine {
   int* d_fwd_bad;
   float* d_wsum;                // ao_rollout_search: w of the root's children
   int log_table_n;
+  // persistent self-play kernel (tower_stag.cu, PERSIST): allowed unless AO_NO_PERSIST is set; `persist_pending` =
+  // the running games wait in ST_WAIT_NN with their requests in nn_in[game] (static slots) and no answer computed yet
+  bool persist_allowed, persist_pending;
+  long long last_running;       // running games after the last self-play call (-1: unknown = all)
+  cudaEvent_t pev[3];
 };
 
 namespace {
@@ -207,6 +212,41 @@ cudaError_t launch_sum_selfplay(ao_engine* h) {
   return ao::launch_sum_counters(h->tp, h->selfplay_games, h->selfplay_games, h->d_counters, h->stream);
 }
 
+// ---- persistent self-play kernel: state transitions
+// usable: PVNet evaluator, single-pass fp16 tower (tower_stag.cu), plain self-play (no arena), at least a few rounds
+// and (nearly) all game slots still playing: the persistent kernel evaluates every slot every round (fixed game -> pass
+// map), the two-kernel path packs the live requests densely, which wins once a batch played to the end thins out
+bool persist_usable(const ao_engine* h, int rounds) {
+  return h->persist_allowed && h->cfg.eval_mode == AO_EVAL_PVNET && h->ws[0].precision == AO_NN_FP16 && h->tp.arena_M == 0 &&
+         h->selfplay_games > 0 && rounds >= 4 &&
+         (h->last_running < 0 || h->last_running * 16 >= (long long)h->selfplay_games * 15);
+}
+// two-kernel state (answers pending in nn_policy[gm->nn_slot], or nothing pending) -> persistent state: one tree step
+// with static request slots consumes what is pending and leaves every running game's next request in nn_in[game]
+int enter_persist(ao_engine* h, int max_iters) {
+  if (h->persist_pending) return 0;
+  h->tp.static_slots = 1;
+  AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, 2 * sizeof(int32_t), h->stream));
+  AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
+  AO_CUDA(ao::launch_tree_step(h->tp, nullptr, h->selfplay_games, max_iters, h->stream));
+  h->launches += 1;
+  h->persist_pending = true;
+  return 0;
+}
+// persistent state -> two-kernel state: one plain tower launch over all game slots answers the pending requests
+// (gm->nn_slot == game slot), after which tree_step_kernel consumes them as usual.  `drop`: the pending requests are
+// about to be discarded anyway (games reset / new roots).
+int leave_persist(ao_engine* h, bool drop) {
+  if (h->persist_pending && !drop) {
+    AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, nullptr, h->selfplay_games, h->tp.nn_policy,
+                             h->tp.nn_value, h->num_sms, h->stream));
+    h->launches += 1;
+  }
+  h->persist_pending = false;
+  h->tp.static_slots = 0;
+  return 0;
+}
+
 int poll_active(ao_engine* h, int* active) {
   AO_CUDA(cudaMemcpyAsync(h->h_pinned, h->tp.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
@@ -263,6 +303,10 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->h_pinned = nullptr;
   h->d_fwd_states = nullptr; h->d_fwd_bad = nullptr;
   h->d_wsum = nullptr; h->log_table_n = 0;
+  h->persist_allowed = getenv("AO_NO_PERSIST") == nullptr;
+  h->persist_pending = false;
+  h->last_running = -1;
+  h->pev[0] = h->pev[1] = h->pev[2] = nullptr;
   if (cfg->stream) {
     h->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
     h->own_stream = false;
@@ -336,6 +380,7 @@ extern "C" int ao_engine_destroy(ao_engine* h) {
   if (h->d_stream) cudaFree(h->d_stream);
   if (h->round_graph) cudaGraphExecDestroy(h->round_graph);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->pev) if (e) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -492,6 +537,7 @@ extern "C" int ao_games_reset(ao_engine* h, const int32_t* game_ids, int n, cons
   for (int i = 0; i < n; ++i)
     if (game_ids[i] < 0 || game_ids[i] >= h->G) return fail(-1, "game id %d out of range", game_ids[i]);
   h->tp.arena_M = 0;
+  leave_persist(h, true);
   AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   if (game_keys) AO_CUDA(cudaMemcpyAsync(h->d_keys, game_keys, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(ao::launch_reset_games(h->tp, h->d_ids, n, game_keys ? h->d_keys : nullptr, 0, h->stream));
@@ -526,6 +572,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
     if (root_lens[i] < 1 || root_lens[i] > A) return fail(-1, "root id length %d out of range 1..%d", root_lens[i], A);
   }
   h->tp.arena_M = 0;
+  leave_persist(h, true);
   AO_CUDA(cudaMemcpyAsync(h->d_ids, game_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(cudaMemcpyAsync(h->d_lens, root_lens, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(cudaMemcpyAsync(h->d_roots, roots, (size_t)n * (A + 1) * 2, cudaMemcpyHostToDevice, h->stream));
@@ -604,12 +651,14 @@ extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_
   int rc = require_weights(h);
   if (rc) return rc;
   h->tp.arena_M = 0;
+  leave_persist(h, true);
   std::vector<uint32_t> keys(n_games);
   for (int i = 0; i < n_games; ++i) keys[i] = first_key + (uint32_t)i;
   AO_CUDA(cudaMemcpyAsync(h->d_keys, keys.data(), (size_t)n_games * 4, cudaMemcpyHostToDevice, h->stream));
   AO_CUDA(ao::launch_reset_games(h->tp, nullptr, n_games, h->d_keys, recycle ? 2 : 1, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->selfplay_games = n_games;
+  h->last_running = -1;
   return 0;
 }
 
@@ -638,6 +687,7 @@ extern "C" int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t firs
   }
   if (!h->d_stream_next && (rc = ealloc(h, &h->d_stream_next, 1)) != 0) return rc;
   h->tp.arena_M = 0;
+  leave_persist(h, true);
   AO_CUDA(cudaMemsetAsync(h->d_stream, 0, (size_t)n_episodes * h->rec_bytes, h->stream));
   const uint32_t next = first_key + (uint32_t)n_slots;
   AO_CUDA(cudaMemcpyAsync(h->d_stream_next, &next, 4, cudaMemcpyHostToDevice, h->stream));
@@ -653,6 +703,7 @@ extern "C" int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t firs
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->selfplay_games = n_slots;
   h->stream_episodes = n_episodes;
+  h->last_running = -1;
   return 0;
 }
 
@@ -696,6 +747,7 @@ extern "C" int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int
     h->stream_capacity = n_rec;
   }
   if (n_rec) AO_CUDA(cudaMemsetAsync(h->d_stream, 0, n_rec * h->rec_bytes, h->stream));
+  leave_persist(h, true);
   ao::TreeParams& tp = h->tp;
   tp.stream_out = n_rec ? h->d_stream : nullptr;
   tp.stream_rec_bytes = h->rec_bytes;
@@ -751,6 +803,7 @@ extern "C" int ao_rollout_search(ao_engine* h, int kind, const int32_t* game_ids
     if (root_lens[i] < 1 || root_lens[i] > A) return fail(-1, "root id length %d out of range 1..%d", root_lens[i], A);
   }
   h->tp.arena_M = 0;
+  leave_persist(h, true);
   if (!h->d_wsum) {
     int rc = ealloc(h, &h->d_wsum, (size_t)h->G * A);
     if (rc) return rc;
@@ -777,12 +830,21 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   const bool synth = h->cfg.eval_mode == AO_EVAL_SYNTH;
   const int max_iters = synth ? (1 << 30) : 64;
   int rc;
-  if ((rc = run_rounds(h, h->selfplay_games, max_iters, rounds)) != 0) return rc;
+  if (persist_usable(h, rounds)) {
+    // ONE launch for all `rounds` rounds: tower and tree step fused in the persistent kernel (tower_stag.cu)
+    if ((rc = enter_persist(h, max_iters)) != 0) return rc;
+    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->stream));
+    h->launches += 1;
+  } else {
+    if ((rc = leave_persist(h, false)) != 0) return rc;
+    if ((rc = run_rounds(h, h->selfplay_games, max_iters, rounds)) != 0) return rc;
+  }
   AO_CUDA(launch_sum_selfplay(h));
   h->launches += 1;
   unsigned long long c[8];
   AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
+  h->last_running = (long long)c[1];
   if (out5) for (int i = 0; i < 8; ++i) out5[i] = c[i];
   return 0;
 }
@@ -794,6 +856,37 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
   DeviceGuard guard(h->cfg.device);
   if (h->selfplay_games <= 0) return fail(-1, "call ao_selfplay_begin first");
   if (rounds < 1 || rounds > 4096) return fail(-1, "rounds out of range 1..4096");
+  if (persist_usable(h, rounds)) {
+    // persistent kernel: tree_ms = the one stand-alone tree step that enters the persistent state (0 when already in
+    // it), tower_ms = the persistent kernel itself (tower + fused tree steps of all `rounds` rounds)
+    for (int i = 0; i < 3; ++i)
+      if (!h->pev[i]) AO_CUDA(cudaEventCreate(&h->pev[i]));
+    const int max_iters_p = 64;
+    int rc;
+    AO_CUDA(cudaEventRecord(h->pev[0], h->stream));
+    if ((rc = enter_persist(h, max_iters_p)) != 0) return rc;
+    AO_CUDA(cudaEventRecord(h->pev[1], h->stream));
+    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->stream));
+    h->launches += 1;
+    AO_CUDA(cudaEventRecord(h->pev[2], h->stream));
+    AO_CUDA(launch_sum_selfplay(h));
+    h->launches += 1;
+    unsigned long long c[8];
+    AO_CUDA(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    AO_CUDA(cudaStreamSynchronize(h->stream));
+    float a = 0.f, b = 0.f;
+    AO_CUDA(cudaEventElapsedTime(&a, h->pev[0], h->pev[1]));
+    AO_CUDA(cudaEventElapsedTime(&b, h->pev[1], h->pev[2]));
+    if (tree_ms) *tree_ms = a;
+    if (tower_ms) *tower_ms = b;
+    h->last_running = (long long)c[1];
+    if (out5) for (int i = 0; i < 8; ++i) out5[i] = c[i];
+    return 0;
+  }
+  {
+    int rc0 = leave_persist(h, false);
+    if (rc0) return rc0;
+  }
   while ((int)h->ev.size() < 3 * rounds) {
     cudaEvent_t e;
     AO_CUDA(cudaEventCreate(&e));
@@ -818,6 +911,7 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
   }
   if (tree_ms) *tree_ms = t_tree;
   if (tower_ms) *tower_ms = t_tower;
+  h->last_running = (long long)c[1];
   if (out5) for (int i = 0; i < 8; ++i) out5[i] = c[i];
   return 0;
 }
@@ -852,6 +946,7 @@ extern "C" int ao_set_nn_precision_set(ao_engine* h, int set, int mode) {
   if (set < 0 || set > 1) return fail(-1, "weight set %d out of range 0..1", set);
   DeviceGuard guard(h->cfg.device);
   if (mode != AO_NN_FP16 && mode != AO_NN_FP16X3 && mode != AO_NN_FP16_1CTA && mode != AO_NN_FP16_LOCKSTEP) return fail(-1, "unknown nn_precision %d", mode);
+  if (set == 0 && mode != h->ws[0].precision) leave_persist(h, false);
   AO_CUDA(cudaStreamSynchronize(h->stream));
   h->ws[set].precision = mode;
   if (set == 0) h->cfg.nn_precision = mode;

@@ -93,6 +93,9 @@ struct TreeParams {
   size_t stream_rec_bytes;
   uint32_t* stream_next_key;   // device counter
   uint32_t stream_first_key, stream_key_end;
+  // request slot = game slot instead of the next free slot of the round (the persistent self-play kernel evaluates game
+  // g in a fixed CTA pass, see tower_stag.cu); 0 = dense packing through nn_count
+  int static_slots;
   // arena (eval_main.py:204-333): matches [0, arena_M); side s (0 player, 1 enemy) of match m lives in game slot
   // s * arena_M + m with its own tree and decision stream; network requests of side s go to nn slots
   // [s * arena_M, ...) and are evaluated with weight set s.  0 = self-play / facade mode.
@@ -156,6 +159,8 @@ cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const Leaf
                          int n_max, float* policy, float* value, int num_sms, cudaStream_t s);
 cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const int32_t* n_ptr, int n_max,
                               float* policy, float* value, int num_sms, cudaStream_t s);
+cudaError_t launch_selfplay_persist(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds,
+                                    int num_sms, cudaStream_t s);
 cudaError_t tower_configure(int B, int precision);
 cudaError_t launch_pack_states(const float* states_dev, int n, int B, int inplanes, LeafIn* out, int* bad_flag_dev,
                                cudaStream_t s);

@@ -29,20 +29,27 @@
 // the tensor pipe, two threads with their own accumulators one per ~87 (tools/probe_mma_rate.py).
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "tower_common.cuh"
+#include "tree_device.cuh"
 
 namespace ao {
 namespace {
 
 constexpr int kStagThreads = 480;
 constexpr int kHeadThreads = 128;
+constexpr int kMaxPassesPerCta = 64;  // persistent mode: passes a CTA owns (4096 games of 15x15 on 148 CTAs: 28)
 
-template <int B>
+// PERSIST (the persistent self-play kernel): the head scratch is shared with the per-warp scratch of the tree step the
+// head warps run after their head job (tree_device.cuh WarpSmem, sized for this board), and the network's answer is
+// handed over in shared memory (pol / val) instead of through HBM.
+template <int B, bool PERSIST>
 struct StagSmem {
   using G = Geo<B>;
   static constexpr int kSlots = 9;
   static constexpr int kSlotBytes = kStageBytes / 2;
+  static constexpr int APad = (G::A + 7) / 8 * 8;
   static constexpr int act = 0;
   static constexpr int wring = G::ActBytes;
   static constexpr int bias2 = wring + kSlots * kSlotBytes;           // [2][128] f32: bias of the layer in flight
@@ -51,21 +58,38 @@ struct StagSmem {
   static constexpr int logits = feat + G::GPC * 3 * G::A * 4;         // [GPC][A]
   static constexpr int hidden = logits + G::GPC * G::A * 4;           // [GPC][128]
   static constexpr int red = hidden + G::GPC * kC * 4;                // [GPC][2]
-  static constexpr int masks = (red + G::GPC * 2 * 4 + 15) / 16 * 16; // [kTiles][9][4]
+  static constexpr int head_end = red + G::GPC * 2 * 4;
+  // tree-step scratch of head warp g (aliases feat .. red, which are dead once the policy is final):
+  // dbuf f64[APad] | dbuf2 f64[APad] | order u8[256] | table i16[128] | rows u16[2][32]
+  static constexpr int kTreeWarpBytes = 16 * APad + 256 + 256 + 128;
+  static constexpr int tree_end = feat + G::GPC * kTreeWarpBytes;
+  static constexpr int scratch_end = PERSIST ? (tree_end > head_end ? tree_end : head_end) : head_end;
+  static constexpr int pol = (scratch_end + 15) / 16 * 16;            // PERSIST: [GPC][APad] f32 final policy
+  static constexpr int val = pol + (PERSIST ? G::GPC * APad * 4 : 0); // PERSIST: [4] f32 values
+  static constexpr int leaf_done = val + (PERSIST ? 16 : 0);          // PERSIST: [kMaxPassesPerCta] u32
+  static constexpr int masks = (leaf_done + (PERSIST ? kMaxPassesPerCta * 4 : 0) + 15) / 16 * 16;  // [kTiles][9][4]
   static constexpr int bars = masks + kTiles * 9 * 4 * 4;
   static constexpr int kBars = 3 * kSlots + 4 + 2 + 2 + 2;
   static constexpr int total = bars + kBars * 8 + 16;
   static_assert(G::ActBytes % 1024 == 0, "weight ring alignment");
+  static_assert(feat % 8 == 0, "tree scratch holds doubles");
 };
 
 __device__ __forceinline__ void head_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
-template <int B>
+// PERSIST = the persistent self-play kernel: `rounds` lock-step rounds in ONE launch.  Game g is always evaluated in
+// the same pass of the same CTA (request slot = game slot, TreeParams.static_slots), and as soon as the head warps have
+// the policy / value of a pass they run the tree step of those games themselves (consume the answer, expand, back up,
+// play the move when the search is complete, select the next leaf and write its request) while the tower of the next
+// pass is already running.  Games never interact, so no grid-wide synchronisation is needed: every CTA pair cycles
+// through its own games; the tree work, the launch gaps and the per-launch ramp of the two-kernel round disappear
+// behind the tensor pipe.
+template <int B, bool PERSIST>
 __global__ void __launch_bounds__(kStagThreads, 1)
 tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
-                  float* __restrict__ policy, float* __restrict__ value) {
+                  float* __restrict__ policy, float* __restrict__ value, TreeParams P, int rounds) {
   using G = Geo<B>;
-  using SL = StagSmem<B>;
+  using SL = StagSmem<B, PERSIST>;
   constexpr bool PAIR = true;
   constexpr int NSLOT = SL::kSlots;
   constexpr uint32_t kSlotBytes = SL::kSlotBytes;
@@ -74,6 +98,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
 
   int n = n_ptr ? *n_ptr : n_max;
   if (n > n_max) n = n_max;
+  if (!PERSIST) rounds = 1;
   {
     int g0_, ng_, nt_;
     if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) return;
@@ -96,6 +121,9 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
   uint64_t* bar_feat_full = bar_bias + 2;       // epilogue -> heads: 1x1-conv sums of the pass are complete
   uint64_t* bar_feat_free = bar_feat_full + 1;  // heads -> epilogue: s_feat is consumed and zeroed again
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_feat_free + 1);
+  float* s_pol = reinterpret_cast<float*>(smem + SL::pol);                       // PERSIST only
+  float* s_val = reinterpret_cast<float*>(smem + SL::val);
+  volatile uint32_t* s_leaf_done = reinterpret_cast<volatile uint32_t*>(smem + SL::leaf_done);
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -105,6 +133,8 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
   for (int i = tid; i < G::ActBytes / 16; i += kStagThreads) reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 3 * kC; i += kStagThreads) s_headw[i] = W.head_w[i];
   for (int i = tid; i < G::GPC * 3 * G::A; i += kStagThreads) s_feat[i] = 0.f;
+  if (PERSIST)
+    for (int i = tid; i < kMaxPassesPerCta; i += kStagThreads) s_leaf_done[i] = 0u;
   for (int i = tid; i < kTiles * 9 * 4; i += kStagThreads) {
     const int tile = i / 36, tap = (i / 4) % 9, word = i % 4;
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -144,6 +174,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
     if (lane == 0) {
       uint32_t lc = 0;
       int g0, ng, ntiles;
+      for (int rd = 0; rd < rounds; ++rd)
       for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         size_t off = 0;
         for (int l = 0; l < n_layers; ++l, ++lc) {
@@ -172,7 +203,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       if (stream == 0 && lane == 0) {
         int g0, ng, ntiles, n_k = 0;
         while (get_pass<G::GPC, G::A, PAIR>(n_k, n, g0, ng, ntiles)) ++n_k;
-        const uint32_t n_stage = (uint32_t)(n_k * n_layers) * 9u;
+        const uint32_t n_stage = (uint32_t)(n_k * n_layers) * 9u * (uint32_t)rounds;
         for (uint32_t si = 0; si < n_stage; ++si) {
           const uint32_t s = si % 9u;
           mbar_wait(&bar_full[s], (si / 9u) & 1u);
@@ -190,6 +221,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       uint32_t lc = 0, act_ph = 0;
       AO_DBG(long long dbg_act_wait = 0, dbg_full_wait = 0; const long long dbg_t0 = W.dbg ? clock64() : 0;)
       int g0, ng, ntiles;
+      for (int rd = 0; rd < rounds; ++rd)
       for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         if (stream == 1 && ntiles < kTiles) {  // one-game tail pass: tile 1 holds no board
           lc += (uint32_t)n_layers;
@@ -310,15 +342,22 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
     };
 
     int g0, ng, ntiles;
+    for (int rd = 0; rd < rounds; ++rd)
     for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+      if (PERSIST && rd > 0) {
+        // the requests of this pass were written by this CTA's head warps one round ago (long done; just make sure)
+        while (s_leaf_done[k] < (uint32_t)(rd * ng)) __nanosleep(200);
+        __threadfence_block();
+      }
       {
         uint4 c0 = make_uint4(0, 0, 0, 0);
         if (gl_in < G::GPC && gl_in < ng) {
           const LeafIn* li = &in[g0 + gl_in];
           const int yy = pos_in / B, xx = pos_in % B;
-          const uint32_t b0 = (li->plane[0][yy] >> xx) & 1u, b1 = (li->plane[1][yy] >> xx) & 1u;
-          const uint32_t b2 = (li->plane[2][yy] >> xx) & 1u, b3 = (li->plane[3][yy] >> xx) & 1u;
-          const uint32_t b4 = li->colour & 1u;
+          // L1-bypassing loads: in persistent mode the request was stored by another warp of this SM moments ago
+          const uint32_t b0 = (__ldcg(&li->plane[0][yy]) >> xx) & 1u, b1 = (__ldcg(&li->plane[1][yy]) >> xx) & 1u;
+          const uint32_t b2 = (__ldcg(&li->plane[2][yy]) >> xx) & 1u, b3 = (__ldcg(&li->plane[3][yy]) >> xx) & 1u;
+          const uint32_t b4 = __ldcg(&li->colour) & 1u;
           c0.x = (b0 ? 0x3C00u : 0u) | (b1 ? 0x3C000000u : 0u);
           c0.y = (b2 ? 0x3C00u : 0u) | (b3 ? 0x3C000000u : 0u);
           c0.z = (b4 ? 0x3C00u : 0u);
@@ -444,6 +483,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
     const int ht = tid - 10 * 32, hw = warp - 10;
     uint32_t pass_ph = 0;
     int g0, ng, ntiles;
+    for (int rd = 0; rd < rounds; ++rd)
     for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
       mbar_wait_sleep(bar_feat_full, pass_ph, 2000);  // a whole tower pass (~100 us) between two head jobs
       pass_ph ^= 1u;
@@ -489,16 +529,44 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
         if (lane == 0) {
           s_red[hw * 2 + 0] = mx;
           s_red[hw * 2 + 1] = sum;
-          value[g0 + hw] = tanhf(hv + W.vfc2_b);
+          const float v = tanhf(hv + W.vfc2_b);
+          if (PERSIST) s_val[hw] = v;
+          else value[g0 + hw] = v;
         }
       }
-      for (int i = ht; i < G::GPC * 3 * G::A; i += kHeadThreads) s_feat[i] = 0.f;  // ready for the next pass's sums
+      if (!PERSIST)
+        for (int i = ht; i < G::GPC * 3 * G::A; i += kHeadThreads) s_feat[i] = 0.f;  // ready for the next pass's sums
       head_bar_sync();
       for (int o = ht; o < G::GPC * G::A; o += kHeadThreads) {
         const int pg = o / G::A, po = o % G::A;
-        if (pg < ng) policy[(size_t)(g0 + pg) * G::A + po] = expf(s_logits[o] - s_red[pg * 2]) / s_red[pg * 2 + 1];
+        if (pg < ng) {
+          const float pr = expf(s_logits[o] - s_red[pg * 2]) / s_red[pg * 2 + 1];
+          if (PERSIST) s_pol[pg * SL::APad + po] = pr;
+          else policy[(size_t)(g0 + pg) * G::A + po] = pr;
+        }
       }
       head_bar_sync();  // s_logits / s_red are rewritten by the next pass only after this
+      if (PERSIST) {
+        // ---- the tree step of this pass's games (tree_device.cuh), head warp g <-> game g0 + g: the head scratch is
+        // dead now and becomes the warp's tree scratch; the answer is read from s_pol / s_val
+        if (hw < ng) {
+          uint8_t* ts = smem + SL::feat + hw * SL::kTreeWarpBytes;
+          WarpSmem ws;
+          ws.dbuf = reinterpret_cast<double*>(ts);
+          ws.dbuf2 = ws.dbuf + SL::APad;
+          ws.order = reinterpret_cast<uint8_t*>(ws.dbuf2 + SL::APad);
+          ws.table = reinterpret_cast<int16_t*>(ws.order + 256);
+          ws.rows = reinterpret_cast<uint16_t(*)[32]>(ws.table + 128);
+          ws.pol = s_pol + hw * SL::APad;
+          (void)tree_step_game<(G::A <= 96 ? 3 : 8)>(P, g0 + hw, &ws, lane, 64, true, s_val[hw]);
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) atomicAdd(const_cast<uint32_t*>(s_leaf_done) + k, 1u);
+        }
+        head_bar_sync();
+        for (int i = ht; i < G::GPC * 3 * G::A; i += kHeadThreads) s_feat[i] = 0.f;  // ready for the next pass's sums
+        head_bar_sync();
+      }
       if (lane == 0) mbar_arrive(bar_feat_free);
     }
   }
@@ -508,14 +576,14 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
   if (warp == 9) tmem_dealloc_pair<512>(tmem);
 }
 
-template <int B>
+template <int B, bool PERSIST>
 cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
-                                float* value, int num_sms, cudaStream_t s) {
-  using SL = StagSmem<B>;
+                                float* value, int num_sms, const TreeParams& P, int rounds, cudaStream_t s) {
+  using SL = StagSmem<B, PERSIST>;
   static_assert(SL::total <= 232448, "staggered tower kernel exceeds 227 KB of shared memory");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tower_stag_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
+    cudaError_t e = cudaFuncSetAttribute(tower_stag_kernel<B, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -533,7 +601,7 @@ cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tower_stag_kernel<B>, w, in, n_ptr, n_max, policy, value);
+  return cudaLaunchKernelEx(&cfg, tower_stag_kernel<B, PERSIST>, w, in, n_ptr, n_max, policy, value, P, rounds);
 }
 
 }  // namespace
@@ -541,8 +609,23 @@ cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const i
 cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const int32_t* n_ptr, int n_max,
                               float* policy, float* value, int num_sms, cudaStream_t s) {
   if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
-  if (B == 9) return launch_tower_stag_t<9>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-  if (B == 15) return launch_tower_stag_t<15>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  TreeParams none;
+  memset(&none, 0, sizeof none);
+  if (B == 9) return launch_tower_stag_t<9, false>(w, in, n_ptr, n_max, policy, value, num_sms, none, 1, s);
+  if (B == 15) return launch_tower_stag_t<15, false>(w, in, n_ptr, n_max, policy, value, num_sms, none, 1, s);
+  return cudaErrorInvalidValue;
+}
+
+// The persistent self-play kernel: `rounds` lock-step rounds over the game slots [0, n_games) in one launch.  Needs
+// p.static_slots = 1 and every running game in ST_WAIT_NN with its request in p.nn_in[game] (engine.cu enter_persist).
+cudaError_t launch_selfplay_persist(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds,
+                                    int num_sms, cudaStream_t s) {
+  if (w.n_layers > kMaxLayers || !p.static_slots) return cudaErrorInvalidValue;
+  const int per_pass = B == 9 ? Geo<9>::GPC : Geo<15>::GPC;
+  const int grid = n_games < num_sms ? n_games : num_sms;
+  if ((n_games + per_pass * grid - 1) / (per_pass * grid) + 1 > kMaxPassesPerCta) return cudaErrorInvalidValue;
+  if (B == 9) return launch_tower_stag_t<9, true>(w, p.nn_in, nullptr, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
+  if (B == 15) return launch_tower_stag_t<15, true>(w, p.nn_in, nullptr, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
   return cudaErrorInvalidValue;
 }
 
