@@ -225,6 +225,9 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
         if (stream == 1 && ntiles < kTiles) {  // one-game tail pass: tile 1 holds no board
           lc += (uint32_t)n_layers;
+          // tile 0's operand-ready barriers complete n_layers phases in this pass without this warp looking: keep the
+          // parities in step (matters in the persistent kernel, where a two-tile pass of the next round follows)
+          if (n_layers & 1) act_ph ^= 3u;
           continue;
         }
         for (int l = 0; l < n_layers; ++l, ++lc) {
