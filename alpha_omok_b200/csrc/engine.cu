@@ -223,12 +223,13 @@ bool persist_usable(const ao_engine* h, int rounds) {
 }
 // two-kernel state (answers pending in nn_policy[gm->nn_slot], or nothing pending) -> persistent state: one tree step
 // with static request slots consumes what is pending and leaves every running game's next request in nn_in[game]
-int enter_persist(ao_engine* h, int max_iters) {
+int enter_persist(ao_engine* h, int max_iters, int n = -1) {
   if (h->persist_pending) return 0;
+  if (n < 0) n = h->selfplay_games;
   h->tp.static_slots = 1;
   AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, 2 * sizeof(int32_t), h->stream));
   AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
-  AO_CUDA(ao::launch_tree_step(h->tp, nullptr, h->selfplay_games, max_iters, h->stream));
+  AO_CUDA(ao::launch_tree_step(h->tp, nullptr, n, max_iters, h->stream));
   h->launches += 1;
   h->persist_pending = true;
   return 0;
@@ -582,6 +583,27 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
   const int max_iters = synth ? (1 << 30) : 64;
   int active = 1, rounds = 0;
   const int blind = synth ? 0 : h->cfg.num_mcts;  // at least this many rounds are needed before anyone can finish
+  bool identity = true;  // the persistent kernel walks the slots [0, n): usable when the caller's ids are exactly those
+  for (int i = 0; i < n && identity; ++i) identity = game_ids[i] == i;
+  if (identity && h->persist_allowed && !synth && h->ws[0].precision == AO_NN_FP16) {
+    // the whole search in one launch of the persistent kernel (tower + fused tree step): a search needs num_mcts (+1)
+    // simulations and every round completes at least one per game; finished games simply stop asking
+    if ((rc = enter_persist(h, max_iters, n)) != 0) return rc;
+    int todo = h->cfg.num_mcts + 1;
+    while (active > 0) {
+      AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, todo, h->num_sms, h->stream));
+      h->launches += 1;
+      rounds += todo;
+      AO_CUDA(ao::launch_sum_counters(h->tp, n, n, h->d_counters, h->stream));
+      unsigned long long cc[8];
+      AO_CUDA(cudaMemcpyAsync(cc, h->d_counters, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+      AO_CUDA(cudaStreamSynchronize(h->stream));
+      active = (int)cc[1];
+      todo = 4;
+      if (rounds > 4 * (h->cfg.num_mcts + 2) + 64) return fail(-6, "search did not converge after %d rounds", rounds);
+    }
+    leave_persist(h, true);
+  }
   while (active > 0) {
     if ((rc = run_round(h, h->d_ids, n, max_iters)) != 0) return rc;
     ++rounds;

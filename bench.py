@@ -466,7 +466,11 @@ def run_ours(a):
             "config": workload_config(a, world),
             "moves_per_s": tot[3] / (ms_max * 1e-3), "games_finished_in_window": int(tot[4]),
             "gpu_launches": int(tot[7]),
-            "roofline": {"bound": "tensor", "kernel": "tower_stag_kernel", "achieved": achieved, "peak": sustained,
+            "roofline": {"bound": "tensor",
+                         "kernel": "tower_stag_kernel<9, PERSIST> - the persistent self-play kernel: PVNet tower of all leaves "
+                                   "of all rounds of a step in ONE launch, the tree step of every pass fused in (head warps); "
+                                   "with AO_NO_PERSIST=1: tower_stag_kernel<9> per round + tree_step_kernel",
+                         "achieved": achieved, "peak": sustained,
                          "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": peak_src + ", bf16 sustained",
                          "frac_of_burst": achieved / burst,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (4096 leaves), from the committed
