@@ -1,8 +1,11 @@
-"""Quick device-side throughput probe: G concurrent self-play games, lock-step rounds, per-kernel times."""
+"""Quick device-side throughput probe: G concurrent self-play games, lock-step rounds, per-kernel times and the tower's
+cycle counters.  The counters exist only in the probe library, which this tool therefore selects (AO_USE_PROBE_LIB)."""
 import argparse
 import os
 import sys
 import time
+
+os.environ.setdefault("AO_USE_PROBE_LIB", "1")
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import _cabi  # noqa: E402

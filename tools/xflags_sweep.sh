@@ -4,5 +4,5 @@
 # 64 no accumulator loads (tcgen05.ld)
 for f in ${@:-0 16 32 64 48 112 4 8}; do
   echo "== AO_TOWER_XFLAGS=$f"
-  AO_TOWER_XFLAGS=$f timeout 200 python tools/perf_selfplay.py --rounds 100 --reps 6 2>&1 | tail -3
+  AO_USE_PROBE_LIB=1 AO_TOWER_XFLAGS=$f timeout 200 python tools/perf_selfplay.py --rounds 100 --reps 6 2>&1 | tail -3
 done
