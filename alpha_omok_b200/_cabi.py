@@ -214,12 +214,33 @@ class Engine:
     def choose_nn_precision(self, tol=5e-5, n_probe=48, seed=0, which=0):
         """Pick the cheapest tower mode whose outputs agree with the hi/lo-split mode within `tol` on a set of probe
         positions (the split mode is within 1e-4 of fp32 even on trained nets). Random-init nets stay on
-        the single-pass fp16 mode; trained nets switch to AO_NN_FP16X3."""
+        the single-pass fp16 mode; trained nets switch to AO_NN_FP16X3.  A heuristic, not a proof: the probe is half
+        uniformly scattered stones and half clustered ones (each stone next to an earlier one, like real games); `tol`
+        is half the contract.  Force a mode with nn_precision=AO_NN_* where the guarantee matters."""
         rs = np.random.RandomState(seed)
         states = np.zeros((n_probe, 5, self.B, self.B), np.float32)
-        for i in range(n_probe):  # random legal-looking positions: k stones, alternating colours
-            k = int(rs.randint(0, self.A - 20))
-            cells = rs.permutation(self.A)[:k]
+        B = self.B
+        for i in range(n_probe):  # legal-looking positions: k stones, alternating colours
+            k = int(rs.randint(0, max(1, self.A - 20)))
+            if i % 2 == 0:
+                cells = rs.permutation(self.A)[:k]
+            else:  # clustered: every stone within distance 2 of an earlier one
+                cells, taken = [], set()
+                c = int(rs.randint(0, self.A))
+                for _ in range(k):
+                    for _try in range(30):
+                        if cells:
+                            b = cells[int(rs.randint(0, len(cells)))]
+                            y, x = b // B + int(rs.randint(-2, 3)), b % B + int(rs.randint(-2, 3))
+                            c = y * B + x if 0 <= y < B and 0 <= x < B else -1
+                        if c >= 0 and c not in taken:
+                            break
+                    else:
+                        free = [q for q in range(self.A) if q not in taken]
+                        c = free[int(rs.randint(0, len(free)))]
+                    cells.append(c)
+                    taken.add(c)
+                cells = np.asarray(cells, np.int64)
             own, opp = cells[k % 2::2], cells[(k + 1) % 2::2]
             states[i, 2].flat[own] = 1
             states[i, 3].flat[opp] = 1

@@ -57,14 +57,29 @@ class _EngineOwner:
                             noise=self.noise, n_blocks=n_blocks, inplanes=self.inplanes, c_puct=self.c_puct,
                             alpha=self.alpha, **kw)
 
+    def invalidate_weights(self):
+        """Force a re-upload of `self.model`'s weights at the next search.  Needed only after in-place writes that bypass
+        autograd's version counter on GPU-resident parameters (`p.data.mul_()`, EMA code, ...): optimizer steps,
+        `load_state_dict` and every change to CPU-resident weights are detected automatically."""
+        self._fingerprint = None
+
     def _sync_weights(self):
         if self.model is None:
             raise RuntimeError("ZeroAgent.model is not set (assign a PVNet before searching, main.py:81)")
         sd = self.model.state_dict()
         # state_dict() hands out fresh detached aliases on every call: identify the weights by storage address and
-        # version counter (shared with the parameter; bumped by optimizer steps and load_state_dict), not by id()
-        fp = (id(self.model),) + tuple((t.data_ptr(), t._version) if hasattr(t, "data_ptr") else (id(t), 0)
-                                       for t in sd.values())
+        # version counter (shared with the parameter; bumped by optimizer steps and load_state_dict), not by id();
+        # `.data` writes use their own counter, so CPU tensors also contribute a few sampled values (cheap, no sync)
+        def sample(t):
+            if not hasattr(t, "data_ptr"):
+                return (id(t), 0, 0.0)
+            probe = 0.0
+            if t.device.type == "cpu" and t.numel() and t.is_floating_point():
+                flat = t.reshape(-1)
+                probe = float(flat[:: max(1, flat.numel() // 4)][:4].double().sum())
+            return (t.data_ptr(), t._version, probe)
+
+        fp = (id(self.model),) + tuple(sample(t) for t in sd.values())
         if fp != self._fingerprint:
             self._engine.load_state_dict(sd)
             self._fingerprint = fp

@@ -120,7 +120,12 @@ class PVNet(nn.Module):
 
     # ---- weights -> device engine (shared with ZeroAgent)
     def weights_fingerprint(self):
+        """storage address + version counter per tensor (bumped by optimizer steps / load_state_dict); writes through
+        `.data` bypass the counter - call `invalidate_inference_weights()` after those"""
         return tuple((t.data_ptr(), t._version) for t in self.state_dict().values())
+
+    def invalidate_inference_weights(self):
+        self._ao_fingerprint = None
 
     def _inference_engine(self, batch):
         fp = self.weights_fingerprint()
