@@ -98,6 +98,9 @@ struct ao_engine {
   bool timing;
   std::vector<cudaEvent_t> ev;  // [tree_begin, tree_end(=tower_begin), tower_end] per round
   unsigned long long launches;  // kernels launched by this engine (bench's gpu_launches)
+  uint32_t ring_cap;            // request-ring capacity per weight set (power of two >= max_games)
+  uint32_t* d_tower_done;       // [2] finished-CTA counters of the running tower launches
+  bool defer_tail;              // towers leave a ragged last wave for the next round (AO_NO_DEFER=1 disables)
   float* d_fwd_states;          // ao_nn_forward staging (lazily allocated)
   int* d_fwd_bad;
   float* d_wsum;                // ao_rollout_search: w of the root's children
@@ -121,9 +124,28 @@ int ealloc(ao_engine* h, T** p, size_t count) {
   return 0;
 }
 
-// one lock-step round: tree step (consume NN output, select next leaf) then the tower on the emitted requests
+ao::NNQueue queue_of(const ao_engine* h, int set, bool defer) {
+  ao::NNQueue q;
+  q.tail = h->tp.nn_count + set;
+  q.head = h->tp.nn_head + set;
+  q.done = h->d_tower_done + set;
+  q.mask = h->tp.nn_ring_mask;
+  q.defer = defer && h->defer_tail ? 1 : 0;
+  return q;
+}
+// all game slots are being reset: requests still queued belong to nobody - mark them served
+cudaError_t drop_queued_requests(ao_engine* h) {
+  return cudaMemcpyAsync(h->tp.nn_head, h->tp.nn_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream);
+}
+ao::NNQueue no_queue() {
+  ao::NNQueue q;
+  memset(&q, 0, sizeof q);
+  return q;
+}
+
+// one lock-step round: tree step (consume the answers that have arrived, select next leaves, queue their requests) then
+// the tower(s) on the queued requests
 int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int timed_slot = -1) {
-  AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, 2 * sizeof(int32_t), h->stream));
   AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
   if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 0], h->stream));
   AO_CUDA(ao::launch_tree_step(h->tp, ids_dev, n, max_iters, h->stream));
@@ -132,13 +154,14 @@ int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int ti
   if (h->cfg.eval_mode == AO_EVAL_PVNET) {
     const int M = h->tp.arena_M;
     if (!(M > 0 && h->tp.arena_kind[0] != AO_SIDE_ZERO)) {
-      AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, h->tp.nn_count, n, h->tp.nn_policy,
-                               h->tp.nn_value, h->num_sms, h->stream));
+      AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, queue_of(h, 0, true), n,
+                               h->tp.nn_policy, h->tp.nn_value, h->num_sms, h->stream));
       h->launches += 1;
     }
-    if (M > 0 && h->tp.arena_kind[1] == AO_SIDE_ZERO) {  // the enemy's requests: nn slots [M, 2M), weight set 1
-      AO_CUDA(ao::launch_tower(h->ws[1].tw, h->B, h->ws[1].precision, h->tp.nn_in + M, h->tp.nn_count + 1, n,
-                               h->tp.nn_policy + (size_t)M * h->A, h->tp.nn_value + M, h->num_sms, h->stream));
+    if (M > 0 && h->tp.arena_kind[1] == AO_SIDE_ZERO) {  // the enemy's queue: second ring, weight set 1
+      const size_t cap = h->ring_cap;
+      AO_CUDA(ao::launch_tower(h->ws[1].tw, h->B, h->ws[1].precision, h->tp.nn_in + cap, queue_of(h, 1, true), n,
+                               h->tp.nn_policy + cap * h->A, h->tp.nn_value + cap, h->num_sms, h->stream));
       h->launches += 1;
     }
   }
@@ -226,8 +249,11 @@ bool persist_usable(const ao_engine* h, int rounds) {
 int enter_persist(ao_engine* h, int max_iters, int n = -1) {
   if (h->persist_pending) return 0;
   if (n < 0) n = h->selfplay_games;
+  // answer whatever is still queued (a deferred tail of the last two-kernel round), without deferring again
+  AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, queue_of(h, 0, false), n, h->tp.nn_policy,
+                           h->tp.nn_value, h->num_sms, h->stream));
+  h->launches += 1;
   h->tp.static_slots = 1;
-  AO_CUDA(cudaMemsetAsync(h->tp.nn_count, 0, 2 * sizeof(int32_t), h->stream));
   AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
   AO_CUDA(ao::launch_tree_step(h->tp, nullptr, n, max_iters, h->stream));
   h->launches += 1;
@@ -239,7 +265,7 @@ int enter_persist(ao_engine* h, int max_iters, int n = -1) {
 // about to be discarded anyway (games reset / new roots).
 int leave_persist(ao_engine* h, bool drop) {
   if (h->persist_pending && !drop) {
-    AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, nullptr, h->selfplay_games, h->tp.nn_policy,
+    AO_CUDA(ao::launch_tower(h->ws[0].tw, h->B, h->ws[0].precision, h->tp.nn_in, no_queue(), h->selfplay_games, h->tp.nn_policy,
                              h->tp.nn_value, h->num_sms, h->stream));
     h->launches += 1;
   }
@@ -344,10 +370,16 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   EA(tp.gc_new, (size_t)G * tp.gc_cap);
   EA(tp.rec_visits, (size_t)G * A * A);
   if (tp.tape_rows) { EA(tp.gamma_tape, (size_t)G * tp.tape_rows * A); }
-  EA(tp.nn_in, (size_t)G);
-  EA(tp.nn_policy, (size_t)G * A);
-  EA(tp.nn_value, (size_t)G);
+  h->ring_cap = 1u;
+  while (h->ring_cap < (uint32_t)G) h->ring_cap <<= 1;
+  tp.nn_ring_mask = h->ring_cap - 1u;
+  h->defer_tail = getenv("AO_NO_DEFER") == nullptr;
+  EA(tp.nn_in, (size_t)2 * h->ring_cap);
+  EA(tp.nn_policy, (size_t)2 * h->ring_cap * A);
+  EA(tp.nn_value, (size_t)2 * h->ring_cap);
   EA(tp.nn_count, 2);
+  EA(tp.nn_head, 2);
+  EA(h->d_tower_done, 2);
   EA(tp.n_active, 1);
   if (tp.nn_log_cap > 0) {
     EA(tp.nnlog_policy, (size_t)G * tp.nn_log_cap * A);
@@ -366,6 +398,10 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
 #undef EA
   if (cudaMallocHost(reinterpret_cast<void**>(&h->h_pinned), 64) != cudaSuccess) { ao_engine_destroy(h); return fail(-2, "cudaMallocHost failed"); }
   cudaError_t e = cudaMemsetAsync(tp.games, 0, (size_t)G * sizeof(ao::Game), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(tp.nn_count, 0, 2 * sizeof(uint32_t), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(tp.nn_head, 0, 2 * sizeof(uint32_t), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->d_tower_done, 0, 2 * sizeof(uint32_t), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(tp.nn_in, 0, (size_t)2 * h->ring_cap * sizeof(ao::LeafIn), h->stream);
   if (e == cudaSuccess && tp.gamma_tape) e = cudaMemsetAsync(tp.gamma_tape, 0, (size_t)G * tp.tape_rows * A * sizeof(double), h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) { ao_engine_destroy(h); return fail(-2, "engine init: %s", cudaGetErrorString(e)); }
@@ -649,7 +685,7 @@ extern "C" int ao_nn_forward_set(ao_engine* h, int set, const float* states, int
     const int m = n - o < chunk ? n - o : chunk;
     cudaError_t e = cudaMemcpyAsync(d_states, states + (size_t)o * C * A, (size_t)m * C * A * 4, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = ao::launch_pack_states(d_states, m, h->B, C, h->tp.nn_in, d_bad, h->stream);
-    if (e == cudaSuccess) e = ao::launch_tower(h->ws[set].tw, h->B, h->ws[set].precision, h->tp.nn_in, nullptr, m, h->tp.nn_policy, h->tp.nn_value, h->num_sms, h->stream);
+    if (e == cudaSuccess) e = ao::launch_tower(h->ws[set].tw, h->B, h->ws[set].precision, h->tp.nn_in, no_queue(), m, h->tp.nn_policy, h->tp.nn_value, h->num_sms, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p + (size_t)o * A, h->tp.nn_policy, (size_t)m * A * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(v + o, h->tp.nn_value, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -674,6 +710,7 @@ extern "C" int ao_selfplay_begin_mode(ao_engine* h, int n_games, uint32_t first_
   if (rc) return rc;
   h->tp.arena_M = 0;
   leave_persist(h, true);
+  AO_CUDA(drop_queued_requests(h));
   std::vector<uint32_t> keys(n_games);
   for (int i = 0; i < n_games; ++i) keys[i] = first_key + (uint32_t)i;
   AO_CUDA(cudaMemcpyAsync(h->d_keys, keys.data(), (size_t)n_games * 4, cudaMemcpyHostToDevice, h->stream));
@@ -710,6 +747,7 @@ extern "C" int ao_selfplay_stream_begin(ao_engine* h, int n_slots, uint32_t firs
   if (!h->d_stream_next && (rc = ealloc(h, &h->d_stream_next, 1)) != 0) return rc;
   h->tp.arena_M = 0;
   leave_persist(h, true);
+  AO_CUDA(drop_queued_requests(h));
   AO_CUDA(cudaMemsetAsync(h->d_stream, 0, (size_t)n_episodes * h->rec_bytes, h->stream));
   const uint32_t next = first_key + (uint32_t)n_slots;
   AO_CUDA(cudaMemcpyAsync(h->d_stream_next, &next, 4, cudaMemcpyHostToDevice, h->stream));
@@ -770,6 +808,7 @@ extern "C" int ao_arena_begin(ao_engine* h, int n_slots, uint32_t first_key, int
   }
   if (n_rec) AO_CUDA(cudaMemsetAsync(h->d_stream, 0, n_rec * h->rec_bytes, h->stream));
   leave_persist(h, true);
+  AO_CUDA(drop_queued_requests(h));
   ao::TreeParams& tp = h->tp;
   tp.stream_out = n_rec ? h->d_stream : nullptr;
   tp.stream_rec_bytes = h->rec_bytes;

@@ -42,6 +42,8 @@ struct __align__(16) Game {
   int32_t leaf_depth;        // path length
   int32_t leaf_n_moves;
   int32_t nn_slot;
+  uint32_t nn_ticket;        // ticket of the pending request in its weight set's queue (answered once head > ticket)
+  int32_t nn_static;         // the pending request sits in the game's own slot (persistent kernel) and is answered
   int32_t winner;
   int32_t error;
   uint32_t nn_log_count;
@@ -83,7 +85,12 @@ struct TreeParams {
   LeafIn* nn_in;         // [G]
   float* nn_policy;      // [G][A]
   float* nn_value;       // [G]
-  int32_t* nn_count;     // device counters [2]: requests of weight set 0 / 1 emitted this round
+  // request queues, one per weight set: rings of nn_ring_mask + 1 slots inside nn_in / nn_policy / nn_value (set s at
+  // offset s * (nn_ring_mask + 1)); the tree step issues tickets (nn_count = tails, monotonic), the tower serves them in
+  // order and advances nn_head - possibly leaving a ragged tail of requests for the next round (NNQueue.defer)
+  uint32_t* nn_count;    // [2] tickets issued
+  uint32_t* nn_head;     // [2] tickets served
+  uint32_t nn_ring_mask;
   int32_t* n_active;     // device counter
   float* nnlog_policy;   // [G][cap][A]
   float* nnlog_value;    // [G][cap]
@@ -140,6 +147,15 @@ struct TowerWeights {
 #define AO_XFLAG(W, bit) false
 #endif
 
+// Request queue of one weight set as the tower sees it.  tail == nullptr: no queue, serve slots [0, n_max).
+struct NNQueue {
+  const uint32_t* tail;  // tickets issued so far (device)
+  uint32_t* head;        // tickets served so far (device); advanced by the last CTA of a tower launch to finish
+  uint32_t* done;        // CTAs of the running launch that have finished
+  uint32_t mask;         // ring capacity - 1
+  int defer;             // leave a ragged last wave (< 60 % full) for the next round instead of paying a whole pass for it
+};
+
 // host-side launchers implemented in the .cu files
 cudaError_t launch_tree_step(const TreeParams& p, const int32_t* game_ids, int n, int max_iters, cudaStream_t s);
 cudaError_t launch_set_roots(const TreeParams& p, const int32_t* game_ids_dev, int n, const int16_t* roots_dev,
@@ -155,9 +171,9 @@ cudaError_t launch_rollout_search(const TreeParams& p, int kind, int num_mcts, c
                                   cudaStream_t s);
 cudaError_t launch_pack_records(const TreeParams& p, int n, uint8_t* out, size_t bytes_per_game, cudaStream_t s);
 
-cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr,
+cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const NNQueue& q,
                          int n_max, float* policy, float* value, int num_sms, cudaStream_t s);
-cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const int32_t* n_ptr, int n_max,
+cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const NNQueue& q, int n_max,
                               float* policy, float* value, int num_sms, cudaStream_t s);
 cudaError_t launch_selfplay_persist(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds,
                                     int num_sms, cudaStream_t s);

@@ -58,17 +58,27 @@ struct SmemLayout {
 // peer's warp 9 forwards "my weights landed" / "my epilogue is done" to the leader.
 template <int B, int RING16, bool X3, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
-tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
+tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int n_max,
              float* __restrict__ policy, float* __restrict__ value) {
   using G = Geo<B>;
   using SL = SmemLayout<B, RING16, X3>;
   extern __shared__ __align__(1024) uint8_t smem[];
 
-  int n = n_ptr ? *n_ptr : n_max;
-  if (n > n_max) n = n_max;
+  int n = n_max;
+  uint32_t qbase = 0u;  // ring position of request 0 of this launch
+  if (q.tail != nullptr) {
+    qbase = *q.head;
+    n = (int)(*q.tail - qbase);
+    if (n > n_max) n = n_max;
+    n = queue_serve_count<G::GPC>(n, q.defer);
+  }
+  const uint32_t qmask = q.tail != nullptr ? q.mask : 0xFFFFFFFFu;
   {
     int g0_, ng_, nt_;
-    if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) return;  // nothing to do for this CTA
+    if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) {  // nothing to do for this CTA
+      queue_finish(q, qbase, n);
+      return;
+    }
   }
 
   uint8_t* s_act = smem + SL::act;
@@ -365,7 +375,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
       {
         uint4 c0 = make_uint4(0, 0, 0, 0);
         if (valid) {
-          const LeafIn* li = &in[g0 + g_local];
+          const LeafIn* li = &in[(qbase + (uint32_t)(g0 + g_local)) & qmask];
           const uint32_t b0 = (li->plane[0][yy] >> xx) & 1u, b1 = (li->plane[1][yy] >> xx) & 1u;
           const uint32_t b2 = (li->plane[2][yy] >> xx) & 1u, b3 = (li->plane[3][yy] >> xx) & 1u;
           const uint32_t b4 = li->colour & 1u;
@@ -528,11 +538,12 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
         if (lane == 0) {
           s_red[warp * 2 + 0] = mx;
           s_red[warp * 2 + 1] = sum;
-          value[g0 + warp] = tanhf(hv + W.vfc2_b);
+          value[(qbase + (uint32_t)(g0 + warp)) & qmask] = tanhf(hv + W.vfc2_b);
         }
       }
       epi_bar_sync();
-      if (p_thread) policy[(size_t)(g0 + pg) * G::A + po] = expf(logit - s_red[pg * 2]) / s_red[pg * 2 + 1];
+      if (p_thread)
+        policy[(size_t)((qbase + (uint32_t)(g0 + pg)) & qmask) * G::A + po] = expf(logit - s_red[pg * 2]) / s_red[pg * 2 + 1];
       // s_feat / s_logits are rewritten only after the next pass's 21 layers: no extra barrier needed
       AO_DBG(if (dbg_on) dbg_heads += clock64() - t_h0;)
     }
@@ -551,6 +562,7 @@ tower_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __res
     if (PAIR) tmem_dealloc_pair<512>(tmem);
     else tmem_dealloc<512>(tmem);
   }
+  queue_finish(q, qbase, n);
 }
 
 // dense float states [n][C][B][B] -> LeafIn row masks
@@ -582,7 +594,7 @@ __global__ void pack_states_kernel(const float* __restrict__ st, int n, int B, i
 }
 
 template <int B, int RING16, bool X3, bool PAIR>
-cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
+cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const NNQueue& q, int n_max, float* policy,
                            float* value, int num_sms, cudaStream_t s) {
   using SL = SmemLayout<B, RING16, X3>;
   static_assert(SL::total <= 232448, "tower kernel exceeds 227 KB of shared memory");
@@ -595,7 +607,7 @@ cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_
   const int grid = n_max < num_sms ? n_max : num_sms;  // see get_pass: up to one game per CTA in a ragged wave
   if (grid <= 0) return cudaSuccess;
   if (!PAIR) {
-    tower_kernel<B, RING16, X3, PAIR><<<grid, kThreads, SL::total, s>>>(w, in, n_ptr, n_max, policy, value);
+    tower_kernel<B, RING16, X3, PAIR><<<grid, kThreads, SL::total, s>>>(w, in, q, n_max, policy, value);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
@@ -610,30 +622,30 @@ cudaError_t launch_tower_t(const TowerWeights& w, const LeafIn* in, const int32_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tower_kernel<B, RING16, X3, PAIR>, w, in, n_ptr, n_max, policy, value);
+  return cudaLaunchKernelEx(&cfg, tower_kernel<B, RING16, X3, PAIR>, w, in, q, n_max, policy, value);
 }
 
 }  // namespace
 
-cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const int32_t* n_ptr, int n_max,
+cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const LeafIn* in, const NNQueue& q, int n_max,
                          float* policy, float* value, int num_sms, cudaStream_t s) {
   if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
   if (precision == AO_NN_FP16X3) {
-    if (B == 9) return launch_tower_t<9, 4, true, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-    if (B == 15) return launch_tower_t<15, 3, true, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    if (B == 9) return launch_tower_t<9, 4, true, true>(w, in, q, n_max, policy, value, num_sms, s);
+    if (B == 15) return launch_tower_t<15, 3, true, true>(w, in, q, n_max, policy, value, num_sms, s);
     return cudaErrorInvalidValue;
   }
   if (precision == AO_NN_FP16_1CTA) {  // single-CTA variant (cta_group::1), kept for comparison
-    if (B == 9) return launch_tower_t<9, 8, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-    if (B == 15) return launch_tower_t<15, 8, false, false>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+    if (B == 9) return launch_tower_t<9, 8, false, false>(w, in, q, n_max, policy, value, num_sms, s);
+    if (B == 15) return launch_tower_t<15, 8, false, false>(w, in, q, n_max, policy, value, num_sms, s);
     return cudaErrorInvalidValue;
   }
   if (precision == AO_NN_FP16)  // default: CTA pairs with staggered tiles (tower_stag.cu)
-    return launch_tower_stag(w, B, in, n_ptr, n_max, policy, value, num_sms, s);
+    return launch_tower_stag(w, B, in, q, n_max, policy, value, num_sms, s);
   if (precision != AO_NN_FP16_LOCKSTEP) return cudaErrorInvalidValue;
   // CTA pairs (cta_group::2), MMA and epilogue in lock-step
-  if (B == 9) return launch_tower_t<9, 8, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
-  if (B == 15) return launch_tower_t<15, 8, false, true>(w, in, n_ptr, n_max, policy, value, num_sms, s);
+  if (B == 9) return launch_tower_t<9, 8, false, true>(w, in, q, n_max, policy, value, num_sms, s);
+  if (B == 15) return launch_tower_t<15, 8, false, true>(w, in, q, n_max, policy, value, num_sms, s);
   return cudaErrorInvalidValue;
 }
 

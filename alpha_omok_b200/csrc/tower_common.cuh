@@ -65,6 +65,29 @@ __device__ __forceinline__ bool pass_of_cta(int b, int k, int n, int& g0, int& n
   ng = min(GPC, n - g0);
   return true;
 }
+// How many of the n queued requests this launch serves: everything, unless `defer` and the last wave would be ragged
+// (fewer than 60 % of GPC * gridDim.x leaves): a ragged wave costs a whole pass (or 0.55 of one as one-game passes), so
+// it is cheaper to let those games wait one round - the chip only ever runs full waves.  Warp-uniform, grid-uniform.
+template <int GPC>
+__device__ __forceinline__ int queue_serve_count(int n, int defer) {
+  const int per_wave = GPC * (int)gridDim.x;
+  if (defer && n > per_wave) {
+    const int r = n % per_wave;
+    if (r != 0 && r * 5 < per_wave * 3) n -= r;
+  }
+  return n;
+}
+// Called once per CTA when it is done (also by CTAs that had nothing to do): the last one publishes the new head.
+__device__ __forceinline__ void queue_finish(const NNQueue& q, uint32_t qbase, int n_served) {
+  if (q.tail == nullptr || threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(q.done, 1u) == gridDim.x - 1u) {
+    *q.head = qbase + (uint32_t)n_served;
+    *q.done = 0u;
+    __threadfence();
+  }
+}
+
 // PAIR: the two CTAs of a cluster issue their MMAs together, so a pass exists for both as soon as either has games
 // (the other one then runs it with ng = 0).
 template <int GPC, int A, bool PAIR>

@@ -86,7 +86,7 @@ __device__ __forceinline__ void head_bar_sync() { asm volatile("bar.sync 2, 128;
 // behind the tensor pipe.
 template <int B, bool PERSIST>
 __global__ void __launch_bounds__(kStagThreads, 1)
-tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* __restrict__ n_ptr, int n_max,
+tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int n_max,
                   float* __restrict__ policy, float* __restrict__ value, TreeParams P, int rounds) {
   using G = Geo<B>;
   using SL = StagSmem<B, PERSIST>;
@@ -96,12 +96,22 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
   constexpr uint32_t kTapBytes = kStageBytes / 2, kStemTapBytes = kStemStageBytes / 2, kBRows = kC / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
 
-  int n = n_ptr ? *n_ptr : n_max;
-  if (n > n_max) n = n_max;
+  int n = n_max;
+  uint32_t qbase = 0u;  // ring position of request 0 of this launch
+  if (!PERSIST && q.tail != nullptr) {
+    qbase = *q.head;
+    n = (int)(*q.tail - qbase);
+    if (n > n_max) n = n_max;
+    n = queue_serve_count<G::GPC>(n, q.defer);
+  }
+  const uint32_t qmask = (!PERSIST && q.tail != nullptr) ? q.mask : 0xFFFFFFFFu;
   if (!PERSIST) rounds = 1;
   {
     int g0_, ng_, nt_;
-    if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) return;
+    if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) {
+      if (!PERSIST) queue_finish(q, qbase, n);
+      return;
+    }
   }
   uint8_t* s_act = smem + SL::act;
   uint8_t* s_w = smem + SL::wring;
@@ -355,7 +365,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
       {
         uint4 c0 = make_uint4(0, 0, 0, 0);
         if (gl_in < G::GPC && gl_in < ng) {
-          const LeafIn* li = &in[g0 + gl_in];
+          const LeafIn* li = &in[(qbase + (uint32_t)(g0 + gl_in)) & qmask];
           const int yy = pos_in / B, xx = pos_in % B;
           // L1-bypassing loads: in persistent mode the request was stored by another warp of this SM moments ago
           const uint32_t b0 = (__ldcg(&li->plane[0][yy]) >> xx) & 1u, b1 = (__ldcg(&li->plane[1][yy]) >> xx) & 1u;
@@ -534,7 +544,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
           s_red[hw * 2 + 1] = sum;
           const float v = tanhf(hv + W.vfc2_b);
           if (PERSIST) s_val[hw] = v;
-          else value[g0 + hw] = v;
+          else value[(qbase + (uint32_t)(g0 + hw)) & qmask] = v;
         }
       }
       if (!PERSIST)
@@ -545,7 +555,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
         if (pg < ng) {
           const float pr = expf(s_logits[o] - s_red[pg * 2]) / s_red[pg * 2 + 1];
           if (PERSIST) s_pol[pg * SL::APad + po] = pr;
-          else policy[(size_t)(g0 + pg) * G::A + po] = pr;
+          else policy[(size_t)((qbase + (uint32_t)(g0 + pg)) & qmask) * G::A + po] = pr;
         }
       }
       head_bar_sync();  // s_logits / s_red are rewritten by the next pass only after this
@@ -577,10 +587,11 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, const int32_t* 
   __syncthreads();
   cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner may still signal / use it
   if (warp == 9) tmem_dealloc_pair<512>(tmem);
+  if (!PERSIST) queue_finish(q, qbase, n);
 }
 
 template <int B, bool PERSIST>
-cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const int32_t* n_ptr, int n_max, float* policy,
+cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const NNQueue& q, int n_max, float* policy,
                                 float* value, int num_sms, const TreeParams& P, int rounds, cudaStream_t s) {
   using SL = StagSmem<B, PERSIST>;
   static_assert(SL::total <= 232448, "staggered tower kernel exceeds 227 KB of shared memory");
@@ -604,18 +615,18 @@ cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tower_stag_kernel<B, PERSIST>, w, in, n_ptr, n_max, policy, value, P, rounds);
+  return cudaLaunchKernelEx(&cfg, tower_stag_kernel<B, PERSIST>, w, in, q, n_max, policy, value, P, rounds);
 }
 
 }  // namespace
 
-cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const int32_t* n_ptr, int n_max,
+cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const NNQueue& q, int n_max,
                               float* policy, float* value, int num_sms, cudaStream_t s) {
   if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
   TreeParams none;
   memset(&none, 0, sizeof none);
-  if (B == 9) return launch_tower_stag_t<9, false>(w, in, n_ptr, n_max, policy, value, num_sms, none, 1, s);
-  if (B == 15) return launch_tower_stag_t<15, false>(w, in, n_ptr, n_max, policy, value, num_sms, none, 1, s);
+  if (B == 9) return launch_tower_stag_t<9, false>(w, in, q, n_max, policy, value, num_sms, none, 1, s);
+  if (B == 15) return launch_tower_stag_t<15, false>(w, in, q, n_max, policy, value, num_sms, none, 1, s);
   return cudaErrorInvalidValue;
 }
 
@@ -627,8 +638,10 @@ cudaError_t launch_selfplay_persist(const TowerWeights& w, int B, const TreePara
   const int per_pass = B == 9 ? Geo<9>::GPC : Geo<15>::GPC;
   const int grid = n_games < num_sms ? n_games : num_sms;
   if ((n_games + per_pass * grid - 1) / (per_pass * grid) + 1 > kMaxPassesPerCta) return cudaErrorInvalidValue;
-  if (B == 9) return launch_tower_stag_t<9, true>(w, p.nn_in, nullptr, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
-  if (B == 15) return launch_tower_stag_t<15, true>(w, p.nn_in, nullptr, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
+  NNQueue none;
+  memset(&none, 0, sizeof none);
+  if (B == 9) return launch_tower_stag_t<9, true>(w, p.nn_in, none, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
+  if (B == 15) return launch_tower_stag_t<15, true>(w, p.nn_in, none, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
   return cudaErrorInvalidValue;
 }
 

@@ -33,7 +33,7 @@ __global__ void reset_games_kernel(TreeParams P, const int32_t* __restrict__ ids
   gm->arena = 0; gm->root_node = CH_UNVISITED; gm->root_n = 0u; gm->root_w = 0.f; gm->slot_count = 0u;
   gm->sims_done = 0; gm->sims_target = P.num_mcts + 1; gm->is_real_root = 1; gm->auto_play = auto_play;
   gm->rng_ctr = 0u; gm->noise_draws = 0u; gm->game_key = keys ? keys[i] : (uint32_t)game;
-  gm->leaf_depth = 0; gm->leaf_n_moves = 0; gm->nn_slot = 0; gm->winner = 0; gm->error = 0; gm->nn_log_count = 0u;
+  gm->leaf_depth = 0; gm->leaf_n_moves = 0; gm->nn_slot = 0; gm->nn_ticket = 0u; gm->nn_static = 0; gm->winner = 0; gm->error = 0; gm->nn_log_count = 0u;
   gm->sims_total = 0ull; gm->nn_evals = 0ull; gm->terminal_sims = 0ull; gm->moves_played = 0ull;
   gm->games_finished = 0ull;
 }
@@ -205,7 +205,7 @@ __global__ void reset_arena_kernel(TreeParams P, int n_slots, uint32_t first_key
   gm->arena = 0; gm->root_node = CH_UNVISITED; gm->root_n = 0u; gm->root_w = 0.f; gm->slot_count = 0u;
   gm->sims_done = 0; gm->sims_target = P.arena_num_mcts[side] + 1; gm->is_real_root = 1; gm->auto_play = 4;
   gm->rng_ctr = 0u; gm->noise_draws = 0u; gm->game_key = first_key + 2u * (uint32_t)m + (uint32_t)side;
-  gm->leaf_depth = 0; gm->leaf_n_moves = 0; gm->nn_slot = 0; gm->winner = 0; gm->error = 0; gm->nn_log_count = 0u;
+  gm->leaf_depth = 0; gm->leaf_n_moves = 0; gm->nn_slot = 0; gm->nn_ticket = 0u; gm->nn_static = 0; gm->winner = 0; gm->error = 0; gm->nn_log_count = 0u;
   gm->sims_total = 0ull; gm->nn_evals = 0ull; gm->terminal_sims = 0ull; gm->moves_played = 0ull;
   gm->games_finished = 0ull;
   gm->arena_match = 0;

@@ -701,7 +701,12 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
 
   for (int it = 0; it < max_iters; ++it) {
     if (g.status == ST_WAIT_NN) {
-      // -------- consume the network output for the pending leaf
+      // -------- consume the network output for the pending leaf - once the tower has served its ticket (a ragged last
+      // wave of requests may have been left for the next round, NNQueue.defer)
+      if (!nn_in_smem && !c.gm->nn_static) {
+        const int qnet = arena ? arena_side(P, c.game) : 0;
+        if ((int32_t)(P.nn_head[qnet] - c.gm->nn_ticket) <= 0) break;  // not answered yet: keep waiting
+      }
       const int slot = c.gm->nn_slot;
       const int depth = c.gm->leaf_depth;
       // the network's answer: from the exchange buffers in HBM, or already in sm->pol (persistent self-play kernel)
@@ -896,9 +901,11 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
       // arena: requests of side s are evaluated with weight set s and live in nn slots [s * M, ...)
       const int net = arena ? arena_side(P, c.game) : 0;
       int slot = c.game;  // static_slots: request slot = game slot (the persistent kernel's fixed game -> CTA pass map)
-      if (!P.static_slots) {
-        if (lane == 0) slot = atomicAdd(P.nn_count + net, 1) + net * P.arena_M;
-        slot = __shfl_sync(kFull, slot, 0);
+      uint32_t ticket = 0u;
+      if (!P.static_slots) {  // next ticket of the weight set's queue; its ring slot
+        if (lane == 0) ticket = atomicAdd(P.nn_count + net, 1u);
+        ticket = __shfl_sync(kFull, ticket, 0);
+        slot = (int)((ticket & P.nn_ring_mask) + (uint32_t)net * (P.nn_ring_mask + 1u));
       }
       // last two actions on the path to the leaf (or of the root position)
       int l1 = g.last1, l2 = g.last2;
@@ -927,6 +934,8 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
         c.gm->leaf_depth = depth;
         c.gm->leaf_n_moves = nm;
         c.gm->nn_slot = slot;
+        c.gm->nn_ticket = ticket;
+        c.gm->nn_static = P.static_slots ? 1 : 0;
         c.gm->nn_evals += 1ull;
       }
       g.status = ST_WAIT_NN;
