@@ -101,6 +101,8 @@ struct ao_engine {
   uint32_t ring_cap;            // request-ring capacity per weight set (power of two >= max_games)
   uint32_t* d_tower_done;       // [2] finished-CTA counters of the running tower launches
   bool defer_tail;              // towers leave a ragged last wave for the next round (AO_NO_DEFER=1 disables)
+  bool free_run;                // persistent kernel cycles through each CTA's games with full passes (AO_NO_FREERUN=1: static map)
+  uint32_t* d_cta_pos;          // [512] cycle position per CTA
   float* d_fwd_states;          // ao_nn_forward staging (lazily allocated)
   int* d_fwd_bad;
   float* d_wsum;                // ao_rollout_search: w of the root's children
@@ -254,6 +256,7 @@ int enter_persist(ao_engine* h, int max_iters, int n = -1) {
                            h->tp.nn_value, h->num_sms, h->stream));
   h->launches += 1;
   h->tp.static_slots = 1;
+  AO_CUDA(cudaMemsetAsync(h->d_cta_pos, 0, 512 * sizeof(uint32_t), h->stream));
   AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
   AO_CUDA(ao::launch_tree_step(h->tp, nullptr, n, max_iters, h->stream));
   h->launches += 1;
@@ -380,6 +383,8 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   EA(tp.nn_count, 2);
   EA(tp.nn_head, 2);
   EA(h->d_tower_done, 2);
+  EA(h->d_cta_pos, 512);
+  h->free_run = getenv("AO_NO_FREERUN") == nullptr;
   EA(tp.n_active, 1);
   if (tp.nn_log_cap > 0) {
     EA(tp.nnlog_policy, (size_t)G * tp.nn_log_cap * A);
@@ -627,7 +632,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
     if ((rc = enter_persist(h, max_iters, n)) != 0) return rc;
     int todo = h->cfg.num_mcts + 1;
     while (active > 0) {
-      AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, todo, h->num_sms, h->stream));
+      AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, todo, h->num_sms, nullptr, h->stream));
       h->launches += 1;
       rounds += todo;
       AO_CUDA(ao::launch_sum_counters(h->tp, n, n, h->d_counters, h->stream));
@@ -894,7 +899,7 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   if (persist_usable(h, rounds)) {
     // ONE launch for all `rounds` rounds: tower and tree step fused in the persistent kernel (tower_stag.cu)
     if ((rc = enter_persist(h, max_iters)) != 0) return rc;
-    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->stream));
+    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream));
     h->launches += 1;
   } else {
     if ((rc = leave_persist(h, false)) != 0) return rc;
@@ -927,7 +932,7 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
     AO_CUDA(cudaEventRecord(h->pev[0], h->stream));
     if ((rc = enter_persist(h, max_iters_p)) != 0) return rc;
     AO_CUDA(cudaEventRecord(h->pev[1], h->stream));
-    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->stream));
+    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream));
     h->launches += 1;
     AO_CUDA(cudaEventRecord(h->pev[2], h->stream));
     AO_CUDA(launch_sum_selfplay(h));

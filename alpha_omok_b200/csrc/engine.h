@@ -176,7 +176,7 @@ cudaError_t launch_tower(const TowerWeights& w, int B, int precision, const Leaf
 cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, const NNQueue& q, int n_max,
                               float* policy, float* value, int num_sms, cudaStream_t s);
 cudaError_t launch_selfplay_persist(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds,
-                                    int num_sms, cudaStream_t s);
+                                    int num_sms, uint32_t* cta_pos, cudaStream_t s);
 cudaError_t tower_configure(int B, int precision);
 cudaError_t launch_pack_states(const float* states_dev, int n, int B, int inplanes, LeafIn* out, int* bad_flag_dev,
                                cudaStream_t s);

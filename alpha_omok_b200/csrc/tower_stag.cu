@@ -87,7 +87,8 @@ __device__ __forceinline__ void head_bar_sync() { asm volatile("bar.sync 2, 128;
 template <int B, bool PERSIST>
 __global__ void __launch_bounds__(kStagThreads, 1)
 tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int n_max,
-                  float* __restrict__ policy, float* __restrict__ value, TreeParams P, int rounds) {
+                  float* __restrict__ policy, float* __restrict__ value, TreeParams P, int rounds, int free_passes,
+                  uint32_t* __restrict__ cta_pos) {
   using G = Geo<B>;
   using SL = StagSmem<B, PERSIST>;
   constexpr bool PAIR = true;
@@ -106,9 +107,34 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
   }
   const uint32_t qmask = (!PERSIST && q.tail != nullptr) ? q.mask : 0xFFFFFFFFu;
   if (!PERSIST) rounds = 1;
+  // PERSIST, free-running (free_passes > 0; enough games per CTA): CTA b owns the games b, b + grid, b + 2 grid, ... and
+  // cycles through them with FULL passes only - pass q holds the games at list positions GPC*q .. GPC*q + GPC-1 (mod
+  // the list length) - for `free_passes` passes per launch, the same number on every CTA.  No ragged tail pass, no round
+  // structure: a CTA with one game fewer simply comes round to its games a little sooner.  cta_pos[b] carries the
+  // cycle position from launch to launch.
+  const bool free_run = PERSIST && free_passes > 0;
+  if (free_run) rounds = 1;
+  const int n_local = free_run ? (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+  const uint32_t q0 = free_run ? cta_pos[blockIdx.x] : 0u;
+  // pass k of this launch: static map (get_pass) or the next full pass of the cycle
+  auto next_pass = [&](int k, int& g0, int& ng, int& ntiles) -> bool {
+    if (free_run) {
+      g0 = 0;
+      ng = G::GPC;
+      ntiles = kTiles;
+      return k < free_passes;
+    }
+    return get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles);
+  };
+  // list position / game slot of game j of pass k (free-running), request slot of game j otherwise
+  auto list_pos = [&](int k, int j) -> int { return (int)(((q0 + (uint32_t)k) * (uint32_t)G::GPC + (uint32_t)j) % (uint32_t)n_local); };
+  auto game_slot = [&](int k, int g0, int j) -> uint32_t {
+    if (free_run) return (uint32_t)((int)blockIdx.x + (int)gridDim.x * list_pos(k, j));
+    return (qbase + (uint32_t)(g0 + j)) & qmask;
+  };
   {
     int g0_, ng_, nt_;
-    if (!get_pass<G::GPC, G::A, PAIR>(0, n, g0_, ng_, nt_)) {
+    if (!next_pass(0, g0_, ng_, nt_)) {
       if (!PERSIST) queue_finish(q, qbase, n);
       return;
     }
@@ -185,7 +211,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
       uint32_t lc = 0;
       int g0, ng, ntiles;
       for (int rd = 0; rd < rounds; ++rd)
-      for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+      for (int k = 0; next_pass(k, g0, ng, ntiles); ++k) {
         size_t off = 0;
         for (int l = 0; l < n_layers; ++l, ++lc) {
           const uint32_t part = AO_XFLAG(W, 8) ? 64u : (l == 0 ? kStemTapBytes : kTapBytes);
@@ -212,7 +238,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
       // ---- peer CTA: forward "my half of slot s has landed" to the leader (the operand-ready arrivals go there directly)
       if (stream == 0 && lane == 0) {
         int g0, ng, ntiles, n_k = 0;
-        while (get_pass<G::GPC, G::A, PAIR>(n_k, n, g0, ng, ntiles)) ++n_k;
+        while (next_pass(n_k, g0, ng, ntiles)) ++n_k;
         const uint32_t n_stage = (uint32_t)(n_k * n_layers) * 9u * (uint32_t)rounds;
         for (uint32_t si = 0; si < n_stage; ++si) {
           const uint32_t s = si % 9u;
@@ -232,7 +258,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
       AO_DBG(long long dbg_act_wait = 0, dbg_full_wait = 0; const long long dbg_t0 = W.dbg ? clock64() : 0;)
       int g0, ng, ntiles;
       for (int rd = 0; rd < rounds; ++rd)
-      for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+      for (int k = 0; next_pass(k, g0, ng, ntiles); ++k) {
         if (stream == 1 && ntiles < kTiles) {  // one-game tail pass: tile 1 holds no board
           lc += (uint32_t)n_layers;
           // tile 0's operand-ready barriers complete n_layers phases in this pass without this warp looking: keep the
@@ -356,16 +382,24 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
 
     int g0, ng, ntiles;
     for (int rd = 0; rd < rounds; ++rd)
-    for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
-      if (PERSIST && rd > 0) {
+    for (int k = 0; next_pass(k, g0, ng, ntiles); ++k) {
+      if (PERSIST && !free_run && rd > 0) {
         // the requests of this pass were written by this CTA's head warps one round ago (long done; just make sure)
         while (s_leaf_done[k] < (uint32_t)(rd * ng)) __nanosleep(200);
+        __threadfence_block();
+      }
+      if (free_run && gl_in < G::GPC) {
+        // this row's game was last evaluated n_local list positions ago: its next request must have been written since
+        const uint32_t t = (uint32_t)k * (uint32_t)G::GPC + (uint32_t)gl_in;  // list position since the launch began
+        const uint32_t need = t / (uint32_t)n_local;
+        const int li = list_pos(k, gl_in);
+        while (s_leaf_done[li] < need) __nanosleep(200);
         __threadfence_block();
       }
       {
         uint4 c0 = make_uint4(0, 0, 0, 0);
         if (gl_in < G::GPC && gl_in < ng) {
-          const LeafIn* li = &in[(qbase + (uint32_t)(g0 + gl_in)) & qmask];
+          const LeafIn* li = &in[game_slot(k, g0, gl_in)];
           const int yy = pos_in / B, xx = pos_in % B;
           // L1-bypassing loads: in persistent mode the request was stored by another warp of this SM moments ago
           const uint32_t b0 = (__ldcg(&li->plane[0][yy]) >> xx) & 1u, b1 = (__ldcg(&li->plane[1][yy]) >> xx) & 1u;
@@ -497,7 +531,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
     uint32_t pass_ph = 0;
     int g0, ng, ntiles;
     for (int rd = 0; rd < rounds; ++rd)
-    for (int k = 0; get_pass<G::GPC, G::A, PAIR>(k, n, g0, ng, ntiles); ++k) {
+    for (int k = 0; next_pass(k, g0, ng, ntiles); ++k) {
       mbar_wait_sleep(bar_feat_full, pass_ph, 2000);  // a whole tower pass (~100 us) between two head jobs
       pass_ph ^= 1u;
       for (int i = ht; i < G::GPC * 3 * G::A; i += kHeadThreads)
@@ -544,7 +578,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
           s_red[hw * 2 + 1] = sum;
           const float v = tanhf(hv + W.vfc2_b);
           if (PERSIST) s_val[hw] = v;
-          else value[(qbase + (uint32_t)(g0 + hw)) & qmask] = v;
+          else value[game_slot(k, g0, hw)] = v;
         }
       }
       if (!PERSIST)
@@ -555,7 +589,7 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
         if (pg < ng) {
           const float pr = expf(s_logits[o] - s_red[pg * 2]) / s_red[pg * 2 + 1];
           if (PERSIST) s_pol[pg * SL::APad + po] = pr;
-          else policy[(size_t)((qbase + (uint32_t)(g0 + pg)) & qmask) * G::A + po] = pr;
+          else policy[(size_t)game_slot(k, g0, pg) * G::A + po] = pr;
         }
       }
       head_bar_sync();  // s_logits / s_red are rewritten by the next pass only after this
@@ -571,10 +605,10 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
           ws.table = reinterpret_cast<int16_t*>(ws.order + 256);
           ws.rows = reinterpret_cast<uint16_t(*)[32]>(ws.table + 128);
           ws.pol = s_pol + hw * SL::APad;
-          (void)tree_step_game<(G::A <= 96 ? 3 : 8)>(P, g0 + hw, &ws, lane, 64, true, s_val[hw]);
+          (void)tree_step_game<(G::A <= 96 ? 3 : 8)>(P, (int)game_slot(k, g0, hw), &ws, lane, 64, true, s_val[hw]);
           __threadfence_block();
           __syncwarp();
-          if (lane == 0) atomicAdd(const_cast<uint32_t*>(s_leaf_done) + k, 1u);
+          if (lane == 0) atomicAdd(const_cast<uint32_t*>(s_leaf_done) + (free_run ? list_pos(k, hw) : k), 1u);
         }
         head_bar_sync();
         for (int i = ht; i < G::GPC * 3 * G::A; i += kHeadThreads) s_feat[i] = 0.f;  // ready for the next pass's sums
@@ -588,11 +622,13 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
   cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner may still signal / use it
   if (warp == 9) tmem_dealloc_pair<512>(tmem);
   if (!PERSIST) queue_finish(q, qbase, n);
+  if (free_run && tid == 0) cta_pos[blockIdx.x] = q0 + (uint32_t)free_passes;
 }
 
 template <int B, bool PERSIST>
 cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const NNQueue& q, int n_max, float* policy,
-                                float* value, int num_sms, const TreeParams& P, int rounds, cudaStream_t s) {
+                                float* value, int num_sms, const TreeParams& P, int rounds, int free_passes,
+                                uint32_t* cta_pos, cudaStream_t s) {
   using SL = StagSmem<B, PERSIST>;
   static_assert(SL::total <= 232448, "staggered tower kernel exceeds 227 KB of shared memory");
   static bool configured = false;
@@ -615,7 +651,8 @@ cudaError_t launch_tower_stag_t(const TowerWeights& w, const LeafIn* in, const N
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tower_stag_kernel<B, PERSIST>, w, in, q, n_max, policy, value, P, rounds);
+  return cudaLaunchKernelEx(&cfg, tower_stag_kernel<B, PERSIST>, w, in, q, n_max, policy, value, P, rounds, free_passes,
+                            cta_pos);
 }
 
 }  // namespace
@@ -625,23 +662,34 @@ cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, co
   if (w.n_layers > kMaxLayers) return cudaErrorInvalidValue;
   TreeParams none;
   memset(&none, 0, sizeof none);
-  if (B == 9) return launch_tower_stag_t<9, false>(w, in, q, n_max, policy, value, num_sms, none, 1, s);
-  if (B == 15) return launch_tower_stag_t<15, false>(w, in, q, n_max, policy, value, num_sms, none, 1, s);
+  if (B == 9) return launch_tower_stag_t<9, false>(w, in, q, n_max, policy, value, num_sms, none, 1, 0, nullptr, s);
+  if (B == 15) return launch_tower_stag_t<15, false>(w, in, q, n_max, policy, value, num_sms, none, 1, 0, nullptr, s);
   return cudaErrorInvalidValue;
 }
 
 // The persistent self-play kernel: `rounds` lock-step rounds over the game slots [0, n_games) in one launch.  Needs
 // p.static_slots = 1 and every running game in ST_WAIT_NN with its request in p.nn_in[game] (engine.cu enter_persist).
+// cta_pos: device uint32[>= grid] cycle positions (zeroed when the persistent state is entered).  With at least
+// 2 * GPC games per CTA the kernel free-runs (full passes only, rounds * ceil(n / grid) / GPC passes per CTA: every game
+// gets at least `rounds` simulations, games of CTAs that own one game fewer a few more); smaller batches keep the
+// static game -> pass map.
 cudaError_t launch_selfplay_persist(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds,
-                                    int num_sms, cudaStream_t s) {
+                                    int num_sms, uint32_t* cta_pos, cudaStream_t s) {
   if (w.n_layers > kMaxLayers || !p.static_slots) return cudaErrorInvalidValue;
   const int per_pass = B == 9 ? Geo<9>::GPC : Geo<15>::GPC;
-  const int grid = n_games < num_sms ? n_games : num_sms;
+  int grid = n_games < num_sms ? n_games : num_sms;
+  grid = (grid + 1) & ~1;
   if ((n_games + per_pass * grid - 1) / (per_pass * grid) + 1 > kMaxPassesPerCta) return cudaErrorInvalidValue;
+  const int min_local = n_games / grid, max_local = (n_games + grid - 1) / grid;
+  int free_passes = 0;
+  if (cta_pos != nullptr && min_local >= 2 * per_pass && max_local <= kMaxPassesPerCta)
+    free_passes = (int)(((long long)rounds * max_local + per_pass - 1) / per_pass);
   NNQueue none;
   memset(&none, 0, sizeof none);
-  if (B == 9) return launch_tower_stag_t<9, true>(w, p.nn_in, none, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
-  if (B == 15) return launch_tower_stag_t<15, true>(w, p.nn_in, none, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, s);
+  if (B == 9)
+    return launch_tower_stag_t<9, true>(w, p.nn_in, none, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, free_passes, cta_pos, s);
+  if (B == 15)
+    return launch_tower_stag_t<15, true>(w, p.nn_in, none, n_games, p.nn_policy, p.nn_value, num_sms, p, rounds, free_passes, cta_pos, s);
   return cudaErrorInvalidValue;
 }
 
