@@ -597,3 +597,31 @@ def test_continuous_selfplay_records_equal_batch_runs(cabi, eval_mode):
     got2 = replay.device_stream_records(eng)
     assert got2.shape[0] == 4 and torch.equal(got2, want[20:24])
     eng.close()
+
+
+@pytest.mark.parametrize("B,G,sims", [(9, 900, 8), (15, 300, 6), (9, 1400, 6)])
+def test_persistent_kernel_and_deferred_tails_equal_the_plain_round_loop(cabi, monkeypatch, B, G, sims):
+    """scheduling must not change a single game: (a) the persistent self-play kernel in its free-running mode (every CTA
+    cycling through its own games with full passes, tree steps fused into the head warps), (b) the two-kernel rounds with
+    ragged request tails deferred to the next round, and (c) the plain two-kernel rounds that serve every request every
+    round play byte-identical episodes (moves, per-ply visit counts, winners) for the same decision-stream keys"""
+    sd = pvnet_ref.make_state_dict(2, 2, 5, 128, B)
+    runs = []
+    for env in ({}, {"AO_NO_PERSIST": "1"}, {"AO_NO_PERSIST": "1", "AO_NO_DEFER": "1"}):
+        for k in ("AO_NO_PERSIST", "AO_NO_DEFER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=13, n_blocks=2)   # switches are read at creation
+        eng.load_state_dict(sd)
+        eng.selfplay_begin(G, first_key=50)
+        st = eng.selfplay_rounds(64)
+        while st["running"]:
+            st = eng.selfplay_rounds(64)
+        assert st["errors"] == 0 and st["games_finished"] == G
+        runs.append(eng.selfplay_fetch(G))
+        eng.close()
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert np.array_equal(a, b)
+    assert set(np.unique(runs[0][2])) <= {1, 2, 3}

@@ -11,10 +11,11 @@ nb = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 9
 eng = _cabi.Engine(board_size=B, num_mcts=6, max_games=n, n_blocks=nb, seed=3)
 eng.load_state_dict(seeded_state_dict(0, nb, 5, 128, B))
-eng.selfplay_begin(n, recycle=True)
+eng.selfplay_begin(n, recycle=False)
 st = eng.selfplay_rounds(rounds)
-print("rounds ok", st, flush=True)
-st = eng.selfplay_rounds(rounds)
+while st["running"]:          # every game to its end: complete episodes do not depend on the scheduling
+    st = eng.selfplay_rounds(rounds)
 moves, n_moves, winners, visits = eng.selfplay_fetch(n)
-print("sims", st["sims"], "moves", st["moves"], "checksum", int(visits.astype(np.int64).sum()), int(moves[:, :3].astype(np.int64).sum()), flush=True)
+print("sims", st["sims"], "moves", st["moves"], "checksum", int(visits.astype(np.int64).sum()), int(moves.astype(np.int64).sum()),
+      int(winners.astype(np.int64).sum()), flush=True)
 eng.close()
