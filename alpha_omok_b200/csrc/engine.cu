@@ -101,6 +101,7 @@ struct ao_engine {
   uint32_t ring_cap;            // request-ring capacity per weight set (power of two >= max_games)
   uint32_t* d_tower_done;       // [2] finished-CTA counters of the running tower launches
   bool defer_tail;              // towers leave a ragged last wave for the next round (AO_NO_DEFER=1 disables)
+  unsigned long long round_no;  // two-kernel rounds issued so far (move rounds: round_no % kMoveEvery == 0)
   bool free_run;                // persistent kernel cycles through each CTA's games with full passes (AO_NO_FREERUN=1: static map)
   uint32_t* d_cta_pos;          // [512] cycle position per CTA
   float* d_fwd_states;          // ao_nn_forward staging (lazily allocated)
@@ -126,6 +127,10 @@ int ealloc(ao_engine* h, T** p, size_t count) {
   return 0;
 }
 
+constexpr int kGraphRounds = 16;
+constexpr int kMoveEvery = kGraphRounds;  // a graph replay = one move round followed by 15 plain rounds
+constexpr int kPollEvery = 4;             // ao_search: host polls of the running-games counter
+
 ao::NNQueue queue_of(const ao_engine* h, int set, bool defer) {
   ao::NNQueue q;
   q.tail = h->tp.nn_count + set;
@@ -150,7 +155,11 @@ ao::NNQueue no_queue() {
 int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int timed_slot = -1) {
   AO_CUDA(cudaMemsetAsync(h->tp.n_active, 0, sizeof(int32_t), h->stream));
   if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 0], h->stream));
-  AO_CUDA(ao::launch_tree_step(h->tp, ids_dev, n, max_iters, h->stream));
+  ao::TreeParams tp = h->tp;
+  // every kMoveEvery-th round is a move round (the synthetic evaluator plays whole games per launch: always)
+  tp.allow_moves = (h->cfg.eval_mode == AO_EVAL_SYNTH || h->round_no % kMoveEvery == 0) ? 1 : 0;
+  h->round_no += 1;
+  AO_CUDA(ao::launch_tree_step(tp, ids_dev, n, max_iters, h->stream));
   if (timed_slot >= 0) AO_CUDA(cudaEventRecord(h->ev[3 * timed_slot + 1], h->stream));
   h->launches += 1;
   if (h->cfg.eval_mode == AO_EVAL_PVNET) {
@@ -171,8 +180,6 @@ int run_round(ao_engine* h, const int32_t* ids_dev, int n, int max_iters, int ti
   return 0;
 }
 
-constexpr int kGraphRounds = 16;
-constexpr int kPollEvery = 4;  // ao_search: host polls of the running-games counter
 
 // `rounds` lock-step rounds over the first n game slots; whole multiples of kGraphRounds are replayed from a CUDA graph
 // (captured from run_round itself, so both paths launch exactly the same work), the rest is issued directly.
@@ -195,11 +202,14 @@ int run_rounds(ao_engine* h, int n, int max_iters, int rounds) {
       cudaGraph_t graph = nullptr;
       h->graph_launches_per_round = h->launches - launches_before_direct;
       const unsigned long long launches0 = h->launches;
+      const unsigned long long round_no0 = h->round_no;
+      h->round_no = 0;  // the captured sequence starts with a move round
       cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
       if (e == cudaSuccess) {
         for (int r = 0; r < kGraphRounds && rc == 0; ++r) rc = run_round(h, nullptr, n, max_iters);
         e = cudaStreamEndCapture(h->stream, &graph);
       }
+      h->round_no = round_no0;
       h->launches = launches0;  // nothing ran during the capture
       if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&h->round_graph, graph, 0);
       if (graph) cudaGraphDestroy(graph);
@@ -217,9 +227,12 @@ int run_rounds(ao_engine* h, int n, int max_iters, int rounds) {
         h->graph_max_iters = max_iters;
       }
     }
+    for (; h->round_graph && done < rounds && h->round_no % kMoveEvery != 0; ++done)  // line up with the move rounds
+      if ((rc = run_round(h, nullptr, n, max_iters)) != 0) return rc;
     while (h->round_graph && rounds - done >= kGraphRounds) {
       AO_CUDA(cudaGraphLaunch(h->round_graph, h->stream));
       h->launches += h->graph_launches_per_round * kGraphRounds;
+      h->round_no += kGraphRounds;
       done += kGraphRounds;
     }
   }
@@ -385,6 +398,8 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   EA(h->d_tower_done, 2);
   EA(h->d_cta_pos, 512);
   h->free_run = getenv("AO_NO_FREERUN") == nullptr;
+  h->round_no = 0;
+  tp.allow_moves = 1;
   EA(tp.n_active, 1);
   if (tp.nn_log_cap > 0) {
     EA(tp.nnlog_policy, (size_t)G * tp.nn_log_cap * A);
@@ -632,7 +647,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
     if ((rc = enter_persist(h, max_iters, n)) != 0) return rc;
     int todo = h->cfg.num_mcts + 1;
     while (active > 0) {
-      AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, todo, h->num_sms, nullptr, h->stream));
+      AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, todo, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream));
       h->launches += 1;
       rounds += todo;
       AO_CUDA(ao::launch_sum_counters(h->tp, n, n, h->d_counters, h->stream));

@@ -100,6 +100,10 @@ struct TreeParams {
   size_t stream_rec_bytes;
   uint32_t* stream_next_key;   // device counter
   uint32_t stream_first_key, stream_key_end;
+  // two-kernel rounds: searches that are complete play their move (arg-max / sampling, win check, subtree compaction -
+  // a few hundred microseconds of one warp) only in rounds with allow_moves set, i.e. every kMoveEvery-th round: once
+  // games have drifted apart there would otherwise be a mover - and its latency - in EVERY round's tree step
+  int allow_moves;
   // request slot = game slot instead of the next free slot of the round (the persistent self-play kernel evaluates game
   // g in a fixed CTA pass, see tower_stag.cu); 0 = dense packing through nn_count
   int static_slots;

@@ -754,6 +754,7 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
         if (g.sims_done < g.sims_target) break;  // to be continued next round
       }
       if (kind != SIDE_ZERO || g.sims_done >= g.sims_target) {
+        if (!P.allow_moves) break;  // moves are played in the move rounds (TreeParams.allow_moves)
         if (!arena_move(c, g)) break;
         continue;
       }
@@ -763,6 +764,7 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
         g.status = ST_SEARCH_DONE;
         break;
       }
+      if (!P.allow_moves) break;  // moves are played in the move rounds (TreeParams.allow_moves)
       play_move<MAXJ>(c, g);
       if (g.status != ST_SEARCH) break;
       continue;
