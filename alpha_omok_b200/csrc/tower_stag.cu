@@ -319,10 +319,16 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
             if (elect_one()) umma_commit_pair(&bar_acc[tile]);
             __syncwarp();
           };
+          // Every accumulator row sees the SAME order of its 72 MMAs whatever tile or kind of pass it sits in - taps
+          // 0-4 x k-steps {0,1,4,5}, taps 0-4 x {2,3,6,7}, taps 5-8 x {0,1,4,5}, taps 5-8 x {2,3,6,7} - so a leaf's floats do
+          // not depend on where the scheduler put it (tensor-core accumulation is order-sensitive in the last bits).
           if (ntiles < kTiles) {          // one-game tail pass: stream 0 alone, arriving for both streams
             wait_act(0);
             wait_act(1);
-            issue(0, 0, 9, 2, true, 2);
+            issue(0, 0, 5, 0, true, 0);
+            issue(0, 0, 5, 1, false, 2);
+            issue(0, 5, 9, 0, true, 0);
+            issue(0, 5, 9, 1, false, 2);
             commit_acc(0);
             commit_acc(0);
           } else if (stream == 0) {       // T0: centre/negative taps need T0's epilogue only, positive taps also T1's
@@ -341,9 +347,11 @@ tower_stag_kernel(TowerWeights W, const LeafIn* __restrict__ in, NNQueue q, int 
             wait_act(1);
             wait_act(2);
             wait_act(3);
-            issue(1, 0, 5, 2, true, 1);
+            issue(1, 0, 5, 0, true, 0);
+            issue(1, 0, 5, 1, false, 1);
             commit_acc(0);                // T1 no longer reads T0's last rows: T0's epilogue may overwrite them
-            issue(1, 5, 9, 2, true, 1);
+            issue(1, 5, 9, 0, true, 0);
+            issue(1, 5, 9, 1, false, 1);
             commit_acc(1);                // T1 accumulated
           }
         }
