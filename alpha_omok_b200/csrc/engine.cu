@@ -67,7 +67,7 @@ struct ao_engine {
     ao::TowerWeights tw;
     bool loaded;
     int precision;  // AO_NN_*
-    __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo;
+    __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo, *d_conv_quad;
     float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
   } ws[2];
   std::vector<void*> allocs;
@@ -111,6 +111,7 @@ struct ao_engine {
   // persistent self-play kernel (tower_stag.cu, PERSIST): allowed unless AO_NO_PERSIST is set; `persist_pending` =
   // the running games wait in ST_WAIT_NN with their requests in nn_in[game] (static slots) and no answer computed yet
   bool persist_allowed, persist_pending;
+  bool solo_allowed;            // a few games: cluster-of-four kernel (AO_NO_SOLO=1: always the CTA-pair kernel)
   long long last_running;       // running games after the last self-play call (-1: unknown = all)
   cudaEvent_t pev[3];
 };
@@ -290,6 +291,14 @@ int leave_persist(ao_engine* h, bool drop) {
   return 0;
 }
 
+// all rounds of a call in one launch: a few games -> one cluster of four CTAs per game (tower_solo.cu, latency-bound
+// end), otherwise the CTA-pair kernel (tower_stag.cu, PERSIST)
+cudaError_t launch_persist_any(ao_engine* h, int n, int rounds) {
+  if (h->solo_allowed && n <= ao::solo_max_games(h->num_sms))
+    return ao::launch_selfplay_solo(h->ws[0].tw, h->B, h->tp, n, rounds, h->stream);
+  return ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, rounds, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream);
+}
+
 int poll_active(ao_engine* h, int* active) {
   AO_CUDA(cudaMemcpyAsync(h->h_pinned, h->tp.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   AO_CUDA(cudaStreamSynchronize(h->stream));
@@ -347,6 +356,7 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->d_fwd_states = nullptr; h->d_fwd_bad = nullptr;
   h->d_wsum = nullptr; h->log_table_n = 0;
   h->persist_allowed = getenv("AO_NO_PERSIST") == nullptr;
+  h->solo_allowed = getenv("AO_NO_SOLO") == nullptr;
   h->persist_pending = false;
   h->last_running = -1;
   h->pev[0] = h->pev[1] = h->pev[2] = nullptr;
@@ -480,7 +490,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
   const int n_layers = 1 + 2 * nb;
   const size_t stem_halves = (size_t)9 * 16 * C, res_halves = (size_t)9 * C * C;
   const size_t total_halves = stem_halves + (size_t)(n_layers - 1) * res_halves;
-  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves), prl(total_halves);
+  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves), prl(total_halves), qd(total_halves);
   std::vector<float> bias((size_t)n_layers * C);
   size_t off = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -512,6 +522,8 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
           const size_t idx_pair = off + (((size_t)t * 2 + co / 64) * (kpad / 8) + ci / 8) * 64 * 8 + (size_t)(co % 64) * 8 + (ci % 8);
           pr[idx_pair] = vh;
           prl[idx_pair] = lo[idx];
+          // cluster-of-four layout (tower_solo.cu): per layer [rank = co / 32][tap][k-chunk][co % 32][8]
+          qd[off + (((size_t)(co / 32) * 9 + t) * (kpad / 8) + ci / 8) * 32 * 8 + (size_t)(co % 32) * 8 + (ci % 8)] = vh;
         }
     }
     off += l == 0 ? stem_halves : res_halves;
@@ -551,6 +563,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
     EA(W->d_conv_lo, total_halves);
     EA(W->d_conv_pair, total_halves);
     EA(W->d_conv_pair_lo, total_halves);
+    EA(W->d_conv_quad, total_halves);
     EA(W->d_bias, bias.size());
     EA(W->d_head_w, head_w.size());
     EA(W->d_head_b, 4);
@@ -566,6 +579,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
   AO_CUDA(cudaMemcpy(W->d_conv_lo, lo.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_conv_pair, pr.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_conv_pair_lo, prl.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_conv_quad, qd.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
@@ -578,7 +592,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
 #ifdef AO_PROBE
   tw.xflags = getenv("AO_TOWER_XFLAGS") ? atoi(getenv("AO_TOWER_XFLAGS")) : 0;
 #endif
-  tw.conv_hi = W->d_conv_hi; tw.conv_lo = W->d_conv_lo; tw.conv_pair = W->d_conv_pair; tw.conv_pair_lo = W->d_conv_pair_lo; tw.bias = W->d_bias; tw.head_w = W->d_head_w; tw.head_b = W->d_head_b;
+  tw.conv_hi = W->d_conv_hi; tw.conv_lo = W->d_conv_lo; tw.conv_pair = W->d_conv_pair; tw.conv_pair_lo = W->d_conv_pair_lo; tw.conv_quad = W->d_conv_quad; tw.bias = W->d_bias; tw.head_w = W->d_head_w; tw.head_b = W->d_head_b;
   tw.pfc_wT = W->d_pfc_wT; tw.pfc_b = W->d_pfc_b; tw.vfc1_wT = W->d_vfc1_wT; tw.vfc1_b = W->d_vfc1_b; tw.vfc2_w = W->d_vfc2_w;
   tw.vfc2_b = v2b[0];
   tw.n_layers = n_layers;
@@ -647,7 +661,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
     if ((rc = enter_persist(h, max_iters, n)) != 0) return rc;
     int todo = h->cfg.num_mcts + 1;
     while (active > 0) {
-      AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, todo, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream));
+      AO_CUDA(launch_persist_any(h, n, todo));
       h->launches += 1;
       rounds += todo;
       AO_CUDA(ao::launch_sum_counters(h->tp, n, n, h->d_counters, h->stream));
@@ -914,7 +928,7 @@ extern "C" int ao_selfplay_rounds(ao_engine* h, int rounds, uint64_t* out5) {
   if (persist_usable(h, rounds)) {
     // ONE launch for all `rounds` rounds: tower and tree step fused in the persistent kernel (tower_stag.cu)
     if ((rc = enter_persist(h, max_iters)) != 0) return rc;
-    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream));
+    AO_CUDA(launch_persist_any(h, h->selfplay_games, rounds));
     h->launches += 1;
   } else {
     if ((rc = leave_persist(h, false)) != 0) return rc;
@@ -947,7 +961,7 @@ extern "C" int ao_selfplay_rounds_timed(ao_engine* h, int rounds, uint64_t* out5
     AO_CUDA(cudaEventRecord(h->pev[0], h->stream));
     if ((rc = enter_persist(h, max_iters_p)) != 0) return rc;
     AO_CUDA(cudaEventRecord(h->pev[1], h->stream));
-    AO_CUDA(ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, h->selfplay_games, rounds, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream));
+    AO_CUDA(launch_persist_any(h, h->selfplay_games, rounds));
     h->launches += 1;
     AO_CUDA(cudaEventRecord(h->pev[2], h->stream));
     AO_CUDA(launch_sum_selfplay(h));
