@@ -54,11 +54,21 @@ struct SoloGeo {
   static constexpr int ActBytes = 16 * Rows * 16;
   static constexpr int TileCols = kSoloN * (1 + kSoloIssuers);      // S (fp32 block input / issuer 0 on even layers), A0..A3
   static constexpr int TmemCols = NT * TileCols <= 256 ? 256 : 512;
-  static constexpr int RingGroups = B <= 9 ? 6 : 4;                 // 24 KB each
+  static constexpr int RingGroups = B <= 9 ? 5 : 4;                 // 24 KB each
   static constexpr int APad = (A + 7) / 8 * 8;
-  static constexpr int KS = 256 / A >= 1 ? 256 / A : 1;             // K splits of the policy FC over the 256 head threads
+  // heads: every CTA computes a quarter of the policy FC outputs and of the value FC1 hidden units
+  static constexpr bool FcSmem = B <= 9;                            // its slices of the FC weights live in shared memory
+  static constexpr int OQ = (A + kSoloNC - 1) / kSoloNC;            // policy outputs per CTA
+  static constexpr int KSP = 256 / OQ;                              // K splits of the policy FC over the 256 head threads
+  static constexpr int KLP = (2 * A + KSP - 1) / KSP;
+  static constexpr int VS = 256 / kSoloN;                           // K splits of the value FC1 (32 hidden units per CTA)
+  static constexpr int KLV = (A + VS - 1) / VS;
+  static constexpr uint32_t ActTx = (uint32_t)A * 2u * 2u * 16u;    // bytes one CTA's epilogue delivers per layer and destination
+  static constexpr uint32_t FeatTx = (uint32_t)A * kSoloParts * 3u * 4u;
+  static constexpr uint32_t FcTx = (uint32_t)(A + kC) * 4u;
   static_assert(NT * TileCols <= 512, "TMEM");
   static_assert(NT <= 2, "board too large");
+  static_assert(KSP >= 1 && KSP * OQ <= 256, "policy FC thread map");
 };
 
 template <int B>
@@ -68,20 +78,22 @@ struct SoloSmem {
   static constexpr int wring = G::ActBytes;
   static constexpr int bias = wring + G::RingGroups * kSoloGroupBytes;      // [kMaxLayers][32] f32 (this CTA's channels)
   static constexpr int headw = bias + kMaxLayers * kSoloN * 4;              // [3][32] f32
-  static constexpr int featp = headw + 3 * kSoloN * 4;                      // leader: [kSoloParts][3][A] f32
+  static constexpr int fcb = headw + 3 * kSoloN * 4;                        // pfc_b slice [OQ] | vfc1_b [32] | vfc2_w [32] | head_b [4]
+  static constexpr int pfcw = fcb + (G::OQ + 2 * kSoloN + 4) * 4;           // FcSmem: [2A][OQ] f32
+  static constexpr int vfcw = pfcw + (G::FcSmem ? 2 * G::A * G::OQ * 4 : 0);   // FcSmem: [A][32] f32
+  static constexpr int featp = vfcw + (G::FcSmem ? G::A * kSoloN * 4 : 0);  // [kSoloParts][3][A] f32 partial 1x1-conv sums
   static constexpr int feat = featp + kSoloParts * 3 * G::A * 4;            // [3][A]
-  static constexpr int fcpart = feat + 3 * G::A * 4;                        // [KS][A]
-  static constexpr int hpart = fcpart + G::KS * G::A * 4;                   // [2][128]
-  static constexpr int logits = hpart + 2 * kC * 4;                         // [A]
-  static constexpr int hidden = logits + G::A * 4;                          // [128]
-  static constexpr int pol = (hidden + kC * 4 + 15) / 16 * 16;              // [APad] f32
-  static constexpr int val = pol + G::APad * 4;                             // [4] f32
-  static constexpr int tree = (val + 16 + 15) / 16 * 16;                    // dbuf f64[APad] | dbuf2 f64[APad] | order | table | rows
+  static constexpr int fcpart = feat + 3 * G::A * 4;                        // [KSP][OQ]
+  static constexpr int hpart = fcpart + G::KSP * G::OQ * 4;                 // [VS][32]
+  static constexpr int logits = hpart + G::VS * kSoloN * 4;                 // leader: [A]
+  static constexpr int hidden = logits + G::A * 4;                          // leader: [128]
+  static constexpr int pol = (hidden + kC * 4 + 15) / 16 * 16;              // leader: [APad] f32
+  static constexpr int tree = (pol + G::APad * 4 + 15) / 16 * 16;           // dbuf f64[APad] | dbuf2 f64[APad] | order | table | rows
   static constexpr int kTreeBytes = 16 * G::APad + 256 + 256 + 128;
   static constexpr int masks = (tree + kTreeBytes + 15) / 16 * 16;          // [NT][9][4] u32
   static constexpr int bars = masks + G::NT * 9 * 4 * 4;
-  static constexpr int kBars = 2 * G::RingGroups + kSoloIssuers + 4;
-  static constexpr int total = bars + kBars * 8 + 16;
+  static constexpr int kBars = 2 * G::RingGroups + kSoloIssuers + 6;
+  static constexpr int total = bars + kBars * 8 + 32;  // + TMEM base address, probe scratch
   static_assert(G::ActBytes % 1024 == 0, "weight ring alignment");
   static_assert(tree % 8 == 0, "tree scratch holds doubles");
 };
@@ -109,16 +121,20 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t caddr, const uint4& v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+// Asynchronous store into the shared memory of a CTA of the cluster (own CTA included) that completes `bytes` on an
+// mbarrier of the SAME destination CTA when the data has landed: the writer needs no fence and no separate arrive (a
+// release fence at cluster scope costs a MEMBAR.ALL.GPU that waits for every outstanding remote store), the consumer
+// waits for the barrier's transaction count.
+__device__ __forceinline__ void st_async_v4(uint32_t caddr, const uint4& v, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(caddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cbar)
                : "memory");
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t caddr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(caddr), "f"(v) : "memory");
+__device__ __forceinline__ void st_async_f32(uint32_t caddr, float v, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(caddr),
+               "r"(__float_as_uint(v)), "r"(cbar)
+               : "memory");
 }
-// Publishing data to the other CTAs of the cluster: ONE release fence at cluster scope per warp, then relaxed arrives on
-// the barriers of all destination CTAs (an arrive.release per destination costs a MEMBAR.ALL.GPU each).
-__device__ __forceinline__ void fence_release_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // arrive on the mbarrier at this offset in every CTA of `mask` once all MMAs issued so far by this thread are complete
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
   asm volatile(
@@ -143,6 +159,9 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
   uint8_t* s_w = smem + SL::wring;
   float* s_bias = reinterpret_cast<float*>(smem + SL::bias);
   float* s_headw = reinterpret_cast<float*>(smem + SL::headw);
+  float* s_fcb = reinterpret_cast<float*>(smem + SL::fcb);
+  float* s_pfcw = reinterpret_cast<float*>(smem + SL::pfcw);
+  float* s_vfcw = reinterpret_cast<float*>(smem + SL::vfcw);
   float* s_featp = reinterpret_cast<float*>(smem + SL::featp);
   float* s_feat = reinterpret_cast<float*>(smem + SL::feat);
   float* s_fcpart = reinterpret_cast<float*>(smem + SL::fcpart);
@@ -150,15 +169,16 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
   float* s_logits = reinterpret_cast<float*>(smem + SL::logits);
   float* s_hidden = reinterpret_cast<float*>(smem + SL::hidden);
   float* s_pol = reinterpret_cast<float*>(smem + SL::pol);
-  float* s_val = reinterpret_cast<float*>(smem + SL::val);
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + SL::masks);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SL::bars);  // [RG] producer -> issuers: the group's taps landed
   uint64_t* bar_empty = bar_full + RG;                                // [RG] issuers -> producer
-  uint64_t* bar_act = bar_empty + RG;              // [4] input channels [32 i, 32 i + 32) of the layer are in MY buffer
-  uint64_t* bar_acc = bar_act + kSoloIssuers;      // the layer is accumulated in ALL CTAs (16 multicast commits)
+  uint64_t* bar_act = bar_empty + RG;              // [4] tx: input channels [32 i, 32 i + 32) of the layer have landed in MY buffer
+  uint64_t* bar_in = bar_act + kSoloIssuers;       // my epilogue warps have written the request's input planes
+  uint64_t* bar_acc = bar_in + 1;                  // the layer is accumulated in ALL CTAs (16 multicast commits)
   uint64_t* bar_tfree = bar_acc + 1;               // my epilogue warps have read the accumulators of the previous layer
-  uint64_t* bar_feat = bar_tfree + 1;              // leader: the head partial sums of all CTAs have arrived
-  uint64_t* bar_req = bar_feat + 1;                // the leader's tree step has published the next request
+  uint64_t* bar_feat = bar_tfree + 1;              // tx: the head partial sums of all CTAs have landed in MY featp
+  uint64_t* bar_fc = bar_feat + 1;                 // leader, tx: logits / value hidden units of all CTAs have landed
+  uint64_t* bar_req = bar_fc + 1;                  // the leader's tree step has published the next request
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_req + 1);
   const uint32_t rank = cluster_ctarank();
   const int game = (int)blockIdx.x / kSoloNC;
@@ -171,6 +191,20 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
   for (int i = tid; i < n_layers * kSoloN; i += kSoloThreads)
     s_bias[i] = W.bias[(i / kSoloN) * kC + (int)rank * kSoloN + i % kSoloN];
   for (int i = tid; i < 3 * kSoloN; i += kSoloThreads) s_headw[i] = W.head_w[(i / kSoloN) * kC + (int)rank * kSoloN + i % kSoloN];
+  for (int i = tid; i < G::OQ; i += kSoloThreads) s_fcb[i] = (int)rank * G::OQ + i < G::A ? W.pfc_b[(int)rank * G::OQ + i] : 0.f;
+  for (int i = tid; i < kSoloN; i += kSoloThreads) {
+    s_fcb[G::OQ + i] = W.vfc1_b[(int)rank * kSoloN + i];
+    s_fcb[G::OQ + kSoloN + i] = W.vfc2_w[(int)rank * kSoloN + i];
+  }
+  if (tid < 3) s_fcb[G::OQ + 2 * kSoloN + tid] = W.head_b[tid];
+  if (G::FcSmem) {
+    for (int i = tid; i < 2 * G::A * G::OQ; i += kSoloThreads) {
+      const int kk = i / G::OQ, o = (int)rank * G::OQ + i % G::OQ;
+      s_pfcw[i] = o < G::A ? W.pfc_wT[(size_t)kk * G::A + o] : 0.f;
+    }
+    for (int i = tid; i < G::A * kSoloN; i += kSoloThreads)
+      s_vfcw[i] = W.vfc1_wT[(size_t)(i / kSoloN) * kC + (int)rank * kSoloN + i % kSoloN];
+  }
   for (int i = tid; i < G::NT * 9 * 4; i += kSoloThreads) {
     const int tile = i / 36, tap = (i / 4) % 9, word = i % 4;
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -187,10 +221,12 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], kSoloIssuers);
     }
-    for (int i = 0; i < kSoloIssuers; ++i) mbar_init(&bar_act[i], kSoloEpiWarps);
+    for (int i = 0; i < kSoloIssuers; ++i) mbar_init(&bar_act[i], 1);
+    mbar_init(bar_in, kSoloEpiWarps);
     mbar_init(bar_acc, kSoloIssuers * kSoloNC);
     mbar_init(bar_tfree, kSoloEpiWarps);
-    mbar_init(bar_feat, kSoloEpiWarps * kSoloNC);
+    mbar_init(bar_feat, 1);
+    mbar_init(bar_fc, 1);
     mbar_init(bar_req, 1);
     fence_mbar_init();
   }
@@ -230,7 +266,8 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
     const uint32_t desc_hi = umma_desc_hi(128u);
     constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;
     constexpr uint32_t kBStep = (2u * (uint32_t)kSoloN * 16u) >> 4;
-    uint32_t lc = 0, gc = 0;
+    uint32_t lc = 0, gc = 0, act_ph = 0;
+    if (lane == 0) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the first delivery of CTA i's channels
     for (int rd = 0; rd < rounds; ++rd)
       for (int l = 0; l < n_layers; ++l, ++lc) {
         const bool to_s = (l & 1) == 0;       // stem and conv2: issuer 0 accumulates in S (conv2: onto the block input x)
@@ -238,9 +275,21 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         const int nk = l == 0 ? 1 : kC / 16;
         const uint32_t tapb = l == 0 ? (uint32_t)kSoloStemTapBytes : (uint32_t)kSoloTapBytes;
         mbar_wait(bar_tfree, lc & 1u);
-        mbar_wait_cluster(&bar_act[i], lc & 1u);
-        fence_proxy_async_smem();  // generic-proxy writes of the other CTAs' epilogues (acquired above) -> my MMAs' operand reads
+        AO_DBG(const long long dbg_i0 = (W.dbg && blockIdx.x == 0 && i == 0) ? clock64() : 0;)
+        if (l == 0) {
+          mbar_wait(bar_in, (uint32_t)rd & 1u);
+        } else {
+          mbar_wait_cluster(&bar_act[i], act_ph);
+          act_ph ^= 1u;
+          if (lane == 0) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the next delivery
+        }
+        fence_proxy_async_smem();  // rows written through the generic proxy (acquired above) -> my MMAs' operand reads
         tc_fence_after_sync();
+        AO_DBG(if (W.dbg && blockIdx.x == 0 && i == 0 && lane == 0) {
+          const long long t = clock64();
+          atomicAdd(&W.dbg[7], (unsigned long long)(t - dbg_i0));
+          *reinterpret_cast<volatile long long*>(s_tmem + 2) = t;
+        })
         const uint32_t acc_col = i == 0 ? (to_s ? 0u : (uint32_t)kSoloN) : (uint32_t)(kSoloN * (1 + i));
         for (int g = 0; g < 3; ++g, ++gc) {
           const uint32_t slot = gc % (uint32_t)RG, ph = (gc / (uint32_t)RG) & 1u;
@@ -278,24 +327,35 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         }
       }
   } else {
-    // =========================================================== epilogue warps (+ heads and tree step on the leader)
+    // =========================================================== epilogue warps; after the tower: heads, tree step
     const int q = warp & 3, half = warp >> 2;   // TMEM lane quarter, half of this CTA's 32 accumulator columns
     const int r = q * 32 + lane;
     const uint32_t chunk_stride = (uint32_t)G::Rows * 16u;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t act_addr = smem_u32(s_act);
-    uint32_t peer_act[kSoloNC];
+    uint32_t peer_act[kSoloNC], peer_bar_act[kSoloNC], peer_featp[kSoloNC], peer_bar_feat[kSoloNC];
 #pragma unroll
-    for (int c = 0; c < kSoloNC; ++c) peer_act[c] = mapa_cluster(act_addr, (uint32_t)c);
-    const uint32_t featp_leader = mapa_cluster(smem_u32(s_featp), 0u);
+    for (int c = 0; c < kSoloNC; ++c) {
+      peer_act[c] = mapa_cluster(smem_u32(s_act), (uint32_t)c);
+      peer_bar_act[c] = mapa_cluster(smem_u32(&bar_act[rank]), (uint32_t)c);
+      peer_featp[c] = mapa_cluster(smem_u32(s_featp), (uint32_t)c);
+      peer_bar_feat[c] = mapa_cluster(smem_u32(bar_feat), (uint32_t)c);
+    }
+    const uint32_t leader_logits = mapa_cluster(smem_u32(s_logits), 0u);
+    const uint32_t leader_hidden = mapa_cluster(smem_u32(s_hidden), 0u);
+    const uint32_t leader_bar_fc = mapa_cluster(smem_u32(bar_fc), 0u);
     uint32_t lc = 0;
-    AO_DBG(const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0; long long dbg_t3 = 0;)
+    AO_DBG(const bool dbg_on = W.dbg != nullptr && blockIdx.x == 0 && tid == 0; long long dbg_t3 = 0;
+           if (dbg_on) { g_tree_dbg_on = 1; for (int k = 0; k < 12; ++k) g_tree_dbg[k] = 0ull; } __syncwarp();)
     // "my accumulator reads are done" for the very first layer of the launch: nothing was read yet
     if (lane == 0) mbar_arrive(bar_tfree);
 
     for (int rd = 0; rd < rounds; ++rd) {
       if (rd > 0) mbar_wait_cluster(bar_req, (uint32_t)(rd - 1) & 1u);
       AO_DBG(const long long dbg_t0 = dbg_on ? clock64() : 0; if (dbg_on && rd > 0) atomicAdd(&W.dbg[4], (unsigned long long)(dbg_t0 - dbg_t3));)
+      if (tid == 0) {  // arm this round's deliveries of the heads
+        mbar_arrive_expect_tx(bar_feat, G::FeatTx);
+        if (rank == 0) mbar_arrive_expect_tx(bar_fc, G::FcTx);
+      }
       // ---- the five input planes of the request (utils.get_state_pt as row bit-masks) -> k-chunks 0 and 1 of my buffer
       {
         const int R_in = (G::NT == 2 ? half * kTileRows : 0) + r;
@@ -312,11 +372,8 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           *reinterpret_cast<uint4*>(s_act + ro) = c0;
           *reinterpret_cast<uint4*>(s_act + chunk_stride + ro) = make_uint4(0, 0, 0, 0);
         }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0)
-          for (int c = 0; c < kSoloIssuers; ++c) mbar_arrive(&bar_act[c]);
+        if (lane == 0) mbar_arrive(bar_in);  // release at CTA scope; the issuers fence the proxies after their wait
       }
 
       for (int l = 0; l < n_layers; ++l, ++lc) {
@@ -326,8 +383,11 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         AO_DBG(const long long dbg_a0 = dbg_on ? clock64() : 0;)
         mbar_wait(bar_acc, lc & 1u);  // arrivals are tcgen05.commits (all CTAs): nothing to acquire but the accumulators
         tc_fence_after_sync();
-        AO_DBG(if (dbg_on) atomicAdd(&W.dbg[5], (unsigned long long)(clock64() - dbg_a0));)
-        float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
+        AO_DBG(if (dbg_on) {
+          const long long t = clock64();
+          atomicAdd(&W.dbg[5], (unsigned long long)(t - dbg_a0));
+          atomicAdd(&W.dbg[6], (unsigned long long)(t - *reinterpret_cast<volatile long long*>(s_tmem + 2)));
+        })
 #pragma unroll
         for (int t = 0; t < G::NT; ++t) {
           const int R = t * kTileRows + r;
@@ -341,11 +401,6 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
             tmem_ld16(col0 + 4u * kSoloN, v3);
           }
           tmem_ld_wait();
-          if (t == G::NT - 1) {  // the issuers may overwrite the accumulators with the next layer
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tfree);
-          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float s = __uint_as_float(v0[j]);
@@ -353,7 +408,6 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
             v0[j] = __float_as_uint(fmaxf(s + bias[j], 0.f));
           }
           if (!last) {
-            if (to_s) tmem_st16(col0, v0);  // fp32 block input for the next residual add
             uint4 pk[2];
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -371,17 +425,16 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
               const uint32_t off0 = (uint32_t)((int)rank * 4 + half * 2) * chunk_stride + (uint32_t)(G::Halo + R) * 16u;
 #pragma unroll
               for (int c = 0; c < kSoloNC; ++c) {
-                if (c == (int)rank) continue;
-                st_cluster_v4(peer_act[c] + off0, pk[0]);
-                st_cluster_v4(peer_act[c] + off0 + chunk_stride, pk[1]);
+                st_async_v4(peer_act[c] + off0, pk[0], peer_bar_act[c]);
+                st_async_v4(peer_act[c] + off0 + chunk_stride, pk[1], peer_bar_act[c]);
               }
-              *reinterpret_cast<uint4*>(s_act + off0) = pk[0];
-              *reinterpret_cast<uint4*>(s_act + off0 + chunk_stride) = pk[1];
             }
+            if (to_s) tmem_st16(col0, v0);  // fp32 block input for the next residual add
           } else {
-            // heads' 1x1 convolutions (model.py:44-46, 64-66) over this thread's 16 channels
+            // heads' 1x1 convolutions (model.py:44-46, 64-66) over this thread's 16 channels -> slot (CTA, half) of every
+            // CTA's partial-sum table (fixed slots: the order of the float adds does not depend on arrival order)
             const float* hw = s_headw + half * 16;
-            hd0 = hd1 = hd2 = 0.f;
+            float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x = __uint_as_float(v0[j]);
@@ -390,113 +443,132 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
               hd2 = fmaf(x, hw[2 * kSoloN + j], hd2);
             }
             if (valid) {
-              const uint32_t fo = featp_leader + (uint32_t)((((int)rank * 2 + half) * 3) * G::A + R) * 4u;
-              st_cluster_f32(fo, hd0);
-              st_cluster_f32(fo + (uint32_t)G::A * 4u, hd1);
-              st_cluster_f32(fo + 2u * (uint32_t)G::A * 4u, hd2);
+              const uint32_t fo = (uint32_t)((((int)rank * 2 + half) * 3) * G::A + R) * 4u;
+#pragma unroll
+              for (int c = 0; c < kSoloNC; ++c) {
+                st_async_f32(peer_featp[c] + fo, hd0, peer_bar_feat[c]);
+                st_async_f32(peer_featp[c] + fo + (uint32_t)G::A * 4u, hd1, peer_bar_feat[c]);
+                st_async_f32(peer_featp[c] + fo + 2u * (uint32_t)G::A * 4u, hd2, peer_bar_feat[c]);
+              }
             }
           }
         }
-        if (!last) {
-          if (to_s) tmem_st_wait();
-          // the rows were written through the generic proxy (DSMEM stores); the consuming issuer orders them against its
-          // MMAs' operand reads with a proxy fence after its acquire
-          tc_fence_before_sync();
-          fence_release_cluster();
-          __syncwarp();
-          if (lane == 0)
-            for (int c = 0; c < kSoloNC; ++c) mbar_arrive_remote_relaxed(&bar_act[rank], (uint32_t)c);
-        } else {
-          fence_release_cluster();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote_relaxed(bar_feat, 0u);
-        }
+        // the issuers may overwrite the accumulators with the next layer (and issuer 0 finds the new block input in S)
+        if (!last && to_s) tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tfree);
       }
 
-      if (rank == 0) {
-        // =========================================================== heads (model.py:43-50, 63-73) + tree step, leader only
-        mbar_wait_cluster(bar_feat, (uint32_t)rd & 1u);
-        AO_DBG(const long long dbg_t1 = dbg_on ? clock64() : 0;)
-        for (int i = tid; i < 3 * G::A; i += 256) {
-          float s = s_featp[i];
+      // =========================================================== heads (model.py:43-50, 63-73): a quarter per CTA
+      mbar_wait_cluster(bar_feat, (uint32_t)rd & 1u);
+      AO_DBG(const long long dbg_t1 = dbg_on ? clock64() : 0;)
+      for (int i = tid; i < 3 * G::A; i += 256) {
+        float s = s_featp[i];
 #pragma unroll
-          for (int pp = 1; pp < kSoloParts; ++pp) s += s_featp[pp * 3 * G::A + i];
-          s_feat[i] = fmaxf(s + W.head_b[i / G::A], 0.f);
+        for (int pp = 1; pp < kSoloParts; ++pp) s += s_featp[pp * 3 * G::A + i];
+        s_feat[i] = fmaxf(s + s_fcb[G::OQ + 2 * kSoloN + i / G::A], 0.f);
+      }
+      solo_epi_sync();
+      if (tid < G::KSP * G::OQ) {  // policy FC outputs [rank OQ, rank OQ + OQ), K split over KSP thread groups
+        const int ks = tid / G::OQ, oo = tid % G::OQ;
+        const int o = (int)rank * G::OQ + oo;
+        const int k0 = ks * G::KLP, k1 = min(2 * G::A, k0 + G::KLP);
+        float acc = 0.f;
+        if (o < G::A) {
+          if (G::FcSmem) {
+#pragma unroll 7
+            for (int kk = k0; kk < k1; ++kk) acc = fmaf(s_pfcw[kk * G::OQ + oo], s_feat[kk], acc);
+          } else {
+            const float* wt = W.pfc_wT + o;
+#pragma unroll 16
+            for (int kk = k0; kk < k1; ++kk) acc = fmaf(__ldg(wt + (size_t)kk * G::A), s_feat[kk], acc);
+          }
         }
-        solo_epi_sync();
-        if (tid < G::KS * G::A) {  // policy FC, K split over KS thread groups
-          constexpr int KL = (2 * G::A + G::KS - 1) / G::KS;
-          const int ks = tid / G::A, po = tid % G::A;
-          const int k0 = ks * KL, k1 = min(2 * G::A, k0 + KL);
-          const float* wt = W.pfc_wT + po;
-          float acc = 0.f;
-#pragma unroll 18
-          for (int kk = k0; kk < k1; ++kk) acc = fmaf(__ldg(wt + (size_t)kk * G::A), s_feat[kk], acc);
-          s_fcpart[ks * G::A + po] = acc;
-        }
-        {  // value FC1, K split in two
-          constexpr int KL = (G::A + 1) / 2;
-          const int vs = tid >> 7, vj = tid & 127;
-          const int k0 = vs * KL, k1 = min(G::A, k0 + KL);
-          const float* f = s_feat + 2 * G::A;
-          const float* wt = W.vfc1_wT + vj;
-          float acc = 0.f;
-#pragma unroll 21
+        s_fcpart[ks * G::OQ + oo] = acc;
+      }
+      {  // value FC1 hidden units [32 rank, 32 rank + 32), K split over VS thread groups
+        const int vs = tid / kSoloN, vj = tid % kSoloN;
+        const int k0 = vs * G::KLV, k1 = min(G::A, k0 + G::KLV);
+        const float* f = s_feat + 2 * G::A;
+        float acc = 0.f;
+        if (G::FcSmem) {
+#pragma unroll 11
+          for (int kk = k0; kk < k1; ++kk) acc = fmaf(s_vfcw[kk * kSoloN + vj], f[kk], acc);
+        } else {
+          const float* wt = W.vfc1_wT + (int)rank * kSoloN + vj;
+#pragma unroll 15
           for (int kk = k0; kk < k1; ++kk) acc = fmaf(__ldg(wt + (size_t)kk * kC), f[kk], acc);
-          s_hpart[vs * kC + vj] = acc;
         }
-        solo_epi_sync();
-        if (tid < G::A) {
-          float acc = W.pfc_b[tid];
+        s_hpart[vs * kSoloN + vj] = acc;
+      }
+      solo_epi_sync();
+      if (tid < G::OQ) {
+        if ((int)rank * G::OQ + tid < G::A) {
+          float acc = s_fcb[tid];
 #pragma unroll
-          for (int ks = 0; ks < G::KS; ++ks) acc += s_fcpart[ks * G::A + tid];
-          s_logits[tid] = acc;
+          for (int ks = 0; ks < G::KSP; ++ks) acc += s_fcpart[ks * G::OQ + tid];
+          st_async_f32(leader_logits + (uint32_t)((int)rank * G::OQ + tid) * 4u, acc, leader_bar_fc);
         }
-        if (tid < kC) s_hidden[tid] = fmaxf(W.vfc1_b[tid] + s_hpart[tid] + s_hpart[kC + tid], 0.f) * W.vfc2_w[tid];
-        solo_epi_sync();
-        if (warp == 0) {
-          float mx = -3.0e38f;
-          for (int kk = lane; kk < G::A; kk += 32) mx = fmaxf(mx, s_logits[kk]);
+      } else if (tid >= 64 && tid < 64 + kSoloN) {
+        const int vj = tid - 64;
+        float acc = s_fcb[G::OQ + vj];
 #pragma unroll
-          for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-          float sum = 0.f;
-          for (int kk = lane; kk < G::A; kk += 32) sum += expf(s_logits[kk] - mx);
+        for (int vs = 0; vs < G::VS; ++vs) acc += s_hpart[vs * kSoloN + vj];
+        st_async_f32(leader_hidden + (uint32_t)((int)rank * kSoloN + vj) * 4u, fmaxf(acc, 0.f) * s_fcb[G::OQ + kSoloN + vj], leader_bar_fc);
+      }
+      if (rank == 0 && warp == 0) {
+        // ---- leader: softmax, tanh, then the tree step of the game
+        mbar_wait_cluster(bar_fc, (uint32_t)rd & 1u);
+        float mx = -3.0e38f;
+        for (int kk = lane; kk < G::A; kk += 32) mx = fmaxf(mx, s_logits[kk]);
 #pragma unroll
-          for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-          float hv = 0.f;
-          for (int kk = lane; kk < kC; kk += 32) hv += s_hidden[kk];
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float sum = 0.f;
+        for (int kk = lane; kk < G::A; kk += 32) sum += expf(s_logits[kk] - mx);
 #pragma unroll
-          for (int o = 16; o; o >>= 1) hv += __shfl_xor_sync(0xFFFFFFFFu, hv, o);
-          for (int kk = lane; kk < G::A; kk += 32) s_pol[kk] = expf(s_logits[kk] - mx) / sum;
-          const float v = tanhf(hv + W.vfc2_b);
-          __syncwarp();
-          AO_DBG(const long long dbg_t2 = dbg_on ? clock64() : 0;)
-          // ---- the tree step of the game (tree_device.cuh): consume the answer, expand, back up, play the move when the
-          // search is complete, select the next leaf and write its request to P.nn_in[game]
-          uint8_t* ts = smem + SL::tree;
-          WarpSmem ws;
-          ws.dbuf = reinterpret_cast<double*>(ts);
-          ws.dbuf2 = ws.dbuf + G::APad;
-          ws.order = reinterpret_cast<uint8_t*>(ws.dbuf2 + G::APad);
-          ws.table = reinterpret_cast<int16_t*>(ws.order + 256);
-          ws.rows = reinterpret_cast<uint16_t(*)[32]>(ws.table + 128);
-          ws.pol = s_pol;
-          (void)tree_step_game<(G::A <= 96 ? 3 : 8)>(P, game, &ws, lane, 64, true, v);
-          __threadfence();  // the request (global memory) before the arrives below
-          __syncwarp();
-          AO_DBG(if (dbg_on) {
-            dbg_t3 = clock64();
-            atomicAdd(&W.dbg[0], 1ull);
-            atomicAdd(&W.dbg[1], (unsigned long long)(dbg_t1 - dbg_t0));
-            atomicAdd(&W.dbg[2], (unsigned long long)(dbg_t2 - dbg_t1));
-            atomicAdd(&W.dbg[3], (unsigned long long)(dbg_t3 - dbg_t2));
-          })
-          if (lane == 0)
-            for (int c = 0; c < kSoloNC; ++c) mbar_arrive_remote_relaxed(bar_req, (uint32_t)c);
-        }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        float hv = 0.f;
+        for (int kk = lane; kk < kC; kk += 32) hv += s_hidden[kk];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) hv += __shfl_xor_sync(0xFFFFFFFFu, hv, o);
+        for (int kk = lane; kk < G::A; kk += 32) s_pol[kk] = expf(s_logits[kk] - mx) / sum;
+        const float v = tanhf(hv + W.vfc2_b);
+        __syncwarp();
+        AO_DBG(const long long dbg_t2 = dbg_on ? clock64() : 0;)
+        // tree_device.cuh: consume the answer, expand, back up, play the move when the search is complete, select the
+        // next leaf and write its request to P.nn_in[game]
+        uint8_t* ts = smem + SL::tree;
+        WarpSmem ws;
+        ws.dbuf = reinterpret_cast<double*>(ts);
+        ws.dbuf2 = ws.dbuf + G::APad;
+        ws.order = reinterpret_cast<uint8_t*>(ws.dbuf2 + G::APad);
+        ws.table = reinterpret_cast<int16_t*>(ws.order + 256);
+        ws.rows = reinterpret_cast<uint16_t(*)[32]>(ws.table + 128);
+        ws.pol = s_pol;
+        (void)tree_step_game<(G::A <= 96 ? 3 : 8)>(P, game, &ws, lane, 64, true, v);
+        __threadfence();  // the request (global memory) before the arrives below
+        __syncwarp();
+        AO_DBG(if (dbg_on) {
+          dbg_t3 = clock64();
+          atomicAdd(&W.dbg[0], 1ull);
+          atomicAdd(&W.dbg[1], (unsigned long long)(dbg_t1 - dbg_t0));
+          atomicAdd(&W.dbg[2], (unsigned long long)(dbg_t2 - dbg_t1));
+          atomicAdd(&W.dbg[3], (unsigned long long)(dbg_t3 - dbg_t2));
+        })
+        if (lane == 0)
+          for (int c = 0; c < kSoloNC; ++c) mbar_arrive_remote_relaxed(bar_req, (uint32_t)c);
       }
     }
   }
+  AO_DBG(if (W.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+    g_tree_dbg_on = 0;
+    printf("tree step phases, cycles per round: regs+leaf loads %llu | expand: legal order %llu, prior sum %llu, noise + child block %llu, backup %llu"
+           " | (expand_and_backup total incl. bookkeeping %llu) | selection walk %llu, win check %llu, terminal backup %llu, request %llu, store regs %llu\n",
+           g_tree_dbg[0] / rounds, g_tree_dbg[2] / rounds, g_tree_dbg[3] / rounds, g_tree_dbg[4] / rounds, g_tree_dbg[5] / rounds,
+           g_tree_dbg[1] / rounds, g_tree_dbg[6] / rounds, g_tree_dbg[7] / rounds, g_tree_dbg[8] / rounds, g_tree_dbg[9] / rounds,
+           g_tree_dbg[10] / rounds);
+  })
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // no CTA leaves while another one of the cluster may still signal it or write into its buffers

@@ -43,6 +43,23 @@ struct WarpSmemStore {
 
 constexpr int kWarpsPerBlock = 4;
 
+// probe build: cycle counters of the phases of tree_step_game (lane 0; one copy per translation unit, printed by the
+// solo kernel at the end of a launch when ao_tower_debug is on)
+#ifdef AO_PROBE
+__device__ unsigned long long g_tree_dbg[12];
+__device__ int g_tree_dbg_on;
+#define AO_TDBG_BEGIN long long tdbg_t = g_tree_dbg_on ? clock64() : 0;
+#define AO_TDBG(k)                                                      \
+  if (g_tree_dbg_on && (threadIdx.x & 31) == 0) {                        \
+    const long long tdbg_n = clock64();                                 \
+    atomicAdd(&g_tree_dbg[k], (unsigned long long)(tdbg_n - tdbg_t));   \
+    tdbg_t = tdbg_n;                                                    \
+  }
+#else
+#define AO_TDBG_BEGIN
+#define AO_TDBG(k)
+#endif
+
 struct Ctx {
   const TreeParams& P;
   Game* gm;
@@ -161,12 +178,14 @@ __device__ bool expand_and_backup(Ctx& c, Regs& g, int depth, float value, bool 
   const TreeParams& P = c.P;
   uint32_t* path = P.path + (size_t)c.game * (P.A + 1);
   float delta;
+  AO_TDBG_BEGIN
   if (!terminal) {
     WarpSmem* sm = c.sm;
     // occupancy rows -> legal actions in reference child order
     if (c.lane < 32) sm->rows[0][c.lane] = (uint16_t)(sm->rows[0][c.lane] | sm->rows[1][c.lane]);
     __syncwarp();
     const int L = legal_order(sm->rows[0], P.B, P.A, sm->order, sm->table, c.lane);
+    AO_TDBG(2)
     // prior_prob = zeros(A); prior_prob[legal] = policy[legal]; prior_prob /= prior_prob.sum()   (agents.py:183-189)
     for (int a = c.lane; a < P.A; a += 32) {
       const bool legal = ((sm->rows[0][a / P.B] >> (a % P.B)) & 1u) == 0u;
@@ -174,6 +193,7 @@ __device__ bool expand_and_backup(Ctx& c, Regs& g, int depth, float value, bool 
     }
     __syncwarp();
     const double S = np_pairwise_sum(sm->dbuf, P.A, c.lane);
+    AO_TDBG(3)
     const bool is_root = depth == 0;
     const bool mix = is_root && P.noise;
     if (mix) draw_dirichlet(c, L, g.noise_draws);
@@ -193,25 +213,28 @@ __device__ bool expand_and_backup(Ctx& c, Regs& g, int depth, float value, bool 
     if (is_root) g.root_node = (int32_t)off;
     else if (c.lane == 0) P.slot_child[path[depth - 1]] = (int32_t)off;
     delta = -value;
+    AO_TDBG(4)
   } else {
     delta = 1.0f;  // reward 1.0 for wins and draws alike (agents.py:216-221)
   }
-  // backup: leaf slot gets +delta, alternating up to and including the root
-  if (c.lane == 0) {
-    float d = delta;
-    for (int i = depth - 1; i >= 0; --i) {
-      uint2 nw = P.slot_nw[path[i]];
+  // backup: leaf slot gets +delta, alternating up to and including the root.  Every level of the path is a slot of its
+  // own, so the lanes take the levels in parallel: one round trip to memory for the whole path instead of two per level
+  // (the arithmetic per slot - one float add of +-delta - is the sequential loop's).
+  for (int i0 = 0; i0 < depth; i0 += 32) {
+    const int i = i0 + c.lane;
+    if (i < depth) {
+      const uint32_t s = path[i];
+      uint2 nw = P.slot_nw[s];
       nw.x += 1u;
-      nw.y = __float_as_uint(__fadd_rn(__uint_as_float(nw.y), d));
-      P.slot_nw[path[i]] = nw;
-      d = -d;
+      nw.y = __float_as_uint(__fadd_rn(__uint_as_float(nw.y), ((depth - 1 - i) & 1) ? -delta : delta));
+      P.slot_nw[s] = nw;
     }
-    g.root_w = __fadd_rn(g.root_w, d);
   }
-  g.root_w = __shfl_sync(kFull, g.root_w, 0);
+  g.root_w = __fadd_rn(g.root_w, (depth & 1) ? -delta : delta);  // the same value in every lane
   g.root_n += 1u;
   g.sims_done += 1;
   __syncwarp();
+  AO_TDBG(5)
   return true;
 }
 
@@ -690,12 +713,19 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
   if (arena) game0 = P.games[game0].arena_cur ? P.arena_M + game0 : game0;  // unit = match; slot of the side to move
   Ctx c{P, &P.games[game0], ws, lane_, game0, 0, make_uint2(P.seed_lo, P.seed_hi)};
   Regs g;
+  AO_TDBG_BEGIN
   load_regs(c, g);
   if (g.status != ST_SEARCH && g.status != ST_WAIT_NN) return false;
   c.abase = arena_base(P, c.game, g.arena);
   const int lane = c.lane;
   WarpSmem* sm = c.sm;
   const bool auto_play = c.gm->auto_play != 0;
+  // the pending leaf (only the first iteration can find the game waiting for the network): loaded together with the
+  // registers above - one round trip to memory instead of three dependent ones
+  const int pre_slot = c.gm->nn_slot, pre_depth = c.gm->leaf_depth, pre_static = c.gm->nn_static;
+  const uint32_t pre_ticket = c.gm->nn_ticket, pre_log = c.gm->nn_log_count;
+  const uint16_t pre_rb = lane_ < kRowsPad ? c.gm->leaf_rows_b[lane_] : (uint16_t)0;
+  const uint16_t pre_rw = lane_ < kRowsPad ? c.gm->leaf_rows_w[lane_] : (uint16_t)0;
   // c.gm / c.game change when an arena match hands over to the other side: always go through them
   auto path = [&]() { return P.path + (size_t)c.game * (P.A + 1); };
 
@@ -703,21 +733,22 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
     if (g.status == ST_WAIT_NN) {
       // -------- consume the network output for the pending leaf - once the tower has served its ticket (a ragged last
       // wave of requests may have been left for the next round, NNQueue.defer)
-      if (!nn_in_smem && !c.gm->nn_static) {
+      const bool pre = it == 0;
+      if (!nn_in_smem && !(pre ? pre_static : c.gm->nn_static)) {
         const int qnet = arena ? arena_side(P, c.game) : 0;
-        if ((int32_t)(P.nn_head[qnet] - c.gm->nn_ticket) <= 0) break;  // not answered yet: keep waiting
+        if ((int32_t)(P.nn_head[qnet] - (pre ? pre_ticket : c.gm->nn_ticket)) <= 0) break;  // not answered yet: keep waiting
       }
-      const int slot = c.gm->nn_slot;
-      const int depth = c.gm->leaf_depth;
+      const int slot = pre ? pre_slot : c.gm->nn_slot;
+      const int depth = pre ? pre_depth : c.gm->leaf_depth;
       // the network's answer: from the exchange buffers in HBM, or already in sm->pol (persistent self-play kernel)
       if (!nn_in_smem)
         for (int a = lane; a < P.A; a += 32) sm->pol[a] = P.nn_policy[(size_t)slot * P.A + a];
       const float value = nn_in_smem ? nn_value_smem : P.nn_value[slot];
-      sm->rows[0][lane] = lane < kRowsPad ? c.gm->leaf_rows_b[lane] : (uint16_t)0;
-      sm->rows[1][lane] = lane < kRowsPad ? c.gm->leaf_rows_w[lane] : (uint16_t)0;
+      sm->rows[0][lane] = pre ? pre_rb : (lane < kRowsPad ? c.gm->leaf_rows_b[lane] : (uint16_t)0);
+      sm->rows[1][lane] = pre ? pre_rw : (lane < kRowsPad ? c.gm->leaf_rows_w[lane] : (uint16_t)0);
       __syncwarp();
       if (P.nn_log_cap > 0) {
-        const uint32_t k = c.gm->nn_log_count;
+        const uint32_t k = pre ? pre_log : c.gm->nn_log_count;
         if (k < (uint32_t)P.nn_log_cap) {
           float* lp = P.nnlog_policy + ((size_t)c.game * P.nn_log_cap + k) * P.A;
           for (int a = lane; a < P.A; a += 32) lp[a] = sm->pol[a];
@@ -727,12 +758,14 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
         if (lane == 0) c.gm->nn_log_count = k + 1u;
       }
       g.status = ST_SEARCH;
+      AO_TDBG(0)
       if (!expand_and_backup(c, g, depth, value, false)) {
         g.status = ST_ERROR;
         if (lane == 0) c.gm->error = 1;
         break;
       }
       if (lane == 0) c.gm->sims_total += 1ull;
+      AO_TDBG(1)
       continue;
     }
     if (arena) {
@@ -866,8 +899,10 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
         }
       }
     }
+    AO_TDBG(6)
     if (need_eval) win = check_win_rows(rb, rw, P.B, nm, sm->rows, lane);
     __syncwarp();
+    AO_TDBG(7)
     if (win != 0) {
       // terminal leaf: mark, backup reward (no network call; the reference's call is discarded, agents.py:171-178)
       if (lane == 0) {
@@ -878,6 +913,7 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
       if (depth == 0) g.root_node = -(1 + win);
       __syncwarp();
       expand_and_backup(c, g, depth, 0.f, true);
+      AO_TDBG(8)
       continue;
     }
     // -------- non-terminal leaf: evaluate
@@ -941,11 +977,13 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
         c.gm->nn_evals += 1ull;
       }
       g.status = ST_WAIT_NN;
+      AO_TDBG(9)
       break;
     }
   }
   __syncwarp();
   store_regs<MAXJ>(c, g);
+  AO_TDBG(10)
   return g.status == ST_SEARCH || g.status == ST_WAIT_NN;
 }
 

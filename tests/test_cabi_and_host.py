@@ -246,6 +246,17 @@ def test_weights_are_uploaded_once_per_change_not_once_per_search():
     agent.model = other
     agent._sync_weights()
     assert agent._engine.uploads == 4
+    with torch.no_grad():                    # `.data` write (own version counter) on CPU weights: seen through the sampled values
+        other.conv1.weight.data.mul_(1.5)
+    agent._sync_weights()
+    assert agent._engine.uploads == 5
+    other.conv1.weight = torch.nn.Parameter(other.conv1.weight.detach().clone())  # replaced Parameter object
+    agent._sync_weights()
+    agent._sync_weights()
+    assert agent._engine.uploads == 6
+    agent.invalidate_weights()
+    agent._sync_weights()
+    assert agent._engine.uploads == 7
     agent._engine = None                     # do not let __del__ paths touch the fake
 
 

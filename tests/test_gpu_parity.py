@@ -627,3 +627,83 @@ def test_persistent_kernel_and_deferred_tails_equal_the_plain_round_loop(cabi, m
         for a, b in zip(runs[0], other):
             assert np.array_equal(a, b)
     assert set(np.unique(runs[0][2])) <= {1, 2, 3}
+
+
+# ------------------------------------------------------------------------------------------------ cluster-of-four kernel
+def _nn_replay_check(cabi, B, sims, G, seed, n_check=24, rounds=64):
+    """self-play of G games through ao_selfplay_rounds with the PVNet evaluator and a noise tape; the oracle replays the
+    logged network outputs (bit-exact visits / moves / winners), the logged floats are checked against torch fp32"""
+    A = B * B
+    sd = pvnet_ref.make_state_dict(3, 10, 5, 128, B)
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=seed, noise_mode=cabi.AO_NOISE_TAPE,
+                      nn_log_cap=(sims + 1) * (A + 1), nn_precision=cabi.AO_NN_FP16)
+    eng.load_state_dict(sd)
+    tapes = [O.make_gamma_tape(seed, g, A + 2, A, 10 / A) for g in range(G)]
+    for g in range(G):
+        eng.set_gamma_tape(g, tapes[g])
+    eng.selfplay_begin(G, first_key=0)
+    st = eng.selfplay_rounds(rounds)
+    while st["running"]:
+        st = eng.selfplay_rounds(rounds)
+    assert st["errors"] == 0
+    moves, n_moves, winners, visits = eng.selfplay_fetch(G)
+    worst_p = worst_v = 0.0
+    for g in range(G):
+        pol, val = eng.nn_log(g, (sims + 1) * (A + 1))
+        it = iter(range(len(val)))
+        leaves = []
+
+        def evaluate(mv, pol=pol, val=val, it=it, leaves=leaves):
+            k = next(it)
+            leaves.append(mv)
+            return pol[k], val[k]
+
+        ora = O.self_play_game(B, sims, evaluate, O.DecisionStream(seed, g, tapes[g]))
+        k = len(ora["moves"])
+        assert n_moves[g] == k and winners[g] == ora["winner"], g
+        assert list(moves[g, :k]) == ora["moves"], g
+        assert np.array_equal(visits[g, :k], np.asarray(ora["visits"], np.uint32)), g
+        assert len(leaves) == len(val)
+        idx = list(range(0, len(leaves), max(1, len(leaves) // n_check)))
+        x = torch.from_numpy(np.stack([O.get_state_pt(leaves[i], B, 5) for i in idx]).astype(np.float32))
+        pr, vr = pvnet_ref.pvnet_forward(sd, x)
+        worst_p = max(worst_p, float(np.abs(pol[idx] - pr.numpy()).max()))
+        worst_v = max(worst_v, float(np.abs(val[idx] - vr.numpy()).max()))
+    eng.close()
+    return worst_p, worst_v
+
+
+@pytest.mark.parametrize("B,sims,G", [(9, 24, 1), (9, 12, 33), (15, 6, 2)])
+def test_solo_kernel_nn_replay_parity(cabi, B, sims, G):
+    """tower_solo.cu (one game per cluster of four CTAs; what ZeroAgent.get_pi and small self-play batches run on):
+    one game, the largest batch it takes (33 clusters) and 15x15 (two row tiles per CTA) - searches bit-exact against
+    the oracle on the logged network outputs, the floats within 1e-4 of torch fp32"""
+    worst_p, worst_v = _nn_replay_check(cabi, B, sims, G, seed=31)
+    assert worst_p < TOL and worst_v < TOL, (worst_p, worst_v)
+
+
+def test_solo_kernel_is_the_one_that_runs_and_agrees_with_the_pair_kernel(cabi, monkeypatch):
+    """ao_search on a few roots with the cluster-of-four kernel (default) and with the CTA-pair kernel (AO_NO_SOLO=1):
+    the two towers group the fp32 accumulation differently, so their floats differ in the last bits only - the root
+    evaluations of the same positions agree within 2e-5"""
+    B, A, sims = 9, 81, 30
+    sd = pvnet_ref.make_state_dict(5, 10, 5, 128, B)
+    roots = [(0,), (0, 40), (0, 40, 41, 30), (0, 3, 77, 12, 50, 51)]
+    logs = []
+    for no_solo in (False, True):
+        if no_solo:
+            monkeypatch.setenv("AO_NO_SOLO", "1")
+        else:
+            monkeypatch.delenv("AO_NO_SOLO", raising=False)
+        eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=len(roots), seed=2, noise=False, nn_log_cap=sims + 2,
+                          nn_precision=cabi.AO_NN_FP16)
+        eng.load_state_dict(sd)
+        vis, pri, real = eng.search(list(range(len(roots))), roots)
+        assert all(real) and (vis.sum(axis=1) >= sims - 1).all()
+        logs.append([eng.nn_log(g, sims + 2) for g in range(len(roots))])
+        eng.close()
+    for g in range(len(roots)):
+        (p0, v0), (p1, v1) = logs[0][g], logs[1][g]
+        assert len(v0) > 0 and len(v1) > 0
+        # the first evaluation of every search is the root position itself in both runs
+        assert np.abs(p0[0] - p1[0]).max() < 2e-5 and abs(float(v0[0]) - float(v1[0])) < 2e-5

@@ -22,7 +22,8 @@ print("search of %d sims: %.2f ms wall = %.1f us/sim" % (sims, dt * 1e3, dt * 1e
 if os.environ.get("AO_NO_SOLO") is None:
     k = max(d[0], 1)
     print("solo kernel (cluster of four), cycles per simulation over %d passes: tower %.0f (of which the epilogue thread waits for the MMAs %.0f), "
-          "heads %.0f, tree step %.0f, request turnaround %.0f" % (d[0], d[1] / k, d[5] / k, d[2] / k, d[3] / k, d[4] / k))
+          "heads %.0f, tree step %.0f, request turnaround %.0f; issuer 0: operands ready -> layer accumulated everywhere %.0f, waits for its operands (after the accumulators are free) %.0f"
+          % (d[0], d[1] / k, d[5] / k, d[2] / k, d[3] / k, d[4] / k, d[6] / k, d[7] / k))
     sys.exit(0)
 print("per simulation, cycles: mma warp total %.0f, waits for operands (epilogue / heads / tree / request) %.0f, waits for weights %.0f; "
       "epilogue thread total %.0f, waits for accumulators %.0f; launches %d"
