@@ -299,7 +299,51 @@ def run_legs(a, local, stream, _cabi):
                            "mean_plies": float(np.mean([len(r["moves"]) for r in recs])), "tree_overflows": st["errors"]}
     legs["arena"] = leg
     eng.close()
+    legs["single_game"] = single_game_leg(local)
     return legs
+
+
+def single_game_leg(device):
+    """BASELINE config 1 on the device: ONE 9x9 self-play game driven move by move through the reference-shaped facade
+    (agents.ZeroAgent.get_pi -> utils.get_action -> env.step, main.py:144-196), batch of one leaf per network call - the
+    latency-bound end of the path (tower_solo.cu: one game on a cluster of four CTAs).  Wall-clock around whole games,
+    host <-> device traffic of every get_pi included."""
+    import torch
+    from alpha_omok_b200 import agents, model, utils
+    from alpha_omok_b200.env import env_small as game
+    out = {"workload": "BASELINE config 1: one 9x9 self-play game through ZeroAgent.get_pi (ao_search), random-init PVNet 10x128 (numpy seed 0), "
+                       "noise on, tau 1 for 6 plies; sims/move = 40 (config 1) and 400 (the headline's search size)",
+           "kernel": "tower_solo_kernel<9>: one cluster of four CTAs per game, whole search in one launch", "unit": "simulations/s"}
+    net = model.PVNet(10, 5, 128, 9)
+    net.load_state_dict(model.seeded_state_dict(0, 10, 5, 128, 9), strict=False)
+    net.eval()
+    for sims in (40, 400):
+        best = None
+        for rep in range(3):
+            np.random.seed(rep)
+            agent = agents.ZeroAgent(9, sims, 5, noise=True, engine_kwargs={"device": device})
+            agent.model = net
+            env = game.GameState("text")
+            root_id, win_index, t, n_sims = (0,), 0, 0, 0
+            agent.get_pi(root_id, 1)          # engine creation + weight upload outside the timed region
+            agent.reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            while win_index == 0:
+                pi = agent.get_pi(root_id, 1 if t < 6 else 0)
+                n_sims += sims + (1 if agent.is_real_root else 0)
+                action, action_index = utils.get_action(pi)
+                root_id += (int(action_index),)
+                _, _, win_index, _, _ = env.step(action)
+                t += 1
+            dt = time.perf_counter() - t0
+            agent._engine.close()
+            r = {"sims_per_s": n_sims / dt, "ms_per_move": 1e3 * dt / t, "us_per_sim": 1e6 * dt / n_sims, "moves": t, "sims": n_sims}
+            if best is None or r["sims_per_s"] > best["sims_per_s"]:
+                best = r
+        out["sims%d" % sims] = best
+    out["value"] = out["sims40"]["sims_per_s"]
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- our arm

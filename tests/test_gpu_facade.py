@@ -294,10 +294,11 @@ def test_graphed_train_step_equals_eager_step():
         runs.append((np.asarray(log), {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}))
     (le, we), (lg, wg) = runs
     assert le.shape == lg.shape == (6, 3)
-    # step 1 sees identical weights: identical forward.  From step 2 on eager and captured runs may pick different cuDNN
-    # backward algorithms; Adam's g / (sqrt(v) + 1e-6) turns such last-bit gradient differences into visible ones
-    # (observed 3e-4 relative on the loss) - the same run-to-run spread two eager runs have.
-    np.testing.assert_allclose(lg[0], le[0], rtol=1e-6)
+    # step 1 sees identical weights; the captured step runs cuDNN's NHWC kernels (channels_last), the eager one the NCHW
+    # wrappers - TF32 tensor-core convolutions either way (torch's default), rounding differently in the last bits
+    # (observed 5e-6 relative on the loss).  From step 2 on Adam's g / (sqrt(v) + 1e-6) turns such last-bit gradient
+    # differences into visible ones (observed 3e-4 relative on the loss) - the same run-to-run spread two eager runs have.
+    np.testing.assert_allclose(lg[0], le[0], rtol=5e-5)
     np.testing.assert_allclose(lg, le, rtol=3e-3)
     np.testing.assert_allclose(le[:2], fx["losses"][:2], rtol=1e-3)   # the reference's own first two steps (CPU fixture)
     sd0 = {k: v for k, v in sd.items()}

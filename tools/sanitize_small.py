@@ -62,3 +62,17 @@ for kind in ("puct", "uct"):
     assert vis.sum(axis=1).tolist() == [24, 24]
     print("rollout", kind, "ok", flush=True)
 eng.close()
+# round 2, second half: the cluster-of-four kernel (tower_solo.cu) is what the 8-game self-play runs above and the
+# searches below use; 40 games are beyond its range and run the CTA-pair persistent kernel (static game -> pass map)
+for B in (9, 15):
+    eng = _cabi.Engine(board_size=B, num_mcts=6, max_games=40, n_blocks=2, seed=4)
+    eng.load_state_dict(seeded_state_dict(0, 2, 5, 128, B))
+    vis, pri, real = eng.search([0, 1, 2], [(0,), (0, 3), (0, 3, 4)])
+    assert all(real) and (vis.sum(axis=1) >= 5).all()
+    vis, pri, real = eng.search([0], [(0, int(np.argmax(vis[0])))])
+    assert vis.sum() >= 5
+    eng.selfplay_begin(40)
+    st = eng.selfplay_rounds(12)
+    assert st["errors"] == 0 and st["sims"] > 0
+    eng.close()
+    print("board", B, "solo search + 40-game persistent kernel ok", flush=True)
