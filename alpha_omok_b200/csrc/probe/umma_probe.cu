@@ -239,8 +239,9 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(int flavour, int iter
   if (warp <= 9 && warp > 9 - n_issuers) {
     if (leader) {
       iters /= n_issuers;
-      const int N = (flavour & 16) ? 64 : ((flavour & 64) ? 256 : 128);
-      const uint32_t idesc = ao::umma_idesc_f16_f32(PAIR ? 256 : 128, N);
+      // 8192: N = 32; 16384: cta_group::2 with M = 128 (64 rows per CTA) instead of 256
+      const int N = (flavour & 8192) ? 32 : (flavour & 16) ? 64 : ((flavour & 64) ? 256 : 128);
+      const uint32_t idesc = ao::umma_idesc_f16_f32(PAIR ? ((flavour & 16384) ? 128 : 256) : 128, N);
       const uint32_t brows = (uint32_t)(PAIR ? N / 2 : N);
       const uint32_t a_lo0 = ao::umma_desc_lo(ao::smem_u32(s_act), kRateRows * 16u);
       const uint32_t b_lo0 = ao::umma_desc_lo(ao::smem_u32(s_w), brows * 16u);

@@ -14,8 +14,9 @@ full.  `value` = simulations completed by all ranks / max-over-ranks device time
 pinned host memory copied H2D and visit counts copied D2H inside the timed region, every step.
 At N = 1 the line also carries `legs`: the other BASELINE configs measured the same way (config 3: 4096 games of 15x15;
 config 5: the arena, 1024 concurrent matches at 800 sims/move, shipped trained checkpoint vs a random-init net, both
-networks in one engine; and 4096-game self-play with the trained checkpoint = the hi/lo split tower), each with its own
-roofline numbers.  `cpu_baseline` = the unmodified reference on the host: BASELINE config 1 verbatim (one 40-sims/move
+networks in one engine; 4096-game self-play with the trained checkpoint = the hi/lo split tower), each with its own
+roofline numbers, and `single_game` = BASELINE config 1 itself on the device: ONE game driven move by move through
+agents.ZeroAgent.get_pi (40 and 400 sims/move; the cluster-of-four kernel of tower_solo.cu), wall clock.  `cpu_baseline` = the unmodified reference on the host: BASELINE config 1 verbatim (one 40-sims/move
 game, all torch threads) and the all-core aggregate at the bench's own 400 sims/move.
 """
 from __future__ import annotations
