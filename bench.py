@@ -101,8 +101,13 @@ def cpu_baseline_block(board, sims, cores, workers, agg_steps=2, with_config1=Tr
            "sample": f"{workers} single-thread processes, each playing its own {board}x{board} self-play game at {sims} sims/move "
                      f"with the {'unmodified reference (agents.ZeroAgent + model.PVNet on torch CPU fp32 + env)' if kind == 'reference' else 'oracle port'}: "
                      f"{agg_steps} moves per process = {n} simulations in {secs:.1f} s; host has {cores} cpus"}
+    c1 = None
     if with_config1:
-        c1 = ref_runner.run_config1_subprocess(workers)
+        try:
+            c1 = ref_runner.run_config1_subprocess(workers)
+        except Exception as e:  # bounded (ref_runner): the aggregate above stands on its own
+            out["config1"] = {"error": repr(e)}
+    if c1 is not None:
         out["config1"] = {"what": "BASELINE config 1 verbatim: one 9x9 self-play game, 40 sims/move, seeds 0, random-init "
                                   "PVNet(10,5,128,9), main.py:144-248 loop, torch threads = cores",
                           "sims_per_s": c1["sims"] / c1["seconds"], "games_per_s": 1.0 / c1["seconds"], "sims": c1["sims"],
@@ -132,6 +137,8 @@ def run_reference(a):
     cb = {"value": value, "unit": "expansions/s", "cores": workers, "kind": kind, "sample": sample}
     try:
         from oracle import ref_runner
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise RuntimeError("config 1 verbatim is timed at N = 1 only")
         c1 = ref_runner.run_config1_subprocess(workers)
         cb["config1"] = {"sims_per_s": c1["sims"] / c1["seconds"], "games_per_s": 1.0 / c1["seconds"], "sims": c1["sims"],
                          "moves": c1["moves"], "winner": c1["winner"], "threads": c1["threads"],
@@ -539,7 +546,7 @@ def run_ours(a):
                                         "verified_own_shard": bool(tot[15] == world)}
         if legs is not None:
             line["legs"] = legs
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:   # the host baseline is timed on rank 0 at N = 1 only (idle host cores)
             cores, workers = host_workers()
             line["cpu_baseline"] = cpu_baseline_block(B, S, cores, workers)
         sys.stdout.flush()

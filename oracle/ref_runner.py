@@ -159,6 +159,7 @@ def config1(threads, sims=40, seed=0, board=9):
 
 def _config1_entry(conn, threads, sims, seed, board):
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    os.environ["OMP_NUM_THREADS"] = str(threads)   # torchrun exports OMP_NUM_THREADS=1 to its ranks and their children
     conn.send(config1(threads, sims, seed, board))
 
 
@@ -206,12 +207,19 @@ class HostPool:
             p.join(timeout=5)
 
 
-def run_config1_subprocess(threads, sims=40, seed=0, board=9):
+def run_config1_subprocess(threads, sims=40, seed=0, board=9, timeout=150.0):
+    """config1() in a fresh process.  Bounded: a host whose cores are busy elsewhere (other ranks of a multi-GPU run
+    spinning in their CUDA / NCCL waits) can slow an all-core OpenMP run down by two orders of magnitude - after
+    `timeout` seconds the process is killed and TimeoutError raised."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     a, b = ctx.Pipe()
     p = ctx.Process(target=_config1_entry, args=(b, threads, sims, seed, board), daemon=True)
     p.start()
+    if not a.poll(timeout):
+        p.kill()
+        p.join(timeout=10)
+        raise TimeoutError("config 1 on the host did not finish within %.0f s" % timeout)
     out = a.recv()
     p.join(timeout=10)
     return out
