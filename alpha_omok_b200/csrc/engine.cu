@@ -347,6 +347,10 @@ extern "C" int ao_engine_create(const ao_config* cfg, ao_engine** out) {
   h->A = h->B * h->B;
   h->G = cfg->max_games;
   h->num_sms = prop.multiProcessorCount;
+#ifdef AO_PROBE  // probe build only: run the tower kernels on fewer SMs (what a cluster shape that strands SMs would start from)
+  if (getenv("AO_SM_LIMIT") && atoi(getenv("AO_SM_LIMIT")) >= 2 && atoi(getenv("AO_SM_LIMIT")) < h->num_sms)
+    h->num_sms = atoi(getenv("AO_SM_LIMIT")) & ~1;
+#endif
   h->selfplay_games = 0;
   h->d_stream = nullptr; h->stream_capacity = 0; h->d_stream_next = nullptr; h->stream_episodes = 0;
   h->round_graph = nullptr; h->graph_n = -1; h->graph_disabled = getenv("AO_NO_GRAPH") != nullptr;

@@ -5,9 +5,11 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alpha_omok_b200 import agents, model, utils
-from alpha_omok_b200.env import env_small as game
-
 sims = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+if len(sys.argv) > 2 and sys.argv[2] == "15":    # BASELINE config 3's board, one game
+    from alpha_omok_b200.env import env_regular as game
+else:
+    from alpha_omok_b200.env import env_small as game
 for rep in range(3):
     np.random.seed(rep)
     B = game.Return_BoardParams()[0]
