@@ -15,6 +15,8 @@ cases = [("cta_group::1 M128 N32 ", F4 + 8192 + MASKSHIFT, 128, 32, 1),
          ("cta_group::2 M128 N128 (64 rows per CTA)", F4 + 2 + 16384 + MASKSHIFT, 64, 128, 2),
          ("cta_group::2 M256 N64 ", F4 + 2 + 16 + MASKSHIFT, 128, 64, 2),
          ("cta_group::2 M256 N128", F4 + 2 + MASKSHIFT, 128, 128, 2)]
+if len(sys.argv) > 1 and sys.argv[1] == "sw128":   # the same shapes with 128-byte-swizzled K-major operands (timing only)
+    cases = [(n + " SW128", f + 128, r, N, c) for n, f, r, N, c in cases]
 for name, fl, rows, N, cg in cases:
     out = (C.c_ulonglong * 3)()
     for rep in range(2):
