@@ -67,7 +67,7 @@ struct ao_engine {
     ao::TowerWeights tw;
     bool loaded;
     int precision;  // AO_NN_*
-    __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo, *d_conv_quad;
+    __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo, *d_conv_quad, *d_conv_quad_lo;
     float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
   } ws[2];
   std::vector<void*> allocs;
@@ -251,12 +251,19 @@ cudaError_t launch_sum_selfplay(ao_engine* h) {
   return ao::launch_sum_counters(h->tp, h->selfplay_games, h->selfplay_games, h->d_counters, h->stream);
 }
 
+// a few games and a tower mode the cluster-of-four kernel exists for (single pass; split precision on 9x9)
+bool solo_usable(const ao_engine* h, int n) {
+  return h->solo_allowed && n >= 1 && n <= ao::solo_max_games(h->num_sms) && ao::solo_supports(h->B, h->ws[0].precision);
+}
+
 // ---- persistent self-play kernel: state transitions
-// usable: PVNet evaluator, single-pass fp16 tower (tower_stag.cu), plain self-play (no arena), at least a few rounds
+// usable: PVNet evaluator, single-pass fp16 tower (tower_stag.cu; a few games: tower_solo.cu, which also has the split
+// mode), plain self-play (no arena), at least a few rounds
 // and (nearly) all game slots still playing: the persistent kernel evaluates every slot every round (fixed game -> pass
 // map), the two-kernel path packs the live requests densely, which wins once a batch played to the end thins out
 bool persist_usable(const ao_engine* h, int rounds) {
-  return h->persist_allowed && h->cfg.eval_mode == AO_EVAL_PVNET && h->ws[0].precision == AO_NN_FP16 && h->tp.arena_M == 0 &&
+  return h->persist_allowed && h->cfg.eval_mode == AO_EVAL_PVNET &&
+         (h->ws[0].precision == AO_NN_FP16 || solo_usable(h, h->selfplay_games)) && h->tp.arena_M == 0 &&
          h->selfplay_games > 0 && rounds >= 4 &&
          (h->last_running < 0 || h->last_running * 16 >= (long long)h->selfplay_games * 15);
 }
@@ -294,8 +301,8 @@ int leave_persist(ao_engine* h, bool drop) {
 // all rounds of a call in one launch: a few games -> one cluster of four CTAs per game (tower_solo.cu, latency-bound
 // end), otherwise the CTA-pair kernel (tower_stag.cu, PERSIST)
 cudaError_t launch_persist_any(ao_engine* h, int n, int rounds) {
-  if (h->solo_allowed && n <= ao::solo_max_games(h->num_sms))
-    return ao::launch_selfplay_solo(h->ws[0].tw, h->B, h->tp, n, rounds, h->stream);
+  if (solo_usable(h, n))
+    return ao::launch_selfplay_solo(h->ws[0].tw, h->B, h->ws[0].precision, h->tp, n, rounds, h->stream);
   return ao::launch_selfplay_persist(h->ws[0].tw, h->B, h->tp, n, rounds, h->num_sms, h->free_run ? h->d_cta_pos : nullptr, h->stream);
 }
 
@@ -494,7 +501,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
   const int n_layers = 1 + 2 * nb;
   const size_t stem_halves = (size_t)9 * 16 * C, res_halves = (size_t)9 * C * C;
   const size_t total_halves = stem_halves + (size_t)(n_layers - 1) * res_halves;
-  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves), prl(total_halves), qd(total_halves);
+  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves), prl(total_halves), qd(total_halves), qdl(total_halves);
   std::vector<float> bias((size_t)n_layers * C);
   size_t off = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -527,7 +534,9 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
           pr[idx_pair] = vh;
           prl[idx_pair] = lo[idx];
           // cluster-of-four layout (tower_solo.cu): per layer [rank = co / 32][tap][k-chunk][co % 32][8]
-          qd[off + (((size_t)(co / 32) * 9 + t) * (kpad / 8) + ci / 8) * 32 * 8 + (size_t)(co % 32) * 8 + (ci % 8)] = vh;
+          const size_t idx_quad = off + (((size_t)(co / 32) * 9 + t) * (kpad / 8) + ci / 8) * 32 * 8 + (size_t)(co % 32) * 8 + (ci % 8);
+          qd[idx_quad] = vh;
+          qdl[idx_quad] = lo[idx];
         }
     }
     off += l == 0 ? stem_halves : res_halves;
@@ -568,6 +577,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
     EA(W->d_conv_pair, total_halves);
     EA(W->d_conv_pair_lo, total_halves);
     EA(W->d_conv_quad, total_halves);
+    EA(W->d_conv_quad_lo, total_halves);
     EA(W->d_bias, bias.size());
     EA(W->d_head_w, head_w.size());
     EA(W->d_head_b, 4);
@@ -584,6 +594,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
   AO_CUDA(cudaMemcpy(W->d_conv_pair, pr.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_conv_pair_lo, prl.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_conv_quad, qd.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_conv_quad_lo, qdl.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
@@ -596,7 +607,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
 #ifdef AO_PROBE
   tw.xflags = getenv("AO_TOWER_XFLAGS") ? atoi(getenv("AO_TOWER_XFLAGS")) : 0;
 #endif
-  tw.conv_hi = W->d_conv_hi; tw.conv_lo = W->d_conv_lo; tw.conv_pair = W->d_conv_pair; tw.conv_pair_lo = W->d_conv_pair_lo; tw.conv_quad = W->d_conv_quad; tw.bias = W->d_bias; tw.head_w = W->d_head_w; tw.head_b = W->d_head_b;
+  tw.conv_hi = W->d_conv_hi; tw.conv_lo = W->d_conv_lo; tw.conv_pair = W->d_conv_pair; tw.conv_pair_lo = W->d_conv_pair_lo; tw.conv_quad = W->d_conv_quad; tw.conv_quad_lo = W->d_conv_quad_lo; tw.bias = W->d_bias; tw.head_w = W->d_head_w; tw.head_b = W->d_head_b;
   tw.pfc_wT = W->d_pfc_wT; tw.pfc_b = W->d_pfc_b; tw.vfc1_wT = W->d_vfc1_wT; tw.vfc1_b = W->d_vfc1_b; tw.vfc2_w = W->d_vfc2_w;
   tw.vfc2_b = v2b[0];
   tw.n_layers = n_layers;
@@ -659,7 +670,7 @@ extern "C" int ao_search(ao_engine* h, const int32_t* game_ids, int n, const int
   const int blind = synth ? 0 : h->cfg.num_mcts;  // at least this many rounds are needed before anyone can finish
   bool identity = true;  // the persistent kernel walks the slots [0, n): usable when the caller's ids are exactly those
   for (int i = 0; i < n && identity; ++i) identity = game_ids[i] == i;
-  if (identity && h->persist_allowed && !synth && h->ws[0].precision == AO_NN_FP16) {
+  if (identity && h->persist_allowed && !synth && (h->ws[0].precision == AO_NN_FP16 || solo_usable(h, n))) {
     // the whole search in one launch of the persistent kernel (tower + fused tree step): a search needs num_mcts (+1)
     // simulations and every round completes at least one per game; finished games simply stop asking
     if ((rc = enter_persist(h, max_iters, n)) != 0) return rc;

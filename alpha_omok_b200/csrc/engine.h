@@ -127,6 +127,7 @@ struct TowerWeights {
   const __half* conv_pair; // hi parts for CTA pairs: per layer and tap [2 cluster ranks][k-chunks][64 co][8]
   const __half* conv_pair_lo;  // low parts in the CTA-pair layout (split mode)
   const __half* conv_quad; // hi parts for clusters of four (tower_solo.cu): per layer [4 ranks][9 taps][k-chunks][32 co][8]
+  const __half* conv_quad_lo;  // low parts in the same layout (split mode)
   const float* bias;       // [1 + 2*n_blocks][128]  BN-folded bias per conv layer
   const float* head_w;     // [3][128] policy c0, policy c1, value conv (BN scale folded)
   const float* head_b;     // [3]
@@ -182,7 +183,9 @@ cudaError_t launch_tower_stag(const TowerWeights& w, int B, const LeafIn* in, co
                               float* policy, float* value, int num_sms, cudaStream_t s);
 cudaError_t launch_selfplay_persist(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds,
                                     int num_sms, uint32_t* cta_pos, cudaStream_t s);
-cudaError_t launch_selfplay_solo(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds, cudaStream_t s);
+cudaError_t launch_selfplay_solo(const TowerWeights& w, int B, int precision, const TreeParams& p, int n_games, int rounds,
+                                 cudaStream_t s);
+bool solo_supports(int B, int precision);
 int solo_max_games(int num_sms);
 cudaError_t tower_configure(int B, int precision);
 cudaError_t launch_pack_states(const float* states_dev, int n, int B, int inplanes, LeafIn* out, int* bad_flag_dev,

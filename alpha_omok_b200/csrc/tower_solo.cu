@@ -45,16 +45,18 @@ constexpr int kSoloGroupTaps = 3;
 constexpr int kSoloGroupBytes = kSoloGroupTaps * kSoloTapBytes;
 constexpr int kSoloParts = 2 * kSoloNC;            // partial head sums per position: (CTA, column half)
 
-template <int B>
+template <int B, bool X3>
 struct SoloGeo {
   static constexpr int A = B * B;
   static constexpr int NT = (A + kTileRows - 1) / kTileRows;       // 128-row tiles of the one board
   static constexpr int Halo = ((B + 1 + 7) / 8) * 8;
   static constexpr int Rows = Halo + NT * kTileRows + Halo;
-  static constexpr int ActBytes = 16 * Rows * 16;
+  static constexpr int ActBytes = 16 * Rows * 16;                   // one operand buffer (X3: a hi and a lo one)
+  static constexpr int ActTotal = (X3 ? 2 : 1) * ActBytes;
   static constexpr int TileCols = kSoloN * (1 + kSoloIssuers);      // S (fp32 block input / issuer 0 on even layers), A0..A3
   static constexpr int TmemCols = NT * TileCols <= 256 ? 256 : 512;
-  static constexpr int RingGroups = B <= 9 ? 5 : 4;                 // 24 KB each
+  static constexpr int RingGroups = (B <= 9 && !X3) ? 5 : 4;        // 24 KB each
+  static constexpr int GroupsPerLayer = X3 ? 9 : 3;                 // X3: lo/hi pairs of the three tap groups, then hi again
   static constexpr int APad = (A + 7) / 8 * 8;
   // heads: every CTA computes a quarter of the policy FC outputs and of the value FC1 hidden units
   static constexpr bool FcSmem = B <= 9;                            // its slices of the FC weights live in shared memory
@@ -63,19 +65,20 @@ struct SoloGeo {
   static constexpr int KLP = (2 * A + KSP - 1) / KSP;
   static constexpr int VS = 256 / kSoloN;                           // K splits of the value FC1 (32 hidden units per CTA)
   static constexpr int KLV = (A + VS - 1) / VS;
-  static constexpr uint32_t ActTx = (uint32_t)A * 2u * 2u * 16u;    // bytes one CTA's epilogue delivers per layer and destination
+  static constexpr uint32_t ActTx = (uint32_t)A * 2u * 2u * 16u * (X3 ? 2u : 1u);  // bytes one CTA's epilogue delivers per layer and destination
   static constexpr uint32_t FeatTx = (uint32_t)A * kSoloParts * 3u * 4u;
   static constexpr uint32_t FcTx = (uint32_t)(A + kC) * 4u;
   static_assert(NT * TileCols <= 512, "TMEM");
   static_assert(NT <= 2, "board too large");
+  static_assert(!X3 || NT == 1, "the split-precision variant holds two operand buffers: 9x9 only");
   static_assert(KSP >= 1 && KSP * OQ <= 256, "policy FC thread map");
 };
 
-template <int B>
+template <int B, bool X3>
 struct SoloSmem {
-  using G = SoloGeo<B>;
+  using G = SoloGeo<B, X3>;
   static constexpr int act = 0;
-  static constexpr int wring = G::ActBytes;
+  static constexpr int wring = G::ActTotal;
   static constexpr int bias = wring + G::RingGroups * kSoloGroupBytes;      // [kMaxLayers][32] f32 (this CTA's channels)
   static constexpr int headw = bias + kMaxLayers * kSoloN * 4;              // [3][32] f32
   static constexpr int fcb = headw + 3 * kSoloN * 4;                        // pfc_b slice [OQ] | vfc1_b [32] | vfc2_w [32] | head_b [4]
@@ -148,11 +151,15 @@ __device__ __forceinline__ void solo_epi_sync() { asm volatile("bar.sync 1, 256;
 // One cluster of four CTAs per game slot [0, n_games): `rounds` simulations (network evaluation of the pending request
 // + tree step) in one launch.  Needs P.static_slots (request of game g in P.nn_in[g]) and every running game waiting
 // for its answer, exactly like the persistent kernel of tower_stag.cu.
-template <int B>
+// X3 = the hi/lo split-precision mode of tower.cu (trained nets): activations and weights as fp16 hi + lo parts, every
+// k-step a_hi*w_lo + a_lo*w_hi (all of a layer's lo terms first, while the accumulator is small: tcgen05 truncates
+// its fp32 accumulation) and then a_hi*w_hi; every layer starts from fresh accumulators, S only stashes the fp32 block
+// input and the residual add is a round-to-nearest add in the epilogue.
+template <int B, bool X3>
 __global__ void __cluster_dims__(kSoloNC, 1, 1) __launch_bounds__(kSoloThreads, 1)
 tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
-  using G = SoloGeo<B>;
-  using SL = SoloSmem<B>;
+  using G = SoloGeo<B, X3>;
+  using SL = SoloSmem<B, X3>;
   constexpr int RG = G::RingGroups;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_act = smem + SL::act;
@@ -187,7 +194,7 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
   const LeafIn* __restrict__ req = P.nn_in + game;
 
   // ---------------- one-time setup
-  for (int i = tid; i < G::ActBytes / 16; i += kSoloThreads) reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < G::ActTotal / 16; i += kSoloThreads) reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < n_layers * kSoloN; i += kSoloThreads)
     s_bias[i] = W.bias[(i / kSoloN) * kC + (int)rank * kSoloN + i % kSoloN];
   for (int i = tid; i < 3 * kSoloN; i += kSoloThreads) s_headw[i] = W.head_w[(i / kSoloN) * kC + (int)rank * kSoloN + i % kSoloN];
@@ -246,12 +253,17 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         size_t off = 0;
         for (int l = 0; l < n_layers; ++l) {
           const uint32_t tapb = l == 0 ? (uint32_t)kSoloStemTapBytes : (uint32_t)kSoloTapBytes;
-          const uint8_t* base = reinterpret_cast<const uint8_t*>(W.conv_quad) + off + (size_t)rank * 9u * tapb;
-          for (int g = 0; g < 3; ++g, ++gc) {
+          const size_t mine = off + (size_t)rank * 9u * tapb;
+          const uint8_t* base_hi = reinterpret_cast<const uint8_t*>(W.conv_quad) + mine;
+          const uint8_t* base_lo = X3 ? reinterpret_cast<const uint8_t*>(W.conv_quad_lo) + mine : base_hi;
+          for (int u = 0; u < G::GroupsPerLayer; ++u, ++gc) {
+            // X3: groups 0..5 = (w_lo, w_hi) of tap groups 0..2 for the lo terms, 6..8 = w_hi of tap groups 0..2 again
+            const int g = !X3 ? u : (u < 6 ? u >> 1 : u - 6);
+            const uint8_t* src = (X3 && u < 6 && (u & 1) == 0) ? base_lo : base_hi;
             const uint32_t slot = gc % (uint32_t)RG, ph = (gc / (uint32_t)RG) & 1u;
             mbar_wait(&bar_empty[slot], ph ^ 1u);
             mbar_arrive_expect_tx(&bar_full[slot], kSoloGroupTaps * tapb);
-            bulk_g2s(s_w + slot * kSoloGroupBytes, base + (size_t)g * kSoloGroupTaps * tapb, kSoloGroupTaps * tapb, &bar_full[slot]);
+            bulk_g2s(s_w + slot * kSoloGroupBytes, src + (size_t)g * kSoloGroupTaps * tapb, kSoloGroupTaps * tapb, &bar_full[slot]);
           }
           off += (size_t)kSoloNC * 9u * tapb;
         }
@@ -267,10 +279,11 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
     constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;
     constexpr uint32_t kBStep = (2u * (uint32_t)kSoloN * 16u) >> 4;
     uint32_t lc = 0, gc = 0, act_ph = 0;
+    constexpr uint32_t kALoOff = (uint32_t)G::ActBytes >> 4;   // X3: the lo operand buffer sits above the hi one
     if (lane == 0) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the first delivery of CTA i's channels
     for (int rd = 0; rd < rounds; ++rd)
       for (int l = 0; l < n_layers; ++l, ++lc) {
-        const bool to_s = (l & 1) == 0;       // stem and conv2: issuer 0 accumulates in S (conv2: onto the block input x)
+        const bool to_s = !X3 && (l & 1) == 0;  // stem and conv2: issuer 0 accumulates in S (conv2: onto the block input x)
         const bool residual = to_s && l > 0;
         const int nk = l == 0 ? 1 : kC / 16;
         const uint32_t tapb = l == 0 ? (uint32_t)kSoloStemTapBytes : (uint32_t)kSoloTapBytes;
@@ -291,37 +304,41 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           *reinterpret_cast<volatile long long*>(s_tmem + 2) = t;
         })
         const uint32_t acc_col = i == 0 ? (to_s ? 0u : (uint32_t)kSoloN) : (uint32_t)(kSoloN * (1 + i));
-        for (int g = 0; g < 3; ++g, ++gc) {
+        for (int u = 0; u < G::GroupsPerLayer; ++u, ++gc) {
+          const int g = !X3 ? u : (u < 6 ? u >> 1 : u - 6);          // tap group of this weight group
+          const bool a_is_lo = X3 && u < 6 && (u & 1) == 1;          // a_lo * w_hi; otherwise a_hi * (w_lo | w_hi)
           const uint32_t slot = gc % (uint32_t)RG, ph = (gc / (uint32_t)RG) & 1u;
           mbar_wait(&bar_full[slot], ph);
           tc_fence_after_sync();
           if (elect_one()) {
+            if (!(a_is_lo && l == 0)) {  // stem: the input planes are exact in fp16, a_lo == 0
 #pragma unroll
-            for (int tile = 0; tile < G::NT; ++tile) {
+              for (int tile = 0; tile < G::NT; ++tile) {
 #pragma unroll
-              for (int tt = 0; tt < kSoloGroupTaps; ++tt) {
-                const int st = g * kSoloGroupTaps + tt;
-                const int t = st == 0 ? 4 : (st <= 4 ? st - 1 : st);  // packed order: centre, 4 negative, 4 positive shifts
-                const int shift = (t / 3 - 1) * B + (t % 3 - 1);
-                const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
-                const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
-                const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + slot * kSoloGroupBytes + (uint32_t)tt * tapb), (uint32_t)kSoloN * 16u);
-                const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);
-                const uint32_t d_tmem = tmem + (uint32_t)(tile * G::TileCols) + acc_col;
+                for (int tt = 0; tt < kSoloGroupTaps; ++tt) {
+                  const int st = g * kSoloGroupTaps + tt;
+                  const int t = st == 0 ? 4 : (st <= 4 ? st - 1 : st);  // packed order: centre, 4 negative, 4 positive shifts
+                  const int shift = (t / 3 - 1) * B + (t % 3 - 1);
+                  const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
+                  const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
+                  const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + slot * kSoloGroupBytes + (uint32_t)tt * tapb), (uint32_t)kSoloN * 16u);
+                  const uint32_t a_lo = a_lo0 + (a_is_lo ? kALoOff : 0u) + (uint32_t)(G::Halo + tile * kTileRows + shift);
+                  const uint32_t d_tmem = tmem + (uint32_t)(tile * G::TileCols) + acc_col;
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                  const int j = 2 * i + kk;
-                  if (j < nk) {
-                    // an accumulator's first MMA of a layer is (centre tap, its first k-step): it writes every row
-                    const uint32_t acc = (st == 0 && kk == 0) ? ((i == 0 && residual) ? 1u : 0u) : 1u;
-                    umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc,
-                                            acc, m0, m1, m2, m3);
+                  for (int kk = 0; kk < 2; ++kk) {
+                    const int j = 2 * i + kk;
+                    if (j < nk) {
+                      // an accumulator's first MMA of a layer is (first group, centre tap, its first k-step): it writes every row
+                      const uint32_t acc = (u == 0 && st == 0 && kk == 0) ? ((i == 0 && residual) ? 1u : 0u) : 1u;
+                      umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc,
+                                              acc, m0, m1, m2, m3);
+                    }
                   }
                 }
               }
             }
             umma_commit(&bar_empty[slot]);
-            if (g == 2) umma_commit_multicast(bar_acc, (uint16_t)((1u << kSoloNC) - 1u));
+            if (u == G::GroupsPerLayer - 1) umma_commit_multicast(bar_acc, (uint16_t)((1u << kSoloNC) - 1u));
           }
           __syncwarp();
         }
@@ -371,13 +388,18 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           const uint32_t ro = (uint32_t)(G::Halo + R_in) * 16u;
           *reinterpret_cast<uint4*>(s_act + ro) = c0;
           *reinterpret_cast<uint4*>(s_act + chunk_stride + ro) = make_uint4(0, 0, 0, 0);
+          if (X3) {  // {0,1} planes are exact in fp16: their low parts are zero
+            *reinterpret_cast<uint4*>(s_act + G::ActBytes + ro) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(s_act + G::ActBytes + chunk_stride + ro) = make_uint4(0, 0, 0, 0);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_in);  // release at CTA scope; the issuers fence the proxies after their wait
       }
 
       for (int l = 0; l < n_layers; ++l, ++lc) {
-        const bool to_s = (l & 1) == 0;
+        const bool stash = (l & 1) == 0;            // stem and conv2 outputs are the next block's fp32 input x
+        const bool to_s = !X3 && stash;             // single-pass mode: issuer 0 accumulated in S (onto x for conv2)
         const bool last = l == n_layers - 1;
         const float* bias = s_bias + l * kSoloN + half * 16;
         AO_DBG(const long long dbg_a0 = dbg_on ? clock64() : 0;)
@@ -393,18 +415,20 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           const int R = t * kTileRows + r;
           const bool valid = R < G::A;
           const uint32_t col0 = lane_base + (uint32_t)(t * G::TileCols + half * 16);
-          uint32_t v0[16], v1[16], v2[16], v3[16];
+          uint32_t v0[16], v1[16], v2[16], v3[16], xr[16];
           tmem_ld16(col0 + (to_s ? 0u : (uint32_t)kSoloN), v0);
           if (l > 0) {  // the stem has a single k-step: issuer 0's accumulator is the whole sum
             tmem_ld16(col0 + 2u * kSoloN, v1);
             tmem_ld16(col0 + 3u * kSoloN, v2);
             tmem_ld16(col0 + 4u * kSoloN, v3);
+            if (X3 && stash) tmem_ld16(col0, xr);  // split mode: out = conv2 + x as a round-to-nearest fp32 add (model.py:29)
           }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float s = __uint_as_float(v0[j]);
             if (l > 0) s = ((s + __uint_as_float(v1[j])) + __uint_as_float(v2[j])) + __uint_as_float(v3[j]);
+            if (X3 && stash && l > 0) s += __uint_as_float(xr[j]);
             v0[j] = __float_as_uint(fmaxf(s + bias[j], 0.f));
           }
           if (!last) {
@@ -428,8 +452,26 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
                 st_async_v4(peer_act[c] + off0, pk[0], peer_bar_act[c]);
                 st_async_v4(peer_act[c] + off0 + chunk_stride, pk[1], peer_bar_act[c]);
               }
+              if (X3) {  // low parts: fp16(y - fp16(y)), into the lo operand buffers
+                uint4 pl[2];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                  const __half2* hh = reinterpret_cast<const __half2*>(&pk[cc]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(hh[e]);
+                    const __half2 l2 = __floats2half2_rn(__uint_as_float(v0[cc * 8 + 2 * e]) - f.x, __uint_as_float(v0[cc * 8 + 2 * e + 1]) - f.y);
+                    reinterpret_cast<uint32_t*>(&pl[cc])[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                  }
+                }
+#pragma unroll
+                for (int c = 0; c < kSoloNC; ++c) {
+                  st_async_v4(peer_act[c] + (uint32_t)G::ActBytes + off0, pl[0], peer_bar_act[c]);
+                  st_async_v4(peer_act[c] + (uint32_t)G::ActBytes + off0 + chunk_stride, pl[1], peer_bar_act[c]);
+                }
+              }
             }
-            if (to_s) tmem_st16(col0, v0);  // fp32 block input for the next residual add
+            if (stash) tmem_st16(col0, v0);  // fp32 block input for the next residual add
           } else {
             // heads' 1x1 convolutions (model.py:44-46, 64-66) over this thread's 16 channels -> slot (CTA, half) of every
             // CTA's partial-sum table (fixed slots: the order of the float adds does not depend on arrival order)
@@ -454,7 +496,7 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           }
         }
         // the issuers may overwrite the accumulators with the next layer (and issuer 0 finds the new block input in S)
-        if (!last && to_s) tmem_st_wait();
+        if (!last && stash) tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tfree);
@@ -575,17 +617,17 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
   if (warp == kSoloEpiWarps) tmem_dealloc<G::TmemCols>(tmem);
 }
 
-template <int B>
+template <int B, bool X3>
 cudaError_t launch_solo_t(const TowerWeights& w, const TreeParams& p, int n_games, int rounds, cudaStream_t s) {
-  using SL = SoloSmem<B>;
+  using SL = SoloSmem<B, X3>;
   static_assert(SL::total <= 232448, "solo tower kernel exceeds 227 KB of shared memory");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tower_solo_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
+    cudaError_t e = cudaFuncSetAttribute(tower_solo_kernel<B, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::total);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  tower_solo_kernel<B><<<dim3((unsigned)(n_games * kSoloNC)), dim3(kSoloThreads), SL::total, s>>>(w, p, rounds);
+  tower_solo_kernel<B, X3><<<dim3((unsigned)(n_games * kSoloNC)), dim3(kSoloThreads), SL::total, s>>>(w, p, rounds);
   return cudaGetLastError();
 }
 
@@ -597,13 +639,25 @@ int solo_max_games(int num_sms) {
   return g < 1 ? 1 : g;
 }
 
+// Does the cluster-of-four kernel exist for this board and tower mode?  (split precision: 9x9 only - two operand buffers)
+bool solo_supports(int B, int precision) {
+  if (precision == AO_NN_FP16) return B == 9 || B == 15;
+  if (precision == AO_NN_FP16X3) return B == 9;
+  return false;
+}
+
 // `rounds` simulations for each of the game slots [0, n_games) in one launch; needs p.static_slots = 1 and every running
-// game in ST_WAIT_NN with its request in p.nn_in[game] (engine.cu enter_persist), w.conv_quad loaded.
-cudaError_t launch_selfplay_solo(const TowerWeights& w, int B, const TreeParams& p, int n_games, int rounds, cudaStream_t s) {
+// game in ST_WAIT_NN with its request in p.nn_in[game] (engine.cu enter_persist), w.conv_quad (+ conv_quad_lo) loaded.
+cudaError_t launch_selfplay_solo(const TowerWeights& w, int B, int precision, const TreeParams& p, int n_games, int rounds,
+                                 cudaStream_t s) {
   if (w.n_layers > kMaxLayers || !p.static_slots || w.conv_quad == nullptr || n_games < 1 || rounds < 1) return cudaErrorInvalidValue;
-  if (B == 9) return launch_solo_t<9>(w, p, n_games, rounds, s);
-  if (B == 15) return launch_solo_t<15>(w, p, n_games, rounds, s);
-  return cudaErrorInvalidValue;
+  if (!solo_supports(B, precision)) return cudaErrorInvalidValue;
+  if (precision == AO_NN_FP16X3) {
+    if (w.conv_quad_lo == nullptr) return cudaErrorInvalidValue;
+    return launch_solo_t<9, true>(w, p, n_games, rounds, s);
+  }
+  if (B == 9) return launch_solo_t<9, false>(w, p, n_games, rounds, s);
+  return launch_solo_t<15, false>(w, p, n_games, rounds, s);
 }
 
 }  // namespace ao
