@@ -67,7 +67,7 @@ struct ao_engine {
     ao::TowerWeights tw;
     bool loaded;
     int precision;  // AO_NN_*
-    __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo, *d_conv_quad, *d_conv_quad_lo;
+    __half *d_conv_hi, *d_conv_lo, *d_conv_pair, *d_conv_pair_lo, *d_conv_quad, *d_conv_quad_x3;
     float *d_bias, *d_head_w, *d_head_b, *d_pfc_wT, *d_pfc_b, *d_vfc1_wT, *d_vfc1_b, *d_vfc2_w;
   } ws[2];
   std::vector<void*> allocs;
@@ -501,7 +501,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
   const int n_layers = 1 + 2 * nb;
   const size_t stem_halves = (size_t)9 * 16 * C, res_halves = (size_t)9 * C * C;
   const size_t total_halves = stem_halves + (size_t)(n_layers - 1) * res_halves;
-  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves), prl(total_halves), qd(total_halves), qdl(total_halves);
+  std::vector<__half> hi(total_halves), lo(total_halves), pr(total_halves), prl(total_halves), qd(total_halves), qx(2 * total_halves);
   std::vector<float> bias((size_t)n_layers * C);
   size_t off = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -536,7 +536,10 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
           // cluster-of-four layout (tower_solo.cu): per layer [rank = co / 32][tap][k-chunk][co % 32][8]
           const size_t idx_quad = off + (((size_t)(co / 32) * 9 + t) * (kpad / 8) + ci / 8) * 32 * 8 + (size_t)(co % 32) * 8 + (ci % 8);
           qd[idx_quad] = vh;
-          qdl[idx_quad] = lo[idx];
+          // split mode of the same kernel: a tap's image is [32 rows hi ; 32 rows lo] of this rank's channels
+          const size_t idx_x3 = 2 * off + (((size_t)(co / 32) * 9 + t) * (kpad / 8) + ci / 8) * 64 * 8 + (size_t)(co % 32) * 8 + (ci % 8);
+          qx[idx_x3] = vh;
+          qx[idx_x3 + 32 * 8] = lo[idx];
         }
     }
     off += l == 0 ? stem_halves : res_halves;
@@ -577,7 +580,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
     EA(W->d_conv_pair, total_halves);
     EA(W->d_conv_pair_lo, total_halves);
     EA(W->d_conv_quad, total_halves);
-    EA(W->d_conv_quad_lo, total_halves);
+    EA(W->d_conv_quad_x3, 2 * total_halves);
     EA(W->d_bias, bias.size());
     EA(W->d_head_w, head_w.size());
     EA(W->d_head_b, 4);
@@ -594,7 +597,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
   AO_CUDA(cudaMemcpy(W->d_conv_pair, pr.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_conv_pair_lo, prl.data(), total_halves * 2, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_conv_quad, qd.data(), total_halves * 2, cudaMemcpyHostToDevice));
-  AO_CUDA(cudaMemcpy(W->d_conv_quad_lo, qdl.data(), total_halves * 2, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMemcpy(W->d_conv_quad_x3, qx.data(), total_halves * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_head_w, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMemcpy(W->d_head_b, head_b.data(), 3 * 4, cudaMemcpyHostToDevice));
@@ -607,7 +610,7 @@ extern "C" int ao_load_weights_set(ao_engine* h, int set, int n_tensors, const c
 #ifdef AO_PROBE
   tw.xflags = getenv("AO_TOWER_XFLAGS") ? atoi(getenv("AO_TOWER_XFLAGS")) : 0;
 #endif
-  tw.conv_hi = W->d_conv_hi; tw.conv_lo = W->d_conv_lo; tw.conv_pair = W->d_conv_pair; tw.conv_pair_lo = W->d_conv_pair_lo; tw.conv_quad = W->d_conv_quad; tw.conv_quad_lo = W->d_conv_quad_lo; tw.bias = W->d_bias; tw.head_w = W->d_head_w; tw.head_b = W->d_head_b;
+  tw.conv_hi = W->d_conv_hi; tw.conv_lo = W->d_conv_lo; tw.conv_pair = W->d_conv_pair; tw.conv_pair_lo = W->d_conv_pair_lo; tw.conv_quad = W->d_conv_quad; tw.conv_quad_x3 = W->d_conv_quad_x3; tw.bias = W->d_bias; tw.head_w = W->d_head_w; tw.head_b = W->d_head_b;
   tw.pfc_wT = W->d_pfc_wT; tw.pfc_b = W->d_pfc_b; tw.vfc1_wT = W->d_vfc1_wT; tw.vfc1_b = W->d_vfc1_b; tw.vfc2_w = W->d_vfc2_w;
   tw.vfc2_b = v2b[0];
   tw.n_layers = n_layers;

@@ -127,7 +127,7 @@ struct TowerWeights {
   const __half* conv_pair; // hi parts for CTA pairs: per layer and tap [2 cluster ranks][k-chunks][64 co][8]
   const __half* conv_pair_lo;  // low parts in the CTA-pair layout (split mode)
   const __half* conv_quad; // hi parts for clusters of four (tower_solo.cu): per layer [4 ranks][9 taps][k-chunks][32 co][8]
-  const __half* conv_quad_lo;  // low parts in the same layout (split mode)
+  const __half* conv_quad_x3;  // split mode: per layer [4 ranks][9 taps][k-chunks][32 co hi ; 32 co lo][8] (twice the size)
   const float* bias;       // [1 + 2*n_blocks][128]  BN-folded bias per conv layer
   const float* head_w;     // [3][128] policy c0, policy c1, value conv (BN scale folded)
   const float* head_b;     // [3]

@@ -39,10 +39,7 @@ constexpr int kSoloN = kC / kSoloNC;               // output channels per CTA
 constexpr int kSoloIssuers = 4;                    // MMA-issuing warps per CTA = K groups of 32 input channels
 constexpr int kSoloEpiWarps = 8;
 constexpr int kSoloThreads = (kSoloEpiWarps + kSoloIssuers + 1) * 32;  // + weight producer
-constexpr int kSoloTapBytes = (kC / 8) * kSoloN * 16;   // [16 k-chunks][32 co][8 halves] = 8 KB
-constexpr int kSoloStemTapBytes = 2 * kSoloN * 16;      // stem: K = 16
 constexpr int kSoloGroupTaps = 3;
-constexpr int kSoloGroupBytes = kSoloGroupTaps * kSoloTapBytes;
 constexpr int kSoloParts = 2 * kSoloNC;            // partial head sums per position: (CTA, column half)
 
 template <int B, bool X3>
@@ -53,10 +50,15 @@ struct SoloGeo {
   static constexpr int Rows = Halo + NT * kTileRows + Halo;
   static constexpr int ActBytes = 16 * Rows * 16;                   // one operand buffer (X3: a hi and a lo one)
   static constexpr int ActTotal = (X3 ? 2 : 1) * ActBytes;
-  static constexpr int TileCols = kSoloN * (1 + kSoloIssuers);      // S (fp32 block input / issuer 0 on even layers), A0..A3
+  // TMEM columns per tile: S (fp32 block input; single pass: issuer 0's accumulator on even layers), then one block per
+  // issuer: A_i (32 columns); X3: [hi | lo] (64 columns: a_hi*w_hi, and a_hi*w_lo + a_lo*w_hi)
+  static constexpr int AccCols = X3 ? 2 * kSoloN : kSoloN;
+  static constexpr int TileCols = kSoloN + kSoloIssuers * AccCols;
   static constexpr int TmemCols = NT * TileCols <= 256 ? 256 : 512;
-  static constexpr int RingGroups = (B <= 9 && !X3) ? 5 : 4;        // 24 KB each
-  static constexpr int GroupsPerLayer = X3 ? 9 : 3;                 // X3: lo/hi pairs of the three tap groups, then hi again
+  static constexpr int BRows = X3 ? 2 * kSoloN : kSoloN;            // rows of a tap's B image: X3 = [32 x w_hi ; 32 x w_lo]
+  static constexpr int TapBytes = (kC / 8) * BRows * 16, StemTapBytes = 2 * BRows * 16;
+  static constexpr int GroupBytes = kSoloGroupTaps * TapBytes;      // 24 KB (X3: 48 KB)
+  static constexpr int RingGroups = X3 ? 2 : (B <= 9 ? 5 : 4);
   static constexpr int APad = (A + 7) / 8 * 8;
   // heads: every CTA computes a quarter of the policy FC outputs and of the value FC1 hidden units
   static constexpr bool FcSmem = B <= 9;                            // its slices of the FC weights live in shared memory
@@ -79,7 +81,7 @@ struct SoloSmem {
   using G = SoloGeo<B, X3>;
   static constexpr int act = 0;
   static constexpr int wring = G::ActTotal;
-  static constexpr int bias = wring + G::RingGroups * kSoloGroupBytes;      // [kMaxLayers][32] f32 (this CTA's channels)
+  static constexpr int bias = wring + G::RingGroups * G::GroupBytes;        // [kMaxLayers][32] f32 (this CTA's channels)
   static constexpr int headw = bias + kMaxLayers * kSoloN * 4;              // [3][32] f32
   static constexpr int fcb = headw + 3 * kSoloN * 4;                        // pfc_b slice [OQ] | vfc1_b [32] | vfc2_w [32] | head_b [4]
   static constexpr int pfcw = fcb + (G::OQ + 2 * kSoloN + 4) * 4;           // FcSmem: [2A][OQ] f32
@@ -151,10 +153,14 @@ __device__ __forceinline__ void solo_epi_sync() { asm volatile("bar.sync 1, 256;
 // One cluster of four CTAs per game slot [0, n_games): `rounds` simulations (network evaluation of the pending request
 // + tree step) in one launch.  Needs P.static_slots (request of game g in P.nn_in[g]) and every running game waiting
 // for its answer, exactly like the persistent kernel of tower_stag.cu.
-// X3 = the hi/lo split-precision mode of tower.cu (trained nets): activations and weights as fp16 hi + lo parts, every
-// k-step a_hi*w_lo + a_lo*w_hi (all of a layer's lo terms first, while the accumulator is small: tcgen05 truncates
-// its fp32 accumulation) and then a_hi*w_hi; every layer starts from fresh accumulators, S only stashes the fp32 block
-// input and the residual add is a round-to-nearest add in the epilogue.
+// X3 = the hi/lo split-precision mode (trained nets, cf. tower.cu): activations and weights as fp16 hi + lo parts, every
+// k-step a_hi*w_hi + a_hi*w_lo + a_lo*w_hi.  The MMAs are bound by operand fetch, and the first two terms share their A
+// tile: a tap's B image is [32 rows w_hi ; 32 rows w_lo] (TowerWeights.conv_quad_x3), so ONE N = 64 instruction computes
+// a_hi*w_hi into the hi columns and a_hi*w_lo into the lo columns of the issuer's accumulator block (A fetched once),
+// and a second N = 32 instruction adds a_lo*w_hi (the first 32 rows of the same image) onto the lo columns: 144 instead
+// of 216 MMAs per layer, 10 KB instead of 15 KB of operands per k-step.  The small lo terms have columns of their own, so
+// tcgen05's truncating fp32 accumulation never adds them to a large accumulator (tower.cu orders them first instead);
+// hi + lo, the four issuers' partial sums and the residual x (stashed in S) are round-to-nearest adds in the epilogue.
 template <int B, bool X3>
 __global__ void __cluster_dims__(kSoloNC, 1, 1) __launch_bounds__(kSoloThreads, 1)
 tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
@@ -252,18 +258,13 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
       for (int rd = 0; rd < rounds; ++rd) {
         size_t off = 0;
         for (int l = 0; l < n_layers; ++l) {
-          const uint32_t tapb = l == 0 ? (uint32_t)kSoloStemTapBytes : (uint32_t)kSoloTapBytes;
-          const size_t mine = off + (size_t)rank * 9u * tapb;
-          const uint8_t* base_hi = reinterpret_cast<const uint8_t*>(W.conv_quad) + mine;
-          const uint8_t* base_lo = X3 ? reinterpret_cast<const uint8_t*>(W.conv_quad_lo) + mine : base_hi;
-          for (int u = 0; u < G::GroupsPerLayer; ++u, ++gc) {
-            // X3: groups 0..5 = (w_lo, w_hi) of tap groups 0..2 for the lo terms, 6..8 = w_hi of tap groups 0..2 again
-            const int g = !X3 ? u : (u < 6 ? u >> 1 : u - 6);
-            const uint8_t* src = (X3 && u < 6 && (u & 1) == 0) ? base_lo : base_hi;
+          const uint32_t tapb = l == 0 ? (uint32_t)G::StemTapBytes : (uint32_t)G::TapBytes;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(X3 ? W.conv_quad_x3 : W.conv_quad) + off + (size_t)rank * 9u * tapb;
+          for (int g = 0; g < 3; ++g, ++gc) {
             const uint32_t slot = gc % (uint32_t)RG, ph = (gc / (uint32_t)RG) & 1u;
             mbar_wait(&bar_empty[slot], ph ^ 1u);
             mbar_arrive_expect_tx(&bar_full[slot], kSoloGroupTaps * tapb);
-            bulk_g2s(s_w + slot * kSoloGroupBytes, src + (size_t)g * kSoloGroupTaps * tapb, kSoloGroupTaps * tapb, &bar_full[slot]);
+            bulk_g2s(s_w + slot * G::GroupBytes, base + (size_t)g * kSoloGroupTaps * tapb, kSoloGroupTaps * tapb, &bar_full[slot]);
           }
           off += (size_t)kSoloNC * 9u * tapb;
         }
@@ -272,12 +273,13 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
   } else if (warp >= kSoloEpiWarps) {
     // =========================================================== MMA issuer i: input channels [32 i, 32 i + 32)
     const int i = warp - kSoloEpiWarps;
-    const uint32_t idesc = umma_idesc_f16_f32(kTileRows, kSoloN);
+    const uint32_t idesc = umma_idesc_f16_f32(kTileRows, G::BRows);   // X3: N = 64 = [hi | lo] columns
+    const uint32_t idesc_lo = umma_idesc_f16_f32(kTileRows, kSoloN);  // X3: a_lo * w_hi onto the lo columns
     const uint32_t lbo_a = (uint32_t)G::Rows * 16u;
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_act), lbo_a);
     const uint32_t desc_hi = umma_desc_hi(128u);
     constexpr uint32_t kAStep = (2u * (uint32_t)G::Rows * 16u) >> 4;
-    constexpr uint32_t kBStep = (2u * (uint32_t)kSoloN * 16u) >> 4;
+    constexpr uint32_t kBStep = (2u * (uint32_t)G::BRows * 16u) >> 4;
     uint32_t lc = 0, gc = 0, act_ph = 0;
     constexpr uint32_t kALoOff = (uint32_t)G::ActBytes >> 4;   // X3: the lo operand buffer sits above the hi one
     if (lane == 0) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the first delivery of CTA i's channels
@@ -286,7 +288,7 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         const bool to_s = !X3 && (l & 1) == 0;  // stem and conv2: issuer 0 accumulates in S (conv2: onto the block input x)
         const bool residual = to_s && l > 0;
         const int nk = l == 0 ? 1 : kC / 16;
-        const uint32_t tapb = l == 0 ? (uint32_t)kSoloStemTapBytes : (uint32_t)kSoloTapBytes;
+        const uint32_t tapb = l == 0 ? (uint32_t)G::StemTapBytes : (uint32_t)G::TapBytes;
         mbar_wait(bar_tfree, lc & 1u);
         AO_DBG(const long long dbg_i0 = (W.dbg && blockIdx.x == 0 && i == 0) ? clock64() : 0;)
         if (l == 0) {
@@ -303,42 +305,42 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           atomicAdd(&W.dbg[7], (unsigned long long)(t - dbg_i0));
           *reinterpret_cast<volatile long long*>(s_tmem + 2) = t;
         })
-        const uint32_t acc_col = i == 0 ? (to_s ? 0u : (uint32_t)kSoloN) : (uint32_t)(kSoloN * (1 + i));
-        for (int u = 0; u < G::GroupsPerLayer; ++u, ++gc) {
-          const int g = !X3 ? u : (u < 6 ? u >> 1 : u - 6);          // tap group of this weight group
-          const bool a_is_lo = X3 && u < 6 && (u & 1) == 1;          // a_lo * w_hi; otherwise a_hi * (w_lo | w_hi)
+        const uint32_t acc_col = X3 ? (uint32_t)(kSoloN + i * G::AccCols)
+                                    : (i == 0 ? (to_s ? 0u : (uint32_t)kSoloN) : (uint32_t)(kSoloN * (1 + i)));
+        for (int g = 0; g < 3; ++g, ++gc) {
           const uint32_t slot = gc % (uint32_t)RG, ph = (gc / (uint32_t)RG) & 1u;
           mbar_wait(&bar_full[slot], ph);
           tc_fence_after_sync();
           if (elect_one()) {
-            if (!(a_is_lo && l == 0)) {  // stem: the input planes are exact in fp16, a_lo == 0
 #pragma unroll
-              for (int tile = 0; tile < G::NT; ++tile) {
+            for (int tile = 0; tile < G::NT; ++tile) {
 #pragma unroll
-                for (int tt = 0; tt < kSoloGroupTaps; ++tt) {
-                  const int st = g * kSoloGroupTaps + tt;
-                  const int t = st == 0 ? 4 : (st <= 4 ? st - 1 : st);  // packed order: centre, 4 negative, 4 positive shifts
-                  const int shift = (t / 3 - 1) * B + (t % 3 - 1);
-                  const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
-                  const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
-                  const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + slot * kSoloGroupBytes + (uint32_t)tt * tapb), (uint32_t)kSoloN * 16u);
-                  const uint32_t a_lo = a_lo0 + (a_is_lo ? kALoOff : 0u) + (uint32_t)(G::Halo + tile * kTileRows + shift);
-                  const uint32_t d_tmem = tmem + (uint32_t)(tile * G::TileCols) + acc_col;
+              for (int tt = 0; tt < kSoloGroupTaps; ++tt) {
+                const int st = g * kSoloGroupTaps + tt;
+                const int t = st == 0 ? 4 : (st <= 4 ? st - 1 : st);  // packed order: centre, 4 negative, 4 positive shifts
+                const int shift = (t / 3 - 1) * B + (t % 3 - 1);
+                const uint32_t* mk = s_mask + (tile * 9 + t) * 4;
+                const uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
+                const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_w + slot * G::GroupBytes + (uint32_t)tt * tapb), (uint32_t)G::BRows * 16u);
+                const uint32_t a_lo = a_lo0 + (uint32_t)(G::Halo + tile * kTileRows + shift);
+                const uint32_t d_tmem = tmem + (uint32_t)(tile * G::TileCols) + acc_col;
 #pragma unroll
-                  for (int kk = 0; kk < 2; ++kk) {
-                    const int j = 2 * i + kk;
-                    if (j < nk) {
-                      // an accumulator's first MMA of a layer is (first group, centre tap, its first k-step): it writes every row
-                      const uint32_t acc = (u == 0 && st == 0 && kk == 0) ? ((i == 0 && residual) ? 1u : 0u) : 1u;
-                      umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc,
-                                              acc, m0, m1, m2, m3);
-                    }
+                for (int kk = 0; kk < 2; ++kk) {
+                  const int j = 2 * i + kk;
+                  if (j < nk) {
+                    // an accumulator's first MMA of a layer is (centre tap, its first k-step): it writes every row
+                    const uint32_t acc = (st == 0 && kk == 0) ? ((i == 0 && residual) ? 1u : 0u) : 1u;
+                    umma_f16_ss_lohi_masked(d_tmem, a_lo + (uint32_t)j * kAStep, b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc,
+                                            acc, m0, m1, m2, m3);
+                    if (X3 && l > 0)  // a_lo * w_hi (rows 0..31 of the image) onto the lo columns; stem: a_lo == 0
+                      umma_f16_ss_lohi_masked(d_tmem + (uint32_t)kSoloN, a_lo + kALoOff + (uint32_t)j * kAStep,
+                                              b_lo0 + (uint32_t)j * kBStep, desc_hi, idesc_lo, 1u, m0, m1, m2, m3);
                   }
                 }
               }
             }
             umma_commit(&bar_empty[slot]);
-            if (u == G::GroupsPerLayer - 1) umma_commit_multicast(bar_acc, (uint16_t)((1u << kSoloNC) - 1u));
+            if (g == 2) umma_commit_multicast(bar_acc, (uint16_t)((1u << kSoloNC) - 1u));
           }
           __syncwarp();
         }
@@ -415,22 +417,47 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           const int R = t * kTileRows + r;
           const bool valid = R < G::A;
           const uint32_t col0 = lane_base + (uint32_t)(t * G::TileCols + half * 16);
-          uint32_t v0[16], v1[16], v2[16], v3[16], xr[16];
-          tmem_ld16(col0 + (to_s ? 0u : (uint32_t)kSoloN), v0);
+          uint32_t v0[16], v1[16], v2[16], v3[16];
+          // single pass: issuer 0's accumulator is S (even layers) or A0; X3: the hi columns of the four issuers' blocks
+          const uint32_t blk0 = X3 ? col0 + (uint32_t)kSoloN : col0 + (to_s ? 0u : (uint32_t)kSoloN);
+          const uint32_t blk_step = (uint32_t)G::AccCols;
+          tmem_ld16(blk0, v0);
           if (l > 0) {  // the stem has a single k-step: issuer 0's accumulator is the whole sum
-            tmem_ld16(col0 + 2u * kSoloN, v1);
-            tmem_ld16(col0 + 3u * kSoloN, v2);
-            tmem_ld16(col0 + 4u * kSoloN, v3);
-            if (X3 && stash) tmem_ld16(col0, xr);  // split mode: out = conv2 + x as a round-to-nearest fp32 add (model.py:29)
+            tmem_ld16((X3 ? blk0 : col0 + (uint32_t)kSoloN) + blk_step, v1);
+            tmem_ld16((X3 ? blk0 : col0 + (uint32_t)kSoloN) + 2u * blk_step, v2);
+            tmem_ld16((X3 ? blk0 : col0 + (uint32_t)kSoloN) + 3u * blk_step, v3);
           }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float s = __uint_as_float(v0[j]);
             if (l > 0) s = ((s + __uint_as_float(v1[j])) + __uint_as_float(v2[j])) + __uint_as_float(v3[j]);
-            if (X3 && stash && l > 0) s += __uint_as_float(xr[j]);
-            v0[j] = __float_as_uint(fmaxf(s + bias[j], 0.f));
+            v0[j] = __float_as_uint(s);
           }
+          if (X3) {  // + the lo columns (a_hi*w_lo + a_lo*w_hi) of the four blocks, + the fp32 block input on conv2 layers
+            uint32_t xr[16];
+            tmem_ld16(blk0 + (uint32_t)kSoloN, v1);
+            if (l > 0) {
+              tmem_ld16(blk0 + (uint32_t)kSoloN + blk_step, v2);
+              tmem_ld16(blk0 + (uint32_t)kSoloN + 2u * blk_step, v3);
+              tmem_ld16(blk0 + (uint32_t)kSoloN + 3u * blk_step, xr);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float lo = __uint_as_float(v1[j]);
+              if (l > 0) lo = ((lo + __uint_as_float(v2[j])) + __uint_as_float(v3[j])) + __uint_as_float(xr[j]);
+              v0[j] = __float_as_uint(__uint_as_float(v0[j]) + lo);
+            }
+            if (stash && l > 0) {  // out = conv2 + x as a round-to-nearest fp32 add (model.py:29)
+              tmem_ld16(col0, xr);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v0[j] = __float_as_uint(__uint_as_float(v0[j]) + __uint_as_float(xr[j]));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v0[j] = __float_as_uint(fmaxf(__uint_as_float(v0[j]) + bias[j], 0.f));
           if (!last) {
             uint4 pk[2];
 #pragma unroll
@@ -647,13 +674,13 @@ bool solo_supports(int B, int precision) {
 }
 
 // `rounds` simulations for each of the game slots [0, n_games) in one launch; needs p.static_slots = 1 and every running
-// game in ST_WAIT_NN with its request in p.nn_in[game] (engine.cu enter_persist), w.conv_quad (+ conv_quad_lo) loaded.
+// game in ST_WAIT_NN with its request in p.nn_in[game] (engine.cu enter_persist), w.conv_quad (split mode: conv_quad_x3) loaded.
 cudaError_t launch_selfplay_solo(const TowerWeights& w, int B, int precision, const TreeParams& p, int n_games, int rounds,
                                  cudaStream_t s) {
   if (w.n_layers > kMaxLayers || !p.static_slots || w.conv_quad == nullptr || n_games < 1 || rounds < 1) return cudaErrorInvalidValue;
   if (!solo_supports(B, precision)) return cudaErrorInvalidValue;
   if (precision == AO_NN_FP16X3) {
-    if (w.conv_quad_lo == nullptr) return cudaErrorInvalidValue;
+    if (w.conv_quad_x3 == nullptr) return cudaErrorInvalidValue;
     return launch_solo_t<9, true>(w, p, n_games, rounds, s);
   }
   if (B == 9) return launch_solo_t<9, false>(w, p, n_games, rounds, s);

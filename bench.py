@@ -320,14 +320,20 @@ def single_game_leg(device):
     from alpha_omok_b200 import agents, model, utils
     from alpha_omok_b200.env import env_small as game
     out = {"workload": "BASELINE config 1: one 9x9 self-play game through ZeroAgent.get_pi (ao_search), random-init PVNet 10x128 (numpy seed 0), "
-                       "noise on, tau 1 for 6 plies; sims/move = 40 (config 1) and 400 (the headline's search size)",
-           "kernel": "tower_solo_kernel<9>: one cluster of four CTAs per game, whole search in one launch", "unit": "simulations/s"}
+                       "noise on, tau 1 for 6 plies; sims/move = 40 (config 1) and 400 (the headline's search size); trained_*: the same "
+                       "with the reference's shipped checkpoint (hi/lo split tower, tower_mode 1)",
+           "kernel": "tower_solo_kernel<9, X3>: one cluster of four CTAs per game, whole search in one launch", "unit": "simulations/s"}
+    nets = {}
     net = model.PVNet(10, 5, 128, 9)
     net.load_state_dict(model.seeded_state_dict(0, 10, 5, 128, 9), strict=False)
-    net.eval()
-    for sims in (40, 400):
+    nets[""] = net.eval()
+    net = model.PVNet(10, 5, 128, 9)    # the reference's shipped checkpoint: the facade picks the hi/lo split tower for it
+    net.load_state_dict(_trained_state_dict(), strict=False)
+    nets["trained_"] = net.eval()
+    for prefix, net in nets.items():
+      for sims in (40, 400):
         best = None
-        for rep in range(3):
+        for rep in range(3 if not prefix else 2):
             np.random.seed(rep)
             agent = agents.ZeroAgent(9, sims, 5, noise=True, engine_kwargs={"device": device})
             agent.model = net
@@ -345,11 +351,13 @@ def single_game_leg(device):
                 _, _, win_index, _, _ = env.step(action)
                 t += 1
             dt = time.perf_counter() - t0
+            mode = agent._engine.nn_precision
             agent._engine.close()
-            r = {"sims_per_s": n_sims / dt, "ms_per_move": 1e3 * dt / t, "us_per_sim": 1e6 * dt / n_sims, "moves": t, "sims": n_sims}
+            r = {"sims_per_s": n_sims / dt, "ms_per_move": 1e3 * dt / t, "us_per_sim": 1e6 * dt / n_sims, "moves": t, "sims": n_sims,
+                 "tower_mode": int(mode)}
             if best is None or r["sims_per_s"] > best["sims_per_s"]:
                 best = r
-        out["sims%d" % sims] = best
+        out["%ssims%d" % (prefix, sims)] = best
     out["value"] = out["sims40"]["sims_per_s"]
     return out
 

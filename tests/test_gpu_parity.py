@@ -630,13 +630,13 @@ def test_persistent_kernel_and_deferred_tails_equal_the_plain_round_loop(cabi, m
 
 
 # ------------------------------------------------------------------------------------------------ cluster-of-four kernel
-def _nn_replay_check(cabi, B, sims, G, seed, n_check=24, rounds=64):
+def _nn_replay_check(cabi, B, sims, G, seed, n_check=24, rounds=64, split=False):
     """self-play of G games through ao_selfplay_rounds with the PVNet evaluator and a noise tape; the oracle replays the
     logged network outputs (bit-exact visits / moves / winners), the logged floats are checked against torch fp32"""
     A = B * B
     sd = pvnet_ref.make_state_dict(3, 10, 5, 128, B)
     eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=G, seed=seed, noise_mode=cabi.AO_NOISE_TAPE,
-                      nn_log_cap=(sims + 1) * (A + 1), nn_precision=cabi.AO_NN_FP16)
+                      nn_log_cap=(sims + 1) * (A + 1), nn_precision=cabi.AO_NN_FP16X3 if split else cabi.AO_NN_FP16)
     eng.load_state_dict(sd)
     tapes = [O.make_gamma_tape(seed, g, A + 2, A, 10 / A) for g in range(G)]
     for g in range(G):
@@ -673,12 +673,14 @@ def _nn_replay_check(cabi, B, sims, G, seed, n_check=24, rounds=64):
     return worst_p, worst_v
 
 
-@pytest.mark.parametrize("B,sims,G", [(9, 24, 1), (9, 12, 33), (15, 6, 2)])
-def test_solo_kernel_nn_replay_parity(cabi, B, sims, G):
+@pytest.mark.parametrize("B,sims,G,split", [(9, 24, 1, False), (9, 12, 33, False), (15, 6, 2, False), (9, 16, 1, True), (9, 8, 33, True)])
+def test_solo_kernel_nn_replay_parity(cabi, B, sims, G, split):
     """tower_solo.cu (one game per cluster of four CTAs; what ZeroAgent.get_pi and small self-play batches run on):
-    one game, the largest batch it takes (33 clusters) and 15x15 (two row tiles per CTA) - searches bit-exact against
-    the oracle on the logged network outputs, the floats within 1e-4 of torch fp32"""
-    worst_p, worst_v = _nn_replay_check(cabi, B, sims, G, seed=31)
+    one game, the largest batch it takes (33 clusters), 15x15 (two row tiles per CTA) and the split-precision variant
+    (one N = 64 MMA for a_hi*[w_hi | w_lo]; the trained checkpoint itself goes through it in
+    test_selfplay_pvnet_nn_replay_parity[trained_split]) - searches bit-exact against the oracle on the logged network
+    outputs, the floats within 1e-4 of torch fp32"""
+    worst_p, worst_v = _nn_replay_check(cabi, B, sims, G, seed=31, split=split)
     assert worst_p < TOL and worst_v < TOL, (worst_p, worst_v)
 
 
