@@ -7,19 +7,25 @@
 //
 //   * CTA r of the cluster owns output channels [32 r, 32 r + 32): tcgen05 cta_group::1, M = 128 (one tile of board
 //     rows; 15x15: two tiles), N = 32, and streams only its quarter of the weights (72 KB per layer, ring of 24 KB groups
-//     of three taps, 1-2 layers deep).  Every CTA holds the full fp16 activations (all 128 input channels) of the game.
+//     of three taps, 4-5 groups deep).  Every CTA holds the full fp16 activations (all 128 input channels) of the game.
 //   * the K dimension is split over FOUR issuing warps with their own fp32 accumulators in TMEM: issuer i takes input
 //     channels [32 i, 32 i + 32) (k-steps 2i, 2i + 1 of every tap) = exactly the channels CTA i of the cluster produces, so
 //     it can start as soon as CTA i's epilogue has delivered them.  18 MMAs per issuer and layer instead of 72 in a row.
 //   * epilogue (8 warps): sum the four accumulators in a fixed order, + bias, ReLU (conv2: the fp32 block input sits in
 //     issuer 0's accumulator, as in the other tower kernels), convert to fp16 and store the CTA's 32 channels into the
-//     activation buffer of ALL FOUR CTAs (st.shared::cluster), then arrive on "channel group r is ready" in each of them.
+//     activation buffer of ALL FOUR CTAs with st.async (DSMEM) that completes bytes on the destination's "channel group r
+//     has landed" barrier: no fence and no arrive on the writer's side, the consumer's barrier counts the bytes.
 //     The buffer is single: before a CTA overwrites rows that the others may still be reading, the layer has to be
 //     accumulated everywhere - every issuer's final tcgen05.commit of a layer is multicast to all four CTAs.
-//   * heads: the 1x1 head convolutions are partial sums over each CTA's channels, written to the leader in fixed slots
-//     (deterministic order of the float adds); the leader's epilogue warps then run the FC layers / softmax / tanh and
-//     warp 0 runs tree_step_game (expand, backup, move, select) for the game and publishes the next request to the
-//     cluster.  All `rounds` simulations of a call are one launch (like tower_stag's PERSIST mode).
+//   * heads: the 1x1 head convolutions are partial sums over each CTA's channels, delivered to every CTA in fixed slots
+//     (deterministic order of the float adds); each CTA computes a quarter of the policy FC outputs / value hidden units
+//     (9x9: from FC weight slices in its shared memory) and sends them to the leader, whose warp 0 does softmax / tanh,
+//     runs tree_step_game (expand, backup, move, select) for the game and publishes the next request to the cluster.
+//     All `rounds` simulations of a call are one launch (like tower_stag's PERSIST mode).
+//   * X3 (9x9): the hi/lo split-precision mode for trained nets, see tower_solo_kernel below.
+//
+// What bounds it: shared-memory operand fetch of the MMAs (tools/probe_mma_small_n.py: 48 cycles per M128 N32 K16 MMA
+// against a 16-cycle math floor - every CTA reads all activation rows of every tap), DESIGN.md 4.0.
 //
 // Results: same arithmetic per MMA, but the fp32 accumulation is grouped differently (4 partial sums per output), so a
 // leaf's floats differ from the batch kernels' in the last bits - both are within the 1e-4 contract of model.PVNet
