@@ -808,6 +808,7 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
     int depth = 0;
     int win = 0;
     bool need_eval = true;
+    int walk_a1 = -1, walk_a2 = -1;  // actions of the last two levels of the walk (= slot_act[path[depth-1]], [depth-2])
     if (g.root_n > 0u) {
       int32_t node = g.root_node;
       if (node <= -2) {
@@ -885,6 +886,8 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
         }
         if (lane == 0) path()[depth] = (uint32_t)(base + s_idx);
         ++depth;
+        walk_a2 = walk_a1;
+        walk_a1 = (int)s_act;
         const int y = (int)s_act / P.B, x = (int)s_act % P.B;
         if (lane == y) {
           if ((nm & 1) == 0) rb |= 1u << x;
@@ -947,10 +950,10 @@ __device__ __forceinline__ bool tree_step_game(const TreeParams& P, int game0, W
       }
       // last two actions on the path to the leaf (or of the root position)
       int l1 = g.last1, l2 = g.last2;
-      if (depth >= 1) {
+      if (depth >= 1) {  // the walk above selected them: no need to chase path[] -> slot_act[] through memory again
         l2 = l1;
-        l1 = P.slot_act[path()[depth - 1]];
-        if (depth >= 2) l2 = P.slot_act[path()[depth - 2]];
+        l1 = walk_a1;
+        if (depth >= 2) l2 = walk_a2;
       }
       const bool black_to_move = (nm & 1) == 0;
       uint32_t own = black_to_move ? rb : rw, opp = black_to_move ? rw : rb;
