@@ -709,3 +709,47 @@ def test_solo_kernel_is_the_one_that_runs_and_agrees_with_the_pair_kernel(cabi, 
         assert len(v0) > 0 and len(v1) > 0
         # the first evaluation of every search is the root position itself in both runs
         assert np.abs(p0[0] - p1[0]).max() < 2e-5 and abs(float(v0[0]) - float(v1[0])) < 2e-5
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_solo_kernel_facade_tree_reuse_and_unvisited_replies_nn_replay(cabi, split):
+    """ao_search on ONE game with the real tower (cluster-of-four kernel, single-pass and split mode): a sequence of
+    searches like ZeroAgent.get_pi sees them in a match - real root, reused roots after visited replies, replies onto
+    cells the search never looked at (reused root with n == 0, agents.py:93-111), root noise re-mixed every time.  The
+    oracle agent replays the logged network outputs in order: visits, priors and is_real_root identical at every ply."""
+    B, A, sims, seed = 9, 81, 48, 17
+    sd = pvnet_ref.make_state_dict(7, 10, 5, 128, B)
+    n_ply = 10
+    eng = cabi.Engine(board_size=B, num_mcts=sims, max_games=1, noise=True, seed=seed, noise_mode=cabi.AO_NOISE_TAPE,
+                      nn_log_cap=n_ply * (sims + 2), nn_precision=cabi.AO_NN_FP16X3 if split else cabi.AO_NN_FP16)
+    eng.load_state_dict(sd)
+    tape = O.make_gamma_tape(seed, 0, n_ply + 2, A, 10 / A)
+    eng.set_gamma_tape(0, tape)
+    eng.games_reset([0], keys=[0])
+    root, seen = (0,), []
+    for ply in range(n_ply):
+        vis, pri, real = eng.search([0], [root])
+        seen.append((root, vis[0].copy(), pri[0].copy(), bool(real[0])))
+        if ply % 3 == 1:   # a cell the search never looked at: the highest empty one
+            a = max(c for c in range(A) if c not in root[1:] and vis[0][c] == 0)
+        else:
+            a = int(np.argmax(vis[0]))
+        root = root + (a,)
+        order = np.argsort(-vis[0].astype(np.int64), kind="stable")
+        reply = int(order[1]) if int(order[1]) not in root[1:] else int(order[2])
+        root = root + (reply,)                     # the opponent's reply: a visited cell, so the subtree is reused
+        if O.check_win(O.get_board(root, B), 5):
+            break
+    pol, val = eng.nn_log(0, n_ply * (sims + 2))
+    it = iter(range(len(val)))
+    agent = O.OracleZeroAgent(B, sims, lambda mv: (lambda k: (pol[k], val[k]))(next(it)), O.DecisionStream(seed, 0, tape), noise=True)
+    n_reused_unvisited = 0
+    for ply, (r, vis, pri, real) in enumerate(seen):
+        agent.get_pi(r, 1)
+        assert np.array_equal(vis, agent.visit.astype(np.uint32)), ply
+        assert np.array_equal(pri, agent.policy), ply
+        assert real == agent.is_real_root, ply
+        n_reused_unvisited += (not real) and int(vis.sum()) == sims - 1
+    assert next(it, None) is None      # every logged evaluation was consumed: same number of network calls
+    assert len(seen) >= 4
+    eng.close()
