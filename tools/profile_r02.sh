@@ -13,3 +13,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 90 --csv --l
 ncu --set full --clock-control none --import-source on -k regex:rollout_search -c 1 -f -o $O/r02_rollout_search python tools/perf_leg.py rollout > $O/r02_ncu_rollout.log 2>&1
 for leg in selfplay9 selfplay15 trained9 arena rollout; do python tools/perf_leg.py $leg 400; done > $O/r02_perf_legs.log 2>&1
 tail -8 $O/r02_perf_legs.log
+# ---- second session of round 2: the cluster-of-four kernel (single game), probes
+ncu --set full --clock-control none --import-source on -k regex:tower_solo -s 3 -c 1 -f -o $O/r3_tower_solo9 python tools/perf_single_game.py 400 > $O/r3_ncu_solo.log 2>&1
+python tools/probe_single_phases.py 400 > $O/r3_phases.log 2>&1; AO_NO_SOLO=1 python tools/probe_single_phases.py 400 >> $O/r3_phases.log 2>&1
+python tools/probe_mma_small_n.py > $O/r3_mma_small_n.log 2>&1; python tools/probe_mma_small_n.py sw128 >> $O/r3_mma_small_n.log 2>&1
+bash tools/sm_limit_experiment.sh > $O/r3_sm_limit.log 2>&1
+python tools/profile_train_step.py graph > $O/r3_train_profile.log 2>&1; python tools/perf_train_step.py >> $O/r3_train_profile.log 2>&1
+for a in "400" "40" "400 9 trained" "40 9 trained" "400 15"; do python tools/perf_single_game.py $a | tail -1; done > $O/r3_single_game.log 2>&1
