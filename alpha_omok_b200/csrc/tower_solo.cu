@@ -155,6 +155,17 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
       : "memory");
 }
 __device__ __forceinline__ void solo_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Waits that span the leader's heads + tree step (~10 us): back off between probes so that a dozen polling warps do not
+// take issue slots from the ONE warp the whole cluster is waiting for.
+__device__ __forceinline__ void solo_wait_sleep_cluster(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    __nanosleep(ns);
+    if ((++spins & 0xFFu) == 0u && globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
 
 // One cluster of four CTAs per game slot [0, n_games): `rounds` simulations (network evaluation of the pending request
 // + tree step) in one launch.  Needs P.static_slots (request of game g in P.nn_in[g]) and every running game waiting
@@ -268,7 +279,7 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
           const uint8_t* base = reinterpret_cast<const uint8_t*>(X3 ? W.conv_quad_x3 : W.conv_quad) + off + (size_t)rank * 9u * tapb;
           for (int g = 0; g < 3; ++g, ++gc) {
             const uint32_t slot = gc % (uint32_t)RG, ph = (gc / (uint32_t)RG) & 1u;
-            mbar_wait(&bar_empty[slot], ph ^ 1u);
+            mbar_wait_sleep(&bar_empty[slot], ph ^ 1u, 100);  // a prefetch: never latency-critical
             mbar_arrive_expect_tx(&bar_full[slot], kSoloGroupTaps * tapb);
             bulk_g2s(s_w + slot * G::GroupBytes, base + (size_t)g * kSoloGroupTaps * tapb, kSoloGroupTaps * tapb, &bar_full[slot]);
           }
@@ -298,7 +309,7 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         mbar_wait(bar_tfree, lc & 1u);
         AO_DBG(const long long dbg_i0 = (W.dbg && blockIdx.x == 0 && i == 0) ? clock64() : 0;)
         if (l == 0) {
-          mbar_wait(bar_in, (uint32_t)rd & 1u);
+          mbar_wait_sleep(bar_in, (uint32_t)rd & 1u, 50);  // spans the heads + tree step of the previous round
         } else {
           mbar_wait_cluster(&bar_act[i], act_ph);
           act_ph ^= 1u;
@@ -375,7 +386,7 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
     if (lane == 0) mbar_arrive(bar_tfree);
 
     for (int rd = 0; rd < rounds; ++rd) {
-      if (rd > 0) mbar_wait_cluster(bar_req, (uint32_t)(rd - 1) & 1u);
+      if (rd > 0) solo_wait_sleep_cluster(bar_req, (uint32_t)(rd - 1) & 1u, 50);
       AO_DBG(const long long dbg_t0 = dbg_on ? clock64() : 0; if (dbg_on && rd > 0) atomicAdd(&W.dbg[4], (unsigned long long)(dbg_t0 - dbg_t3));)
       if (tid == 0) {  // arm this round's deliveries of the heads
         mbar_arrive_expect_tx(bar_feat, G::FeatTx);
