@@ -251,7 +251,9 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], kSoloIssuers);
     }
-    for (int i = 0; i < kSoloIssuers; ++i) mbar_init(&bar_act[i], 1);
+    // remote channel groups arrive as st.async bytes (count 1 = the consumer's arming arrive); the CTA's OWN group is
+    // written with plain stores and signalled by its 8 epilogue warps - no trip through the async-store path
+    for (int i = 0; i < kSoloIssuers; ++i) mbar_init(&bar_act[i], i == (int)rank ? kSoloEpiWarps : 1);
     mbar_init(bar_in, kSoloEpiWarps);
     mbar_init(bar_acc, kSoloIssuers * kSoloNC);
     mbar_init(bar_tfree, kSoloEpiWarps);
@@ -299,7 +301,8 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
     constexpr uint32_t kBStep = (2u * (uint32_t)G::BRows * 16u) >> 4;
     uint32_t lc = 0, gc = 0, act_ph = 0;
     constexpr uint32_t kALoOff = (uint32_t)G::ActBytes >> 4;   // X3: the lo operand buffer sits above the hi one
-    if (lane == 0) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the first delivery of CTA i's channels
+    const bool own_group = i == (int)rank;
+    if (lane == 0 && !own_group) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the first delivery of CTA i's channels
     for (int rd = 0; rd < rounds; ++rd)
       for (int l = 0; l < n_layers; ++l, ++lc) {
         const bool to_s = !X3 && (l & 1) == 0;  // stem and conv2: issuer 0 accumulates in S (conv2: onto the block input x)
@@ -313,7 +316,7 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         } else {
           mbar_wait_cluster(&bar_act[i], act_ph);
           act_ph ^= 1u;
-          if (lane == 0) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the next delivery
+          if (lane == 0 && !own_group) mbar_arrive_expect_tx(&bar_act[i], G::ActTx);  // arm the next delivery
         }
         fence_proxy_async_smem();  // rows written through the generic proxy (acquired above) -> my MMAs' operand reads
         tc_fence_after_sync();
@@ -491,8 +494,11 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
             }
             if (valid) {  // rows beyond the board stay zero for ever: no on-board tap of a real row reads them
               const uint32_t off0 = (uint32_t)((int)rank * 4 + half * 2) * chunk_stride + (uint32_t)(G::Halo + R) * 16u;
+              *reinterpret_cast<uint4*>(s_act + off0) = pk[0];
+              *reinterpret_cast<uint4*>(s_act + off0 + chunk_stride) = pk[1];
 #pragma unroll
-              for (int c = 0; c < kSoloNC; ++c) {
+              for (int k = 1; k < kSoloNC; ++k) {  // destinations rotated by rank: no CTA's inbound port is everyone's first
+                const int c = ((int)rank + k) % kSoloNC;
                 st_async_v4(peer_act[c] + off0, pk[0], peer_bar_act[c]);
                 st_async_v4(peer_act[c] + off0 + chunk_stride, pk[1], peer_bar_act[c]);
               }
@@ -508,8 +514,11 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
                     reinterpret_cast<uint32_t*>(&pl[cc])[e] = *reinterpret_cast<const uint32_t*>(&l2);
                   }
                 }
+                *reinterpret_cast<uint4*>(s_act + G::ActBytes + off0) = pl[0];
+                *reinterpret_cast<uint4*>(s_act + G::ActBytes + off0 + chunk_stride) = pl[1];
 #pragma unroll
-                for (int c = 0; c < kSoloNC; ++c) {
+                for (int k = 1; k < kSoloNC; ++k) {
+                  const int c = ((int)rank + k) % kSoloNC;
                   st_async_v4(peer_act[c] + (uint32_t)G::ActBytes + off0, pl[0], peer_bar_act[c]);
                   st_async_v4(peer_act[c] + (uint32_t)G::ActBytes + off0 + chunk_stride, pl[1], peer_bar_act[c]);
                 }
@@ -538,6 +547,11 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
               }
             }
           }
+        }
+        if (!last) {  // my own channel group sits in my buffer (plain stores): tell this CTA's issuer `rank`
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_act[rank]);
         }
         // the issuers may overwrite the accumulators with the next layer (and issuer 0 finds the new block input in S)
         if (!last && stash) tmem_st_wait();
