@@ -322,15 +322,17 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
         tc_fence_after_sync();
         AO_DBG(if (W.dbg && blockIdx.x == 0 && i == 0 && lane == 0) {
           const long long t = clock64();
-          atomicAdd(&W.dbg[7], (unsigned long long)(t - dbg_i0));
+          if (l > 0) atomicAdd(&W.dbg[7], (unsigned long long)(t - dbg_i0));   // layers 1..: delivery of CTA i's channels
           *reinterpret_cast<volatile long long*>(s_tmem + 2) = t;
         })
         const uint32_t acc_col = X3 ? (uint32_t)(kSoloN + i * G::AccCols)
                                     : (i == 0 ? (to_s ? 0u : (uint32_t)kSoloN) : (uint32_t)(kSoloN * (1 + i)));
         for (int g = 0; g < 3; ++g, ++gc) {
           const uint32_t slot = gc % (uint32_t)RG, ph = (gc / (uint32_t)RG) & 1u;
+          AO_DBG(const long long dbg_f0 = (W.dbg && blockIdx.x == 0 && i == 0 && lane == 0) ? clock64() : 0;)
           mbar_wait(&bar_full[slot], ph);
           tc_fence_after_sync();
+          AO_DBG(if (W.dbg && blockIdx.x == 0 && i == 0 && lane == 0) atomicAdd(&g_tree_dbg[11], (unsigned long long)(clock64() - dbg_f0));)
           if (elect_one()) {
 #pragma unroll
             for (int tile = 0; tile < G::NT; ++tile) {
@@ -664,10 +666,11 @@ tower_solo_kernel(TowerWeights W, TreeParams P, int rounds) {
   AO_DBG(if (W.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
     g_tree_dbg_on = 0;
     printf("tree step phases, cycles per round: regs+leaf loads %llu | expand: legal order %llu, prior sum %llu, noise + child block %llu, backup %llu"
-           " | (expand_and_backup total incl. bookkeeping %llu) | selection walk %llu, win check %llu, terminal backup %llu, request %llu, store regs %llu\n",
+           " | (expand_and_backup total incl. bookkeeping %llu) | selection walk %llu, win check %llu, terminal backup %llu, request %llu, store regs %llu"
+           " || issuer 0 waits for weights %llu\n",
            g_tree_dbg[0] / rounds, g_tree_dbg[2] / rounds, g_tree_dbg[3] / rounds, g_tree_dbg[4] / rounds, g_tree_dbg[5] / rounds,
            g_tree_dbg[1] / rounds, g_tree_dbg[6] / rounds, g_tree_dbg[7] / rounds, g_tree_dbg[8] / rounds, g_tree_dbg[9] / rounds,
-           g_tree_dbg[10] / rounds);
+           g_tree_dbg[10] / rounds, g_tree_dbg[11] / rounds);
   })
   tc_fence_before_sync();
   __syncthreads();
